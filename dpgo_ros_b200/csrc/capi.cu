@@ -1,0 +1,458 @@
+// extern "C" surface declared in include/dpgo_b200.h.  Every entry point
+// converts exceptions into negative error codes; nothing here computes on the
+// CPU -- a missing / unusable CUDA device surfaces as DPGO_B200_ERR_CUDA.
+#include <cstring>
+#include <string>
+
+#include "host.hpp"
+
+using namespace dpgo;
+
+struct dpgo_b200_agent_s {
+  Agent *a;
+};
+struct dpgo_b200_team_s {
+  Team *t;
+};
+
+static thread_local std::string g_last_error;
+
+#define API_BEGIN try {
+#define API_END                                    \
+  }                                                \
+  catch (const Error &e) {                         \
+    g_last_error = e.msg;                          \
+    return e.code;                                 \
+  }                                                \
+  catch (const std::exception &e) {                \
+    g_last_error = e.what();                       \
+    return DPGO_B200_ERR_INVALID;                  \
+  }                                                \
+  return DPGO_B200_OK;
+
+static Agent *A(dpgo_b200_agent_t h) {
+  if (!h || !h->a) fail(DPGO_B200_ERR_INVALID, "null agent handle");
+  return h->a;
+}
+static Team *TT(dpgo_b200_team_t h) {
+  if (!h || !h->t) fail(DPGO_B200_ERR_INVALID, "null team handle");
+  return h->t;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *dpgo_b200_version(void) { return "dpgo_b200 0.1 (sm_100a)"; }
+const char *dpgo_b200_last_error(void) { return g_last_error.c_str(); }
+int dpgo_b200_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+long long dpgo_b200_kernel_launch_count(void) { return kernel_launch_count() + dense_inverse_launch_count(); }
+
+int dpgo_b200_agent_create(int id, const dpgo_b200_params *params, int device, dpgo_b200_agent_t *out) {
+  API_BEGIN
+  if (!params || !out) fail(DPGO_B200_ERR_INVALID, "null argument");
+  Agent *a = new Agent(id, *params, device);
+  *out = new dpgo_b200_agent_s{a};
+  API_END
+}
+int dpgo_b200_agent_destroy(dpgo_b200_agent_t h) {
+  API_BEGIN
+  if (h) {
+    delete h->a;
+    delete h;
+  }
+  API_END
+}
+int dpgo_b200_reset(dpgo_b200_agent_t h) {
+  API_BEGIN
+  A(h)->reset();
+  API_END
+}
+
+int dpgo_b200_add_measurements(dpgo_b200_agent_t h, int m, const int *r1, const int *p1, const int *r2,
+                               const int *p2, const double *R, const double *t, const double *kappa,
+                               const double *tau, const double *weight, const unsigned char *fixed) {
+  API_BEGIN
+  Agent *a = A(h);
+  for (int e = 0; e < m; ++e) {
+    Meas ms;
+    ms.r1 = r1[e]; ms.p1 = p1[e]; ms.r2 = r2[e]; ms.p2 = p2[e];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) ms.R[j * 3 + i] = R[(size_t)e * 9 + i * 3 + j];
+    for (int i = 0; i < 3; ++i) ms.t[i] = t[(size_t)e * 3 + i];
+    ms.kappa = kappa[e];
+    ms.tau = tau[e];
+    ms.weight = weight ? weight[e] : 1.0;
+    ms.fixed = fixed ? fixed[e] != 0 : false;
+    a->add_measurement(ms);
+  }
+  API_END
+}
+int dpgo_b200_num_poses(dpgo_b200_agent_t h) { return h && h->a ? h->a->n : DPGO_B200_ERR_INVALID; }
+int dpgo_b200_iteration_number(dpgo_b200_agent_t h) { return h && h->a ? h->a->iter : DPGO_B200_ERR_INVALID; }
+int dpgo_b200_num_neighbors(dpgo_b200_agent_t h) {
+  return h && h->a ? (int)h->a->nbrs.size() : DPGO_B200_ERR_INVALID;
+}
+int dpgo_b200_get_neighbors(dpgo_b200_agent_t h, int *ids, int cap) {
+  API_BEGIN
+  int k = 0;
+  for (int b : A(h)->nbrs) {
+    if (k >= cap) fail(DPGO_B200_ERR_INVALID, "buffer too small");
+    ids[k++] = b;
+  }
+  API_END
+}
+int dpgo_b200_measurement_counts(dpgo_b200_agent_t h, int *o, int *p, int *s) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (o) *o = (int)a->odom.size();
+  if (p) *p = (int)a->plc.size();
+  if (s) *s = (int)a->slc.size();
+  API_END
+}
+
+int dpgo_b200_set_lifting_matrix(dpgo_b200_agent_t h, const double *Y) {
+  API_BEGIN
+  A(h)->set_lifting_matrix(Y);
+  API_END
+}
+int dpgo_b200_get_lifting_matrix(dpgo_b200_agent_t h, double *Y) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (!a->have_lift) fail(DPGO_B200_ERR_STATE, "lifting matrix not set");
+  std::memcpy(Y, a->ylift, sizeof(double) * a->r * 3);
+  API_END
+}
+int dpgo_b200_initialize(dpgo_b200_agent_t h, const double *T) {
+  API_BEGIN
+  A(h)->initialize(T);
+  API_END
+}
+int dpgo_b200_initialize_in_global_frame(dpgo_b200_agent_t h, const double *Tw) {
+  API_BEGIN
+  A(h)->initialize_in_global_frame(Tw);
+  API_END
+}
+
+int dpgo_b200_iterate(dpgo_b200_agent_t h, int do_opt) {
+  API_BEGIN
+  A(h)->iterate(do_opt != 0);
+  API_END
+}
+int dpgo_b200_get_opt_result(dpgo_b200_agent_t h, dpgo_b200_opt_result *out) {
+  API_BEGIN
+  *out = A(h)->opt;
+  API_END
+}
+int dpgo_b200_get_status(dpgo_b200_agent_t h, dpgo_b200_status *out) {
+  API_BEGIN
+  *out = A(h)->get_status();
+  API_END
+}
+int dpgo_b200_set_neighbor_status(dpgo_b200_agent_t h, const dpgo_b200_status *s) {
+  API_BEGIN
+  A(h)->team_status[s->agent_id] = *s;
+  API_END
+}
+int dpgo_b200_should_terminate(dpgo_b200_agent_t h) {
+  try {
+    return A(h)->should_terminate() ? 1 : 0;
+  } catch (const Error &e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+int dpgo_b200_should_update_measurement_weights(dpgo_b200_agent_t h) {
+  try {
+    return A(h)->should_update_weights() ? 1 : 0;
+  } catch (const Error &e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+
+int dpgo_b200_get_x(dpgo_b200_agent_t h, int which, double *out) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "getX: agent not initialized");
+  cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+  const DevBuf<double> &b = which == 0 ? a->dX : (which == 1 ? a->dY : a->dV);
+  cuda_check(cudaMemcpy(out, b.p, sizeof(double) * a->r * 4 * a->n, cudaMemcpyDeviceToHost), "D2H X");
+  API_END
+}
+int dpgo_b200_set_x(dpgo_b200_agent_t h, const double *X) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "setX: agent not initialized");
+  cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+  const size_t bytes = sizeof(double) * a->r * 4 * a->n;
+  cuda_check(cudaMemcpy(a->dX.p, X, bytes, cudaMemcpyHostToDevice), "H2D X");
+  if (a->P.acceleration) {
+    cuda_check(cudaMemcpy(a->dV.p, X, bytes, cudaMemcpyHostToDevice), "H2D V");
+    cuda_check(cudaMemcpy(a->dY.p, X, bytes, cudaMemcpyHostToDevice), "H2D Y");
+    a->team->ctl.gamma = a->team->ctl.alpha = 0;
+  }
+  a->outbox_stale = true;
+  API_END
+}
+
+int dpgo_b200_num_shared_poses(dpgo_b200_agent_t h, int nbr) {
+  try {
+    return (int)A(h)->my_public_frames(nbr).size();
+  } catch (const Error &e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+int dpgo_b200_get_shared_pose_dict(dpgo_b200_agent_t h, int nbr, int aux, int *frames, double *poses, int cap,
+                                   int *count) {
+  API_BEGIN
+  *count = A(h)->get_shared_pose_dict(nbr, aux != 0, frames, poses, cap);
+  API_END
+}
+int dpgo_b200_update_neighbor_poses(dpgo_b200_agent_t h, int nbr, int aux, const int *frames, const double *poses,
+                                    int count) {
+  API_BEGIN
+  A(h)->update_neighbor_poses(nbr, aux != 0, frames, poses, count);
+  API_END
+}
+int dpgo_b200_outbox_device_ptr(dpgo_b200_agent_t h, int nbr, int aux, void **ptr, size_t *bytes) {
+  API_BEGIN
+  Agent *a = A(h);
+  a->team->prepare();
+  auto it = a->outbox_range.find(nbr);
+  if (it == a->outbox_range.end()) fail(DPGO_B200_ERR_MISSING, "not a neighbour");
+  *ptr = (aux ? a->d_outbox_aux.p : a->d_outbox_reg.p) + (size_t)it->second.first * 4 * a->r;
+  *bytes = (size_t)it->second.second * 4 * a->r * sizeof(double);
+  API_END
+}
+int dpgo_b200_inbox_device_ptr(dpgo_b200_agent_t h, int nbr, int aux, void **ptr, size_t *bytes) {
+  API_BEGIN
+  Agent *a = A(h);
+  a->team->prepare();
+  int first = -1, cnt = 0;
+  for (size_t s = 0; s < a->slot_key.size(); ++s)
+    if (a->slot_key[s].first == nbr) {
+      if (first < 0) first = (int)s;
+      ++cnt;
+    }
+  if (first < 0) fail(DPGO_B200_ERR_MISSING, "not a neighbour");
+  *ptr = (aux ? a->d_inbox_aux.p : a->d_inbox_reg.p) + (size_t)first * 4 * a->r;
+  *bytes = (size_t)cnt * 4 * a->r * sizeof(double);
+  API_END
+}
+int dpgo_b200_mark_inbox_updated(dpgo_b200_agent_t h, int nbr, int aux) {
+  API_BEGIN
+  Agent *a = A(h);
+  auto &v = aux ? a->inbox_valid_aux : a->inbox_valid_reg;
+  for (size_t s = 0; s < a->slot_key.size(); ++s)
+    if (a->slot_key[s].first == nbr) v[s] = 1;
+  API_END
+}
+
+int dpgo_b200_update_measurement_weights(dpgo_b200_agent_t h) {
+  API_BEGIN
+  A(h)->update_measurement_weights();
+  API_END
+}
+int dpgo_b200_set_measurement_weight(dpgo_b200_agent_t h, int r1, int p1, int r2, int p2, double w, int fixed) {
+  API_BEGIN
+  Agent *a = A(h);
+  Meas *m = a->find_measurement(r1, p1, r2, p2);
+  if (!m) fail(DPGO_B200_ERR_MISSING, "setMeasurementWeight: no such measurement");
+  m->weight = w;
+  m->fixed = fixed != 0;
+  API_END
+}
+int dpgo_b200_compute_measurement_residual(dpgo_b200_agent_t h, int r1, int p1, int r2, int p2, double *res) {
+  API_BEGIN
+  Agent *a = A(h);
+  Meas *m = a->find_measurement(r1, p1, r2, p2);
+  if (!m) fail(DPGO_B200_ERR_MISSING, "computeMeasurementResidual: no such measurement");
+  if (!a->compute_residual(*m, res)) fail(DPGO_B200_ERR_MISSING, "computeMeasurementResidual: pose unavailable");
+  API_END
+}
+double dpgo_b200_robust_weight(dpgo_b200_agent_t h, double residual) {
+  return h && h->a ? h->a->robust_weight(residual) : -1.0;
+}
+int dpgo_b200_clear_data_matrices(dpgo_b200_agent_t h) {
+  API_BEGIN
+  Agent *a = A(h);
+  a->values_dirty = a->precon_dirty = true;
+  if (a->team) a->team->team_dirty = true;
+  API_END
+}
+int dpgo_b200_get_lc_weights(dpgo_b200_agent_t h, double *out, int cap) {
+  try {
+    Agent *a = A(h);
+    int k = 0;
+    for (auto &m : a->plc)
+      if (k < cap) out[k++] = m.weight;
+    for (auto &m : a->slc)
+      if (k < cap) out[k++] = m.weight;
+    return k;
+  } catch (const Error &e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+int dpgo_b200_weight_update_count(dpgo_b200_agent_t h) {
+  return h && h->a ? h->a->weight_update_count : DPGO_B200_ERR_INVALID;
+}
+
+// ---- parity hooks -----------------------------------------------------------------
+int dpgo_b200_eval(dpgo_b200_agent_t h, const double *X, double *f, double *egrad, double *rgrad) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "eval: agent not initialized");
+  a->team->prepare();
+  if (!a->all_inbox_valid(false)) fail(DPGO_B200_ERR_MISSING, "eval: neighbour poses missing");
+  const size_t cnt = (size_t)a->r * 4 * a->n;
+  const int grid = a->team->grid;
+  DevBuf<double> dX, dE, dR, dP;
+  dX.upload(std::vector<double>(X, X + cnt));
+  dE.alloc(cnt);
+  dR.alloc(cnt);
+  dP.alloc((size_t)grid * 2);
+  const AgentDev view = a->team->T.ag[a->local_index];
+  cuda_check(launch_eval(view, dX.p, a->d_inbox_reg.p, dE.p, dR.p, dP.p, grid, 0), "k_eval");
+  std::vector<double> part((size_t)grid * 2);
+  cuda_check(cudaMemcpy(part.data(), dP.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H partials");
+  if (f) {
+    double s = 0;
+    for (int b = 0; b < grid; ++b) s += part[(size_t)b * 2];
+    *f = s;
+  }
+  if (egrad) cuda_check(cudaMemcpy(egrad, dE.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H egrad");
+  if (rgrad) cuda_check(cudaMemcpy(rgrad, dR.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H rgrad");
+  API_END
+}
+
+int dpgo_b200_hess(dpgo_b200_agent_t h, const double *X, const double *V, double *out) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "hess: agent not initialized");
+  a->team->prepare();
+  if (!a->all_inbox_valid(false)) fail(DPGO_B200_ERR_MISSING, "hess: neighbour poses missing");
+  const size_t cnt = (size_t)a->r * 4 * a->n;
+  const int grid = a->team->grid;
+  DevBuf<double> dX, dV, dE, dR, dP, dH;
+  dX.upload(std::vector<double>(X, X + cnt));
+  dV.upload(std::vector<double>(V, V + cnt));
+  dE.alloc(cnt);
+  dR.alloc(cnt);
+  dH.alloc(cnt);
+  dP.alloc((size_t)grid * 2);
+  const AgentDev view = a->team->T.ag[a->local_index];
+  cuda_check(launch_eval(view, dX.p, a->d_inbox_reg.p, dE.p, dR.p, dP.p, grid, 0), "k_eval");
+  cuda_check(launch_hess(view, dX.p, dV.p, dH.p, grid, 0), "k_hess");
+  cuda_check(cudaMemcpy(out, dH.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H hess");
+  API_END
+}
+
+int dpgo_b200_precond(dpgo_b200_agent_t h, const double *X, const double *V, double *out) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "precond: agent not initialized");
+  if (!a->need_preconditioner()) fail(DPGO_B200_ERR_STATE, "precond: preconditioner disabled by the parameters");
+  a->team->prepare();
+  const size_t cnt = (size_t)a->r * 4 * a->n;
+  const int grid = a->team->grid;
+  DevBuf<double> dX, dV, dVT, dZ;
+  dX.upload(std::vector<double>(X, X + cnt));
+  dV.upload(std::vector<double>(V, V + cnt));
+  dVT.alloc(cnt);
+  dZ.alloc(cnt);
+  const AgentDev view = a->team->T.ag[a->local_index];
+  cuda_check(launch_transpose_rows(dV.p, dVT.p, a->r, 4 * a->n, 0), "k_transpose_rows");
+  cuda_check(launch_precond(view, dX.p, dV.p, dVT.p, dZ.p, grid, 0), "k_precond");
+  cuda_check(cudaMemcpy(out, dZ.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H precond");
+  API_END
+}
+
+static int manifold_op(int device, int op, int r, int n, const double *Ain, const double *Bin, double *out) {
+  API_BEGIN
+  if (r < 3 || r > 8 || n < 0) fail(DPGO_B200_ERR_INVALID, "manifold op: bad shape");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    fail(DPGO_B200_ERR_CUDA, "no usable CUDA device (the RBCD path has no CPU fallback)");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  if (n == 0) return DPGO_B200_OK;
+  const size_t cnt = (size_t)r * 4 * n;
+  DevBuf<double> dA, dB, dO;
+  dA.upload(std::vector<double>(Ain, Ain + cnt));
+  if (Bin) dB.upload(std::vector<double>(Bin, Bin + cnt));
+  dO.alloc(cnt);
+  const int grid = std::min(max_coop_grid(device), (n + 31) / 32);
+  cuda_check(launch_manifold_op(op, r, n, dA.p, dB.p, dO.p, std::max(1, grid), 0), "k_manifold_op");
+  cuda_check(cudaMemcpy(out, dO.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H manifold op");
+  API_END
+}
+int dpgo_b200_manifold_project(int device, int r, int n, const double *M, double *out) {
+  return manifold_op(device, 0, r, n, M, nullptr, out);
+}
+int dpgo_b200_tangent_project(int device, int r, int n, const double *X, const double *Z, double *out) {
+  return manifold_op(device, 1, r, n, X, Z, out);
+}
+int dpgo_b200_retract(int device, int r, int n, const double *X, const double *xi, double *out) {
+  return manifold_op(device, 2, r, n, X, xi, out);
+}
+
+// ---- team ---------------------------------------------------------------------------
+int dpgo_b200_team_create(int device, dpgo_b200_team_t *out) {
+  API_BEGIN
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    fail(DPGO_B200_ERR_CUDA, "no usable CUDA device (the RBCD path has no CPU fallback)");
+  *out = new dpgo_b200_team_s{new Team(device)};
+  API_END
+}
+int dpgo_b200_team_destroy(dpgo_b200_team_t h) {
+  API_BEGIN
+  if (h) {
+    delete h->t;
+    delete h;
+  }
+  API_END
+}
+int dpgo_b200_team_add_agent(dpgo_b200_team_t h, dpgo_b200_agent_t a) {
+  API_BEGIN
+  TT(h)->add(A(a));
+  API_END
+}
+int dpgo_b200_team_exchange_all(dpgo_b200_team_t h) {
+  API_BEGIN
+  TT(h)->exchange_all();
+  API_END
+}
+int dpgo_b200_team_run(dpgo_b200_team_t h, int max_iters, int stop_on_terminate, dpgo_b200_run_result *out) {
+  API_BEGIN
+  dpgo_b200_run_result r = TT(h)->run(max_iters, stop_on_terminate != 0);
+  if (out) *out = r;
+  API_END
+}
+double dpgo_b200_team_global_cost(dpgo_b200_team_t h, int *status) {
+  try {
+    const double c = TT(h)->global_cost();
+    if (status) *status = 0;
+    return c;
+  } catch (const Error &e) {
+    g_last_error = e.msg;
+    if (status) *status = e.code;
+    return 0.0;
+  }
+}
+int dpgo_b200_team_set_grid(dpgo_b200_team_t h, int num_ctas) {
+  API_BEGIN
+  Team *t = TT(h);
+  const int mx = max_coop_grid(t->device);
+  t->grid = (num_ctas <= 0 || num_ctas > mx) ? mx : num_ctas;
+  t->team_dirty = true;
+  API_END
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,344 @@
+// Device-side data layout and primitives of the B200 RBCD path (sm_100a).
+//
+// Layout in HBM (all FP64): every lifted variable (X, Y, V, gradients, tCG
+// vectors) is r x 4n column-major -- pose i owns 4r contiguous doubles
+// [Y_i(:,0) Y_i(:,1) Y_i(:,2) p_i].  One 8-lane group works on one pose with
+// lane a holding row a of the r x 4 block (r <= 8), so a pose is one coalesced
+// 4r*8-byte segment and every per-pose 3x3 Gram matrix is three xor-shuffles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpgo {
+
+constexpr int kMaxLocal = 8;     // co-located agents per team / device
+constexpr int kMaxRobots = 64;   // robots in the whole problem
+constexpr int kThreads = 256;    // CTA size of every kernel here
+constexpr int kGroupsPerCta = kThreads / 8;
+constexpr int kRed = 4;          // doubles per grid reduction
+
+struct AgentStat {
+  double relchange, f_init, f_opt, gn_init, gn_opt;
+  int ready, optimized, tcg_iters, rtr_outer, rtr_rej, pad;
+};
+
+struct AgentDev {
+  int id, n, r, n_in;
+  // state
+  double *X, *Y, *V, *Xinit;
+  // Q as block-CSR by OUTPUT pose j: out_j += X_{col} * val (4x4 col-major)
+  const int *q_rowptr, *q_col;
+  const double *q_val;
+  // linear term by output pose: G_j += inbox[slot] * val
+  const int *s_rowptr, *s_slot;
+  const double *s_val;
+  // neighbour public poses (regular and auxiliary), r x 4 per slot
+  double *inbox_reg, *inbox_aux;
+  // publication lists, CSR by my pose: destinations of X (reg) and Y (aux)
+  const int *pub_rowptr;
+  double *const *pub_dst_reg;
+  double *const *pub_dst_aux;
+  // dense preconditioner (Q + lambda I)^-1, 4n x 4n, symmetric
+  const double *Pinv;
+  // work vectors (r x 4n) and their row-major "T" copies ([r][4n]) for the dense phase
+  double *G, *Rg, *RgT, *Z, *eta, *dlt0, *dlt1, *Hd, *rv, *rvT, *X2, *X3, *Rg2, *Rg2T, *zeta;
+  double *S, *S2;  // per pose sym(Y^T egrad_Y): 6 doubles
+  AgentStat *stat;
+};
+
+struct SolverParams {
+  int method;  // 0 RTR, 1 RGD
+  double rgd_stepsize;
+  int rgd_use_precond;
+  int rtr_iterations, rtr_tcg_iterations;
+  double rtr_initial_radius, gradnorm_tol;
+  int acceleration, restart_interval;
+  int robust;  // cost type != L2
+  int robust_num_weight_updates, robust_inner_iters;
+  int max_num_iters;
+  double rel_change_tol;
+};
+
+// control state carried across launches (uniform across the grid)
+struct TeamCtl {
+  int iter;       // global iteration number (== every agent's iteration_number)
+  int selected;   // robot id that holds the UPDATE token
+  double gamma, alpha;
+  unsigned long long ready_mask;
+  int weight_update_count, robust_inner_iter;
+  int stop_reason;  // 0 ran out of max_iters, 1 terminate, 2 weight update requested
+  int iters_done;
+};
+
+struct GridSync {
+  unsigned *count;
+  unsigned *gen;
+  double *slots;  // [2][gridDim.x][kRed]
+};
+
+struct TeamDev {
+  int num_local, num_robots;
+  int local_of_robot[kMaxRobots];
+  int pose_prefix[kMaxLocal + 1];
+  AgentDev ag[kMaxLocal];
+  SolverParams p;
+  GridSync gs;
+  TeamCtl *ctl;
+};
+
+// ---------------------------------------------------------------------------
+// 8-lane group primitives (all 32 lanes of the warp must call these)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double gsum8(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ double wsum32(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// load / store row `a` of an r x 4 column-major pose block
+__device__ __forceinline__ void ld4(const double *P, int r, int a, bool act, double (&x)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) x[c] = act ? P[c * r + a] : 0.0;
+}
+__device__ __forceinline__ void st4(double *P, int r, int a, bool act, const double (&x)[4]) {
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) P[c * r + a] = x[c];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 3x3 symmetric helpers.  Symmetric storage order: 00 01 02 11 12 22.
+// ---------------------------------------------------------------------------
+struct Sym3 {
+  double a00, a01, a02, a11, a12, a22;
+};
+
+__device__ __forceinline__ Sym3 sym3_mul_sym_commuting(const Sym3 &A, const Sym3 &B) {
+  // product of two commuting symmetric matrices (result symmetric)
+  Sym3 C;
+  C.a00 = A.a00 * B.a00 + A.a01 * B.a01 + A.a02 * B.a02;
+  C.a01 = A.a00 * B.a01 + A.a01 * B.a11 + A.a02 * B.a12;
+  C.a02 = A.a00 * B.a02 + A.a01 * B.a12 + A.a02 * B.a22;
+  C.a11 = A.a01 * B.a01 + A.a11 * B.a11 + A.a12 * B.a12;
+  C.a12 = A.a01 * B.a02 + A.a11 * B.a12 + A.a12 * B.a22;
+  C.a22 = A.a02 * B.a02 + A.a12 * B.a12 + A.a22 * B.a22;
+  return C;
+}
+
+// Jacobi eigen-decomposition based A^{-1/2} (robust path, any SPD A)
+static __device__ __noinline__ Sym3 sym3_invsqrt_jacobi(Sym3 A) {
+  double w00 = 1, w01 = 0, w02 = 0, w10 = 0, w11 = 1, w12 = 0, w20 = 0, w21 = 0, w22 = 1;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    bool rotated = false;
+    // (0,1)
+    if (fabs(A.a01) > 1e-17 * sqrt(fabs(A.a00 * A.a11))) {
+      rotated = true;
+      double th = (A.a11 - A.a00) / (2.0 * A.a01);
+      double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      double c = rsqrt(t * t + 1.0), s = t * c;
+      double a00 = A.a00 - t * A.a01, a11 = A.a11 + t * A.a01;
+      double a02 = c * A.a02 - s * A.a12, a12 = s * A.a02 + c * A.a12;
+      A.a00 = a00; A.a11 = a11; A.a01 = 0; A.a02 = a02; A.a12 = a12;
+      double t0, t1;
+      t0 = c * w00 - s * w01; t1 = s * w00 + c * w01; w00 = t0; w01 = t1;
+      t0 = c * w10 - s * w11; t1 = s * w10 + c * w11; w10 = t0; w11 = t1;
+      t0 = c * w20 - s * w21; t1 = s * w20 + c * w21; w20 = t0; w21 = t1;
+    }
+    // (0,2)
+    if (fabs(A.a02) > 1e-17 * sqrt(fabs(A.a00 * A.a22))) {
+      rotated = true;
+      double th = (A.a22 - A.a00) / (2.0 * A.a02);
+      double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      double c = rsqrt(t * t + 1.0), s = t * c;
+      double a00 = A.a00 - t * A.a02, a22 = A.a22 + t * A.a02;
+      double a01 = c * A.a01 - s * A.a12, a12 = s * A.a01 + c * A.a12;
+      A.a00 = a00; A.a22 = a22; A.a02 = 0; A.a01 = a01; A.a12 = a12;
+      double t0, t1;
+      t0 = c * w00 - s * w02; t1 = s * w00 + c * w02; w00 = t0; w02 = t1;
+      t0 = c * w10 - s * w12; t1 = s * w10 + c * w12; w10 = t0; w12 = t1;
+      t0 = c * w20 - s * w22; t1 = s * w20 + c * w22; w20 = t0; w22 = t1;
+    }
+    // (1,2)
+    if (fabs(A.a12) > 1e-17 * sqrt(fabs(A.a11 * A.a22))) {
+      rotated = true;
+      double th = (A.a22 - A.a11) / (2.0 * A.a12);
+      double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      double c = rsqrt(t * t + 1.0), s = t * c;
+      double a11 = A.a11 - t * A.a12, a22 = A.a22 + t * A.a12;
+      double a01 = c * A.a01 - s * A.a02, a02 = s * A.a01 + c * A.a02;
+      A.a11 = a11; A.a22 = a22; A.a12 = 0; A.a01 = a01; A.a02 = a02;
+      double t0, t1;
+      t0 = c * w01 - s * w02; t1 = s * w01 + c * w02; w01 = t0; w02 = t1;
+      t0 = c * w11 - s * w12; t1 = s * w11 + c * w12; w11 = t0; w12 = t1;
+      t0 = c * w21 - s * w22; t1 = s * w21 + c * w22; w21 = t0; w22 = t1;
+    }
+    if (!rotated) break;
+  }
+  const double d0 = 1.0 / sqrt(A.a00), d1 = 1.0 / sqrt(A.a11), d2 = 1.0 / sqrt(A.a22);
+  Sym3 B;
+  B.a00 = w00 * w00 * d0 + w01 * w01 * d1 + w02 * w02 * d2;
+  B.a01 = w00 * w10 * d0 + w01 * w11 * d1 + w02 * w12 * d2;
+  B.a02 = w00 * w20 * d0 + w01 * w21 * d1 + w02 * w22 * d2;
+  B.a11 = w10 * w10 * d0 + w11 * w11 * d1 + w12 * w12 * d2;
+  B.a12 = w10 * w20 * d0 + w11 * w21 * d1 + w12 * w22 * d2;
+  B.a22 = w20 * w20 * d0 + w21 * w21 * d1 + w22 * w22 * d2;
+  return B;
+}
+
+// A^{-1/2} for SPD A.  Near the identity (the hot-path case: A = M^T M with M a
+// convex combination of nearby Stiefel points) use the coupled Newton-Schulz
+// iteration -- multiply-add only, quadratic convergence, all iterates are
+// polynomials in A so they commute and stay symmetric.  Otherwise Jacobi.
+__device__ __forceinline__ Sym3 sym3_invsqrt(const Sym3 &A) {
+  const double e00 = 1.0 - A.a00, e11 = 1.0 - A.a11, e22 = 1.0 - A.a22;
+  const double en = e00 * e00 + e11 * e11 + e22 * e22 + 2.0 * (A.a01 * A.a01 + A.a02 * A.a02 + A.a12 * A.a12);
+  if (!(en < 0.04)) return sym3_invsqrt_jacobi(A);
+  Sym3 Yk = A;
+  Sym3 Zk = {1, 0, 0, 1, 0, 1};
+  for (int it = 0; it < 8; ++it) {
+    Sym3 ZY = sym3_mul_sym_commuting(Zk, Yk);
+    Sym3 T = {0.5 * (3.0 - ZY.a00), -0.5 * ZY.a01, -0.5 * ZY.a02, 0.5 * (3.0 - ZY.a11), -0.5 * ZY.a12,
+              0.5 * (3.0 - ZY.a22)};
+    const double r00 = 1.0 - ZY.a00, r11 = 1.0 - ZY.a11, r22 = 1.0 - ZY.a22;
+    const double rn = r00 * r00 + r11 * r11 + r22 * r22 + 2.0 * (ZY.a01 * ZY.a01 + ZY.a02 * ZY.a02 + ZY.a12 * ZY.a12);
+    Yk = sym3_mul_sym_commuting(Yk, T);
+    Zk = sym3_mul_sym_commuting(T, Zk);
+    if (rn < 1e-20) break;  // residual before this step < 1e-10 => after it ~1e-20
+  }
+  return Zk;
+}
+
+// Stiefel projection U V^T = M (M^T M)^{-1/2} of the r x 3 block whose row `a`
+// this lane holds in m[0..2].  Group-collective.
+__device__ __forceinline__ void stiefel_project_row(double (&m)[4]) {
+  Sym3 A;
+  A.a00 = gsum8(m[0] * m[0]);
+  A.a01 = gsum8(m[0] * m[1]);
+  A.a02 = gsum8(m[0] * m[2]);
+  A.a11 = gsum8(m[1] * m[1]);
+  A.a12 = gsum8(m[1] * m[2]);
+  A.a22 = gsum8(m[2] * m[2]);
+  const Sym3 B = sym3_invsqrt(A);
+  const double o0 = m[0] * B.a00 + m[1] * B.a01 + m[2] * B.a02;
+  const double o1 = m[0] * B.a01 + m[1] * B.a11 + m[2] * B.a12;
+  const double o2 = m[0] * B.a02 + m[1] * B.a12 + m[2] * B.a22;
+  m[0] = o0; m[1] = o1; m[2] = o2;
+}
+
+// sym(Y^T Z) of the rotation blocks (row a of each in y[], z[]).  Group-collective.
+__device__ __forceinline__ Sym3 sym_ytz(const double (&y)[4], const double (&z)[4]) {
+  Sym3 S;
+  S.a00 = gsum8(y[0] * z[0]);
+  S.a11 = gsum8(y[1] * z[1]);
+  S.a22 = gsum8(y[2] * z[2]);
+  S.a01 = 0.5 * gsum8(y[0] * z[1] + y[1] * z[0]);
+  S.a02 = 0.5 * gsum8(y[0] * z[2] + y[2] * z[0]);
+  S.a12 = 0.5 * gsum8(y[1] * z[2] + y[2] * z[1]);
+  return S;
+}
+// z_Y <- z_Y - y * S   (row-wise); translation column untouched
+__device__ __forceinline__ void sub_y_sym(const double (&y)[4], const Sym3 &S, double (&z)[4]) {
+  const double o0 = y[0] * S.a00 + y[1] * S.a01 + y[2] * S.a02;
+  const double o1 = y[0] * S.a01 + y[1] * S.a11 + y[2] * S.a12;
+  const double o2 = y[0] * S.a02 + y[1] * S.a12 + y[2] * S.a22;
+  z[0] -= o0; z[1] -= o1; z[2] -= o2;
+}
+// tangent projection at y of z (rotation part); group-collective
+__device__ __forceinline__ void tangent_project_row(const double (&y)[4], double (&z)[4]) {
+  const Sym3 S = sym_ytz(y, z);
+  sub_y_sym(y, S, z);
+}
+
+// QF retraction of the rotation block: Q factor of (y + xi) with diag(R) > 0,
+// computed as Cholesky-QR (A^T A = R^T R, Q = A R^{-1}); A^T A = I + xi^T xi is
+// well conditioned on the tangent space so this matches Householder QR to
+// rounding.  Translation: p + xi_p.  In/out: x = y + xi on entry (row a).
+__device__ __forceinline__ void qf_row(double (&x)[4]) {
+  const double g00 = gsum8(x[0] * x[0]);
+  const double g01 = gsum8(x[0] * x[1]);
+  const double g02 = gsum8(x[0] * x[2]);
+  const double g11 = gsum8(x[1] * x[1]);
+  const double g12 = gsum8(x[1] * x[2]);
+  const double g22 = gsum8(x[2] * x[2]);
+  // upper-triangular R with R^T R = G
+  const double i00 = rsqrt(g00);          // 1 / r00
+  const double r01 = g01 * i00, r02 = g02 * i00;
+  const double i11 = rsqrt(g11 - r01 * r01);
+  const double r12 = (g12 - r01 * r02) * i11;
+  const double i22 = rsqrt(g22 - r02 * r02 - r12 * r12);
+  const double q0 = x[0] * i00;
+  const double q1 = (x[1] - q0 * r01) * i11;
+  const double q2 = (x[2] - q0 * r02 - q1 * r12) * i22;
+  x[0] = q0; x[1] = q1; x[2] = q2;
+}
+
+// ---------------------------------------------------------------------------
+// grid-wide barrier + deterministic reduction (persistent cooperative kernel)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(const GridSync &gs) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned *gen = gs.gen;
+    const unsigned g = *gen;
+    __threadfence();
+    if (atomicAdd(gs.count, 1u) == gridDim.x - 1) {
+      *((volatile unsigned *)gs.count) = 0u;
+      __threadfence();
+      atomicAdd(gs.gen, 1u);
+    } else {
+      while (*gen == g) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Sum `vals` over every thread of the grid; every thread gets the same totals,
+// summed in a fixed order (bitwise reproducible run to run).  Includes a grid
+// barrier, so it also orders global memory between phases.  `parity` flips on
+// every call (slot double-buffering).
+template <int K>
+__device__ __forceinline__ void grid_reduce(const GridSync &gs, int &parity, double (&vals)[K], double *sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) vals[k] = wsum32(vals[k]);
+  __syncthreads();  // sm reuse
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sm[warp * K + k] = vals[k];
+  }
+  __syncthreads();
+  double *slots = gs.slots + (size_t)parity * gridDim.x * kRed;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double s = 0;
+      for (int w = 0; w < kThreads / 32; ++w) s += sm[w * K + k];
+      slots[(size_t)blockIdx.x * kRed + k] = s;
+    }
+  }
+  grid_barrier(gs);
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double s = 0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&slots[(size_t)b * kRed + k]);
+      s = wsum32(s);
+      if (lane == 0) sm[k] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) vals[k] = sm[k];
+  parity ^= 1;
+}
+
+}  // namespace dpgo

@@ -1,0 +1,939 @@
+// Host side of the B200 RBCD path (see host.hpp).  No arithmetic of the hot
+// path happens here: this file keeps the pose graph, lays the data out for the
+// kernels, and sequences launches.  There is no CPU fallback.
+#include "host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace dpgo {
+
+[[noreturn]] void fail(int code, const std::string &msg) { throw Error{code, msg}; }
+void cuda_check(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) fail(DPGO_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static inline size_t roundup32(size_t x) { return (x + 31) / 32 * 32; }
+
+// T~ = [R t; 0 1], Omega = w diag(kappa, kappa, kappa, tau)
+static void edge_blocks(const Meas &m, double *T, double *Om) {
+  std::memset(T, 0, 16 * sizeof(double));
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) T[j * 4 + i] = m.R[j * 3 + i];
+  for (int i = 0; i < 3; ++i) T[12 + i] = m.t[i];
+  T[15] = 1.0;
+  Om[0] = Om[1] = Om[2] = m.weight * m.kappa;
+  Om[3] = m.weight * m.tau;
+}
+
+// ============================================================================
+// Agent
+// ============================================================================
+Agent::Agent(int id_, const dpgo_b200_params &p, int device_) : id(id_), P(p), device(device_), r(p.r) {
+  if (p.d != 3) fail(DPGO_B200_ERR_INVALID, "only d = 3 is supported (src/PGOAgentROSNode.cpp:63)");
+  if (p.r < 3 || p.r > 8) fail(DPGO_B200_ERR_INVALID, "relaxation rank r must satisfy 3 <= r <= 8");
+  if (p.num_robots < 1 || p.num_robots > kMaxRobots) fail(DPGO_B200_ERR_INVALID, "num_robots out of range");
+  if (id_ < 0 || id_ >= p.num_robots) fail(DPGO_B200_ERR_INVALID, "agent id out of range");
+  if (p.cost_type != 0 && p.cost_type != 5)
+    fail(DPGO_B200_ERR_INVALID, "only L2 and GNC_TLS robust costs are in scope (SURVEY §2 #4)");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= device_ || device_ < 0)
+    fail(DPGO_B200_ERR_CUDA, "no usable CUDA device (the RBCD path has no CPU fallback)");
+  cuda_check(cudaSetDevice(device_), "cudaSetDevice");
+  mu = p.gnc_init_mu;
+  status.agent_id = id;
+  own.reset(new Team(device_));
+  own->add(this);
+}
+
+Agent::~Agent() {
+  if (team && team != own.get()) team->remove(this);
+  if (own) own->agents.clear();
+  team = nullptr;
+}
+
+void Agent::add_measurement(const Meas &m) {
+  if (m.r1 != id && m.r2 != id) return;  // irrelevant measurement, src/PGOAgentROS.cpp:273
+  auto key = std::make_pair(std::make_pair(m.r1, m.p1), std::make_pair(m.r2, m.p2));
+  if (have.count(key)) return;  // hasMeasurement, :276
+  if (m.r1 < 0 || m.r2 < 0 || m.r1 >= P.num_robots || m.r2 >= P.num_robots || m.p1 < 0 || m.p2 < 0)
+    fail(DPGO_B200_ERR_INVALID, "measurement index out of range");
+  have.insert(key);
+  if (m.r1 == id && m.r2 == id) {
+    if (m.p1 + 1 == m.p2)
+      odom.push_back(m);
+    else
+      plc.push_back(m);
+    n = std::max(n, std::max(m.p1, m.p2) + 1);
+  } else {
+    slc.push_back(m);
+    if (m.r1 == id) {
+      n = std::max(n, m.p1 + 1);
+      nbrs.insert(m.r2);
+    } else {
+      n = std::max(n, m.p2 + 1);
+      nbrs.insert(m.r1);
+    }
+  }
+  structure_dirty = values_dirty = precon_dirty = wiring_dirty = true;
+  if (team) team->team_dirty = true;
+}
+
+Meas *Agent::find_measurement(int r1, int p1, int r2, int p2) {
+  for (auto *vec : {&odom, &plc, &slc})
+    for (auto &m : *vec)
+      if (m.r1 == r1 && m.p1 == p1 && m.r2 == r2 && m.p2 == p2) return &m;
+  return nullptr;
+}
+
+std::vector<int> Agent::my_public_frames(int nbr) const {
+  std::set<int> s;
+  for (const auto &m : slc) {
+    if (m.r1 == id && m.r2 == nbr) s.insert(m.p1);
+    if (m.r2 == id && m.r1 == nbr) s.insert(m.p2);
+  }
+  return std::vector<int>(s.begin(), s.end());
+}
+
+void Agent::set_lifting_matrix(const double *Y) {
+  std::memcpy(ylift, Y, sizeof(double) * r * 3);
+  have_lift = true;
+}
+
+void Agent::initialize(const double *T) {
+  if (n == 0) fail(DPGO_B200_ERR_STATE, "initialize: empty pose graph");
+  Tlocal.assign((size_t)12 * n, 0.0);
+  if (T) {
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 4; ++c) Tlocal[(size_t)i * 12 + c * 3 + a] = T[(size_t)i * 12 + a * 4 + c];
+  } else {
+    // Odometry chain from identity (local_initialization_method Odometry, src/PGOAgentROSNode.cpp:106-108)
+    std::vector<const Meas *> by_src(n, nullptr);
+    for (const auto &m : odom) by_src[m.p1] = &m;
+    for (int c = 0; c < 3; ++c) Tlocal[c * 3 + c] = 1.0;
+    for (int i = 0; i + 1 < n; ++i) {
+      const Meas *m = by_src[i];
+      if (!m) fail(DPGO_B200_ERR_MISSING, "initialize: missing odometry edge");
+      const double *Ti = &Tlocal[(size_t)i * 12];
+      double *Tn = &Tlocal[(size_t)(i + 1) * 12];
+      for (int c = 0; c < 3; ++c)
+        for (int a = 0; a < 3; ++a) {
+          double s = 0;
+          for (int k = 0; k < 3; ++k) s += Ti[k * 3 + a] * m->R[c * 3 + k];
+          Tn[c * 3 + a] = s;
+        }
+      for (int a = 0; a < 3; ++a) {
+        double s = Ti[9 + a];
+        for (int k = 0; k < 3; ++k) s += Ti[k * 3 + a] * m->t[k];
+        Tn[9 + a] = s;
+      }
+    }
+  }
+  state = 1;
+}
+
+void Agent::initialize_in_global_frame(const double *Tw_rm) {
+  if (state == 0) fail(DPGO_B200_ERR_STATE, "initializeInGlobalFrame before initialize");
+  if (!have_lift) fail(DPGO_B200_ERR_STATE, "initializeInGlobalFrame: lifting matrix not set");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  double Tw[12];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 4; ++c) Tw[c * 3 + a] = Tw_rm[a * 4 + c];
+  std::vector<double> X((size_t)r * 4 * n);
+  for (int i = 0; i < n; ++i) {
+    double Tg[12];
+    for (int c = 0; c < 4; ++c)
+      for (int a = 0; a < 3; ++a) {
+        double s = (c == 3) ? Tw[9 + a] : 0.0;
+        for (int k = 0; k < 3; ++k) s += Tw[k * 3 + a] * Tlocal[(size_t)i * 12 + c * 3 + k];
+        Tg[c * 3 + a] = s;
+      }
+    for (int c = 0; c < 4; ++c)
+      for (int a = 0; a < r; ++a) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += ylift[k * r + a] * Tg[c * 3 + k];
+        X[((size_t)i * 4 + c) * r + a] = s;
+      }
+  }
+  dX.upload(X);
+  dXinit.upload(X);
+  dY.upload(X);
+  dV.upload(X);
+  state = 2;
+  status.state = 2;
+  team->ctl.gamma = team->ctl.alpha = 0;
+  team->team_dirty = true;
+  outbox_stale = true;
+}
+
+void Agent::reset() {
+  instance++;
+  iter = 0;
+  state = 0;
+  status = dpgo_b200_status{};
+  status.agent_id = id;
+  status.instance_number = instance;
+  team_status.clear();
+  std::fill(inbox_valid_reg.begin(), inbox_valid_reg.end(), 0);
+  std::fill(inbox_valid_aux.begin(), inbox_valid_aux.end(), 0);
+  weight_update_count = 0;
+  robust_inner_iter = 0;
+  mu = P.gnc_init_mu;
+  opt = dpgo_b200_opt_result{};
+  if (team) {
+    team->ctl = TeamCtl{};
+    team->team_dirty = true;
+  }
+}
+
+// ---- device structures --------------------------------------------------------
+void Agent::build_structure() {
+  // neighbour slots, ordered by (robot, frame)
+  slot_of.clear();
+  slot_key.clear();
+  std::set<std::pair<int, int>> keys;
+  for (const auto &m : slc) keys.insert(m.r1 == id ? std::make_pair(m.r2, m.p2) : std::make_pair(m.r1, m.p1));
+  for (const auto &k : keys) {
+    slot_of[k] = (int)slot_key.size();
+    slot_key.push_back(k);
+  }
+  const int n_in = (int)slot_key.size();
+  inbox_valid_reg.assign(n_in, 0);
+  inbox_valid_aux.assign(n_in, 0);
+  // Q structure by output pose
+  std::vector<std::set<int>> rows(n);
+  for (int j = 0; j < n; ++j) rows[j].insert(j);
+  for (auto *vec : {&odom, &plc})
+    for (const auto &m : *vec) {
+      rows[m.p2].insert(m.p1);
+      rows[m.p1].insert(m.p2);
+    }
+  h_q_rowptr.assign(n + 1, 0);
+  h_q_col.clear();
+  for (int j = 0; j < n; ++j) {
+    for (int i : rows[j]) h_q_col.push_back(i);
+    h_q_rowptr[j + 1] = (int)h_q_col.size();
+  }
+  // shared-edge terms by my pose, in slc order
+  std::vector<std::vector<int>> sl(n);
+  for (size_t e = 0; e < slc.size(); ++e) {
+    const auto &m = slc[e];
+    sl[m.r1 == id ? m.p1 : m.p2].push_back((int)e);
+  }
+  h_s_rowptr.assign(n + 1, 0);
+  h_s_slot.clear();
+  std::vector<int> s_edge;
+  for (int j = 0; j < n; ++j) {
+    for (int e : sl[j]) {
+      const auto &m = slc[e];
+      h_s_slot.push_back(slot_of[m.r1 == id ? std::make_pair(m.r2, m.p2) : std::make_pair(m.r1, m.p1)]);
+      s_edge.push_back(e);
+    }
+    h_s_rowptr[j + 1] = (int)h_s_slot.size();
+  }
+  // publication entries by my pose: (neighbour, frame)
+  std::vector<std::set<int>> pubs(n);
+  for (const auto &m : slc) {
+    if (m.r1 == id)
+      pubs[m.p1].insert(m.r2);
+    else
+      pubs[m.p2].insert(m.r1);
+  }
+  h_pub_rowptr.assign(n + 1, 0);
+  h_pub_entries.clear();
+  for (int j = 0; j < n; ++j) {
+    for (int b : pubs[j]) h_pub_entries.push_back({b, j});
+    h_pub_rowptr[j + 1] = (int)h_pub_entries.size();
+  }
+  outbox_range.clear();
+  outbox_total = 0;
+  for (int b : nbrs) {
+    const int cnt = (int)my_public_frames(b).size();
+    outbox_range[b] = {outbox_total, cnt};
+    outbox_total += cnt;
+  }
+  // loop closures subject to reweighting
+  lc_list.clear();
+  for (auto &m : plc)
+    if (!m.fixed) lc_list.push_back(&m);
+  for (auto &m : slc)
+    if (!m.fixed) lc_list.push_back(&m);
+
+  d_q_rowptr.upload(h_q_rowptr);
+  d_q_col.upload(h_q_col);
+  d_s_rowptr.upload(h_s_rowptr);
+  d_s_slot.upload(h_s_slot);
+  d_pub_rowptr.upload(h_pub_rowptr);
+  const size_t vec = (size_t)r * 4 * n;
+  d_inbox_reg.alloc((size_t)n_in * 4 * r);
+  d_inbox_aux.alloc((size_t)n_in * 4 * r);
+  d_outbox_reg.alloc((size_t)std::max(1, outbox_total) * 4 * r);
+  d_outbox_aux.alloc((size_t)std::max(1, outbox_total) * 4 * r);
+  for (auto *b : {&dG, &dRg, &dRgT, &dZ, &dEta, &dDlt0, &dDlt1, &dHd, &dRv, &dRvT, &dX2, &dX3, &dRg2, &dRg2T, &dZeta})
+    b->alloc(vec);
+  dS.alloc((size_t)6 * n);
+  dS2.alloc((size_t)6 * n);
+  dStat.alloc(1);
+  if (dX.n != vec) {  // not initialised yet: allocate so the views are valid
+    dX.alloc(vec);
+    dY.alloc(vec);
+    dV.alloc(vec);
+    dXinit.alloc(vec);
+  }
+  structure_dirty = false;
+  values_dirty = true;
+  precon_dirty = true;
+  wiring_dirty = true;
+}
+
+void Agent::build_values() {
+  std::vector<double> qv((size_t)h_q_col.size() * 16, 0.0);
+  auto entry = [&](int i, int j) -> double * {
+    auto b = h_q_col.begin() + h_q_rowptr[j], e = h_q_col.begin() + h_q_rowptr[j + 1];
+    auto it = std::lower_bound(b, e, i);
+    return &qv[(size_t)(it - h_q_col.begin()) * 16];
+  };
+  double T[16], Om[4], TOm[16], TOmTt[16];
+  auto prep = [&](const Meas &m) {
+    edge_blocks(m, T, Om);
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 4; ++i) TOm[j * 4 + i] = T[j * 4 + i] * Om[j];
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 4; ++i) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += TOm[k * 4 + i] * T[k * 4 + j];
+        TOmTt[j * 4 + i] = s;
+      }
+  };
+  for (auto *vec : {&odom, &plc})
+    for (const auto &m : *vec) {
+      prep(m);
+      double *ii = entry(m.p1, m.p1), *jj = entry(m.p2, m.p2), *ij = entry(m.p1, m.p2), *ji = entry(m.p2, m.p1);
+      for (int q = 0; q < 16; ++q) ii[q] += TOmTt[q];
+      for (int c = 0; c < 4; ++c) jj[c * 4 + c] += Om[c];
+      for (int q = 0; q < 16; ++q) ij[q] -= TOm[q];                       // Q_ij = -T Om
+      for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) ji[j * 4 + i] -= TOm[i * 4 + j];      // Q_ji = -(T Om)^T
+    }
+  for (const auto &m : slc) {
+    prep(m);
+    if (m.r1 == id) {
+      double *ii = entry(m.p1, m.p1);
+      for (int q = 0; q < 16; ++q) ii[q] += TOmTt[q];
+    } else {
+      double *jj = entry(m.p2, m.p2);
+      for (int c = 0; c < 4; ++c) jj[c * 4 + c] += Om[c];
+    }
+  }
+  d_q_val.upload(qv);
+  // G blocks in the order of h_s_slot (per pose, slc order)
+  std::vector<double> sv((size_t)h_s_slot.size() * 16, 0.0);
+  {
+    std::vector<std::vector<int>> sl(n);
+    for (size_t e = 0; e < slc.size(); ++e) sl[slc[e].r1 == id ? slc[e].p1 : slc[e].p2].push_back((int)e);
+    size_t k = 0;
+    for (int j = 0; j < n; ++j)
+      for (int e : sl[j]) {
+        const auto &m = slc[e];
+        edge_blocks(m, T, Om);
+        double *M = &sv[k * 16];
+        if (m.r1 == id) {  // outgoing: G_i -= X_j Om T^T
+          for (int jj = 0; jj < 4; ++jj)
+            for (int ii = 0; ii < 4; ++ii) M[jj * 4 + ii] = -Om[ii] * T[ii * 4 + jj];
+        } else {  // incoming: G_j -= X_i T Om
+          for (int jj = 0; jj < 4; ++jj)
+            for (int ii = 0; ii < 4; ++ii) M[jj * 4 + ii] = -T[jj * 4 + ii] * Om[jj];
+        }
+        ++k;
+      }
+  }
+  d_s_val.upload(sv);
+  // loop-closure arrays
+  const size_t L = lc_list.size();
+  std::vector<int> src(L), dst(L);
+  std::vector<unsigned char> sr(L), dr(L), mask(L);
+  std::vector<double> R(L * 9), t(L * 3), ka(L), ta(L), w(L);
+  for (size_t e = 0; e < L; ++e) {
+    const Meas &m = *lc_list[e];
+    sr[e] = m.r1 != id;
+    dr[e] = m.r2 != id;
+    src[e] = sr[e] ? slot_of[{m.r1, m.p1}] : m.p1;
+    dst[e] = dr[e] ? slot_of[{m.r2, m.p2}] : m.p2;
+    const int other = sr[e] ? m.r1 : (dr[e] ? m.r2 : id);
+    mask[e] = (other >= id);  // lower ID owns a shared edge's weight (src/PGOAgentROS.cpp:732,1340)
+    std::memcpy(&R[e * 9], m.R, 9 * sizeof(double));
+    std::memcpy(&t[e * 3], m.t, 3 * sizeof(double));
+    ka[e] = m.kappa;
+    ta[e] = m.tau;
+    w[e] = m.weight;
+  }
+  d_lc_src.upload(src);
+  d_lc_dst.upload(dst);
+  d_lc_src_remote.upload(sr);
+  d_lc_dst_remote.upload(dr);
+  d_lc_mask.upload(mask);
+  d_lc_R.upload(R);
+  d_lc_t.upload(t);
+  d_lc_kappa.upload(ka);
+  d_lc_tau.upload(ta);
+  d_lc_weight.upload(w);
+  d_lc_residual.alloc(L);
+  values_dirty = false;
+  precon_dirty = true;
+}
+
+void Agent::build_preconditioner() {
+  if (!need_preconditioner()) {
+    precon_dirty = false;
+    return;
+  }
+  const size_t npad = roundup32((size_t)4 * n);
+  dPinv.alloc(npad * npad, false);
+  DevBuf<double> work, dinv;
+  DevBuf<int> info;
+  work.alloc(npad * npad, false);
+  dinv.alloc((npad / 32) * 1024, false);
+  info.alloc(1);
+  cuda_check(launch_scatter_blocks(dPinv.p, npad, d_q_rowptr.p, d_q_col.p, d_q_val.p, n, P.precond_lambda,
+                                   (int)npad, 0),
+             "scatter_blocks");
+  cuda_check(spd_inverse(dPinv.p, work.p, dinv.p, (int)npad, info.p, 0), "spd_inverse");
+  int h_info = 0;
+  cuda_check(cudaMemcpy(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
+  if (h_info != 0) fail(DPGO_B200_ERR_NUMERIC, "preconditioner: Q + lambda I is not positive definite");
+  precon_dirty = false;
+}
+
+void Agent::ensure_device() {
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  if (structure_dirty) build_structure();
+  if (values_dirty) build_values();
+  if (precon_dirty) build_preconditioner();
+}
+
+AgentDev Agent::dev_view() const {
+  AgentDev A{};
+  A.id = id; A.n = n; A.r = r; A.n_in = (int)slot_key.size();
+  A.X = dX.p; A.Y = dY.p; A.V = dV.p; A.Xinit = dXinit.p;
+  A.q_rowptr = d_q_rowptr.p; A.q_col = d_q_col.p; A.q_val = d_q_val.p;
+  A.s_rowptr = d_s_rowptr.p; A.s_slot = d_s_slot.p; A.s_val = d_s_val.p;
+  A.inbox_reg = d_inbox_reg.p; A.inbox_aux = d_inbox_aux.p;
+  A.pub_rowptr = d_pub_rowptr.p; A.pub_dst_reg = d_pub_dst_reg.p; A.pub_dst_aux = d_pub_dst_aux.p;
+  A.Pinv = dPinv.p;
+  A.G = dG.p; A.Rg = dRg.p; A.RgT = dRgT.p; A.Z = dZ.p; A.eta = dEta.p; A.dlt0 = dDlt0.p; A.dlt1 = dDlt1.p;
+  A.Hd = dHd.p; A.rv = dRv.p; A.rvT = dRvT.p; A.X2 = dX2.p; A.X3 = dX3.p; A.Rg2 = dRg2.p; A.Rg2T = dRg2T.p;
+  A.zeta = dZeta.p; A.S = dS.p; A.S2 = dS2.p; A.stat = dStat.p;
+  return A;
+}
+
+bool Agent::all_inbox_valid(bool aux) const {
+  const auto &v = aux ? inbox_valid_aux : inbox_valid_reg;
+  for (char c : v)
+    if (!c) return false;
+  return true;
+}
+
+// ---- iterate (standalone path: a team of one, neighbours fed through the inbox)
+bool Agent::iterate(bool do_opt) {
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  Team *tm = team;
+  if (state != 2) {
+    iter++;
+    tm->ctl.iter = iter;
+    if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
+    return false;
+  }
+  tm->prepare();
+  const bool accel = P.acceleration != 0;
+  const bool restart = accel && ((iter + 2) % P.restart_interval == 0);
+  bool can_opt = do_opt;
+  if (do_opt && !all_inbox_valid(accel && !restart)) can_opt = false;  // data matrices cannot be built
+  if (!accel && !can_opt) {
+    iter++;
+    tm->ctl.iter = iter;
+    if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
+    return false;
+  }
+  tm->run_forced(can_opt ? local_index : -1);
+  publish_requested = accel || can_opt;  // mPublishPublicPosesRequested, src/PGOAgentROS.cpp:109
+  return can_opt;
+}
+
+int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, int cap) {
+  if (state != 2) fail(DPGO_B200_ERR_STATE, "getSharedPoseDictWithNeighbor: agent not initialized");
+  if (aux && !P.acceleration) fail(DPGO_B200_ERR_STATE, "auxiliary poses need acceleration");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  team->prepare();
+  const std::vector<int> fr = my_public_frames(nbr);
+  const int cnt = (int)fr.size();
+  if (cnt > cap) fail(DPGO_B200_ERR_INVALID, "getSharedPoseDictWithNeighbor: buffer too small");
+  if (cnt == 0) return 0;
+  for (int k = 0; k < cnt; ++k) frames[k] = fr[k];
+  bool colocated = false;
+  for (Agent *o : team->agents)
+    if (o->id == nbr) colocated = true;
+  const size_t pb = (size_t)4 * r * sizeof(double);
+  if (!colocated) {
+    if (outbox_stale) team->exchange_all();
+    const auto rg = outbox_range.at(nbr);
+    const double *src = (aux ? d_outbox_aux.p : d_outbox_reg.p) + (size_t)rg.first * 4 * r;
+    cuda_check(cudaMemcpy(poses, src, pb * cnt, cudaMemcpyDeviceToHost), "D2H outbox");
+  } else {
+    const double *base = aux ? dY.p : dX.p;
+    for (int k = 0; k < cnt; ++k)
+      cuda_check(cudaMemcpy(poses + (size_t)k * 4 * r, base + (size_t)fr[k] * 4 * r, pb, cudaMemcpyDeviceToHost),
+                 "D2H pose");
+  }
+  return cnt;
+}
+
+void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const double *poses, int count) {
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  if (structure_dirty) build_structure();
+  double *inbox = aux ? d_inbox_aux.p : d_inbox_reg.p;
+  auto &valid = aux ? inbox_valid_aux : inbox_valid_reg;
+  const size_t pb = (size_t)4 * r * sizeof(double);
+  int k = 0;
+  while (k < count) {
+    auto it = slot_of.find({nbr, frames[k]});
+    if (it == slot_of.end()) {  // a pose this agent does not need: ignore
+      ++k;
+      continue;
+    }
+    // extend over a run of consecutive slots to batch the copy
+    int run = 1;
+    while (k + run < count) {
+      auto nx = slot_of.find({nbr, frames[k + run]});
+      if (nx == slot_of.end() || nx->second != it->second + run) break;
+      ++run;
+    }
+    cuda_check(cudaMemcpy(inbox + (size_t)it->second * 4 * r, poses + (size_t)k * 4 * r, pb * run,
+                          cudaMemcpyHostToDevice),
+               "H2D inbox");
+    for (int q = 0; q < run; ++q) valid[it->second + q] = 1;
+    k += run;
+  }
+}
+
+dpgo_b200_status Agent::get_status() const {
+  dpgo_b200_status s = status;
+  s.agent_id = id;
+  s.state = state;
+  s.instance_number = instance;
+  s.iteration_number = iter;
+  return s;
+}
+
+bool Agent::should_terminate() const {
+  if (iter > P.max_num_iters) return true;
+  if (P.cost_type != 0 && weight_update_count < P.robust_opt_num_weight_updates) return false;
+  for (int rid = 0; rid < P.num_robots; ++rid) {
+    auto it = team_status.find(rid);
+    if (it == team_status.end()) return false;
+    if (it->second.state != 2 || !it->second.ready_to_terminate) return false;
+  }
+  return true;
+}
+
+bool Agent::should_update_weights() const {
+  if (P.cost_type == 0) return false;
+  if (weight_update_count >= P.robust_opt_num_weight_updates) return false;
+  if (robust_inner_iter >= P.robust_opt_inner_iters) return true;
+  for (int rid = 0; rid < P.num_robots; ++rid) {
+    auto it = team_status.find(rid);
+    if (it == team_status.end()) return false;
+    if (it->second.state != 2 || !it->second.ready_to_terminate) return false;
+  }
+  return true;
+}
+
+double Agent::robust_weight(double res) const {
+  if (P.cost_type == 0) return 1.0;
+  const double bsq = P.gnc_barc * P.gnc_barc;
+  const double upper = (mu + 1.0) / mu * bsq, lower = mu / (mu + 1.0) * bsq, rsq = res * res;
+  if (rsq >= upper) return 0.0;
+  if (rsq <= lower) return 1.0;
+  return std::sqrt(bsq * mu * (mu + 1.0) / rsq) - mu;
+}
+
+void Agent::update_measurement_weights() {
+  if (state != 2) return;
+  team->gnc_update_all();
+}
+
+bool Agent::compute_residual(const Meas &m, double *res) {
+  if (state != 2) return false;
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  team->prepare();
+  // single-measurement residual through the same kernel as the weight update
+  DevBuf<int> src, dst;
+  DevBuf<unsigned char> sr, dr, mask;
+  DevBuf<double> R, t, ka, ta, w, rs;
+  const bool s_rem = m.r1 != id, d_rem = m.r2 != id;
+  int si, di;
+  if (s_rem) {
+    auto it = slot_of.find({m.r1, m.p1});
+    if (it == slot_of.end() || !inbox_valid_reg[it->second]) return false;
+    si = it->second;
+  } else {
+    si = m.p1;
+  }
+  if (d_rem) {
+    auto it = slot_of.find({m.r2, m.p2});
+    if (it == slot_of.end() || !inbox_valid_reg[it->second]) return false;
+    di = it->second;
+  } else {
+    di = m.p2;
+  }
+  src.upload({si});
+  dst.upload({di});
+  sr.upload({(unsigned char)s_rem});
+  dr.upload({(unsigned char)d_rem});
+  mask.upload({(unsigned char)0});
+  R.upload(std::vector<double>(m.R, m.R + 9));
+  t.upload(std::vector<double>(m.t, m.t + 3));
+  ka.upload({m.kappa});
+  ta.upload({m.tau});
+  w.upload({m.weight});
+  rs.alloc(1);
+  LcDev L{1, src.p, dst.p, sr.p, dr.p, mask.p, R.p, t.p, ka.p, ta.p, w.p, rs.p};
+  cuda_check(launch_gnc_weights(L, r, dX.p, d_inbox_reg.p, P.gnc_barc * P.gnc_barc, mu, P.cost_type, 0),
+             "gnc_weights");
+  cuda_check(cudaMemcpy(res, rs.p, sizeof(double), cudaMemcpyDeviceToHost), "D2H residual");
+  return true;
+}
+
+// ============================================================================
+// Team
+// ============================================================================
+Team::Team(int device_) : device(device_) {
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(cudaEventCreate(&ev0), "eventCreate");
+  cuda_check(cudaEventCreate(&ev1), "eventCreate");
+}
+
+Team::~Team() {
+  for (Agent *a : agents) {
+    if (a->team != this) continue;
+    if (a->own.get() == this || !a->own) {
+      a->team = nullptr;
+      continue;
+    }
+    a->team = a->own.get();
+    a->own->agents.assign(1, a);
+    a->local_index = 0;
+    a->wiring_dirty = true;
+    a->own->team_dirty = true;
+  }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+}
+
+void Team::add(Agent *a) {
+  if ((int)agents.size() >= kMaxLocal) fail(DPGO_B200_ERR_INVALID, "too many agents on one device (max 8)");
+  if (a->device != device) fail(DPGO_B200_ERR_INVALID, "agent lives on another device");
+  if (!agents.empty() && (agents[0]->r != a->r || agents[0]->P.num_robots != a->P.num_robots))
+    fail(DPGO_B200_ERR_INVALID, "agents of one team must share r and num_robots");
+  if (a->team && a->team != this && a->team != a->own.get()) a->team->remove(a);
+  if (agents.empty() && a->own && a->own.get() != this) ctl = a->own->ctl;
+  if (a->own && a->own.get() != this) a->own->agents.clear();
+  a->team = this;
+  a->local_index = (int)agents.size();
+  agents.push_back(a);
+  for (Agent *o : agents) o->wiring_dirty = true;
+  team_dirty = true;
+}
+
+void Team::remove(Agent *a) {
+  auto it = std::find(agents.begin(), agents.end(), a);
+  if (it == agents.end()) return;
+  agents.erase(it);
+  for (size_t i = 0; i < agents.size(); ++i) {
+    agents[i]->local_index = (int)i;
+    agents[i]->wiring_dirty = true;
+  }
+  team_dirty = true;
+  if (a->own && a->own.get() != this) {
+    a->team = a->own.get();
+    a->own->agents.assign(1, a);
+    a->local_index = 0;
+    a->wiring_dirty = true;
+    a->own->team_dirty = true;
+  } else {
+    a->team = nullptr;
+  }
+}
+
+void Team::prepare() {
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  if (agents.empty()) fail(DPGO_B200_ERR_STATE, "team has no agents");
+  bool rewire = team_dirty;
+  for (Agent *a : agents) {
+    if (a->structure_dirty || a->values_dirty || a->precon_dirty) rewire = true;
+    a->ensure_device();
+    if (a->wiring_dirty) rewire = true;
+  }
+  if (!rewire) return;
+  const int r = agents[0]->r;
+  for (Agent *a : agents) {
+    std::vector<double *> reg(a->h_pub_entries.size()), aux(a->h_pub_entries.size());
+    std::map<int, std::vector<int>> frames_of;
+    for (size_t e = 0; e < a->h_pub_entries.size(); ++e) {
+      const int b = a->h_pub_entries[e].first, f = a->h_pub_entries[e].second;
+      Agent *peer = nullptr;
+      for (Agent *o : agents)
+        if (o->id == b) peer = o;
+      if (peer) {
+        auto it = peer->slot_of.find({a->id, f});
+        if (it == peer->slot_of.end()) {
+          // the peer does not hold this shared edge (measurements not synchronised): park in the outbox
+          peer = nullptr;
+        } else {
+          reg[e] = peer->d_inbox_reg.p + (size_t)it->second * 4 * r;
+          aux[e] = peer->d_inbox_aux.p + (size_t)it->second * 4 * r;
+        }
+      }
+      if (!peer) {
+        auto &fr = frames_of[b];
+        if (fr.empty()) fr = a->my_public_frames(b);
+        const int idx = (int)(std::lower_bound(fr.begin(), fr.end(), f) - fr.begin());
+        const size_t o = (size_t)(a->outbox_range.at(b).first + idx) * 4 * r;
+        reg[e] = a->d_outbox_reg.p + o;
+        aux[e] = a->d_outbox_aux.p + o;
+      }
+    }
+    if (reg.empty()) {
+      reg.push_back(nullptr);
+      aux.push_back(nullptr);
+    }
+    a->d_pub_dst_reg.upload(reg);
+    a->d_pub_dst_aux.upload(aux);
+    a->wiring_dirty = false;
+  }
+  // TeamDev
+  std::memset(&T, 0, sizeof(T));
+  T.num_local = (int)agents.size();
+  T.num_robots = agents[0]->P.num_robots;
+  for (int i = 0; i < kMaxRobots; ++i) T.local_of_robot[i] = -1;
+  T.pose_prefix[0] = 0;
+  for (size_t i = 0; i < agents.size(); ++i) {
+    T.local_of_robot[agents[i]->id] = (int)i;
+    T.ag[i] = agents[i]->dev_view();
+    T.pose_prefix[i + 1] = T.pose_prefix[i] + agents[i]->n;
+  }
+  const dpgo_b200_params &P = agents[0]->P;
+  T.p.method = P.method;
+  T.p.rgd_stepsize = P.rgd_stepsize;
+  T.p.rgd_use_precond = P.rgd_use_preconditioner;
+  T.p.rtr_iterations = P.rtr_iterations;
+  T.p.rtr_tcg_iterations = P.rtr_tcg_iterations;
+  T.p.rtr_initial_radius = P.rtr_initial_radius;
+  T.p.gradnorm_tol = P.gradnorm_tol;
+  T.p.acceleration = P.acceleration;
+  T.p.restart_interval = P.restart_interval;
+  T.p.robust = P.cost_type != 0;
+  T.p.robust_num_weight_updates = P.robust_opt_num_weight_updates;
+  T.p.robust_inner_iters = P.robust_opt_inner_iters;
+  T.p.max_num_iters = P.max_num_iters;
+  T.p.rel_change_tol = P.rel_change_tol;
+  if (grid <= 0) grid = max_coop_grid(device);
+  dBar.alloc(2);
+  dSlots.alloc((size_t)2 * grid * kRed);
+  dCtl.alloc(1);
+  T.gs.count = dBar.p;
+  T.gs.gen = dBar.p + 1;
+  T.gs.slots = dSlots.p;
+  T.ctl = dCtl.p;
+  team_dirty = false;
+}
+
+void Team::read_back() {
+  cuda_check(cudaMemcpy(&ctl, dCtl.p, sizeof(TeamCtl), cudaMemcpyDeviceToHost), "D2H ctl");
+  for (Agent *a : agents) {
+    AgentStat st;
+    cuda_check(cudaMemcpy(&st, a->dStat.p, sizeof(AgentStat), cudaMemcpyDeviceToHost), "D2H stat");
+    a->iter = ctl.iter;
+    a->robust_inner_iter = ctl.robust_inner_iter;
+    if (st.optimized) {
+      a->opt.success = 1;
+      a->opt.f_init = st.f_init;
+      a->opt.f_opt = st.f_opt;
+      a->opt.gradnorm_init = st.gn_init;
+      a->opt.gradnorm_opt = st.gn_opt;
+      a->opt.relative_change = st.relchange;
+      a->opt.tcg_iters = st.tcg_iters;
+      a->opt.rtr_outer_iters = st.rtr_outer;
+      a->opt.rtr_rejections = st.rtr_rej;
+      a->status.relative_change = st.relchange;
+      a->status.ready_to_terminate = st.ready;
+    }
+    a->status.iteration_number = a->iter;
+    a->status.state = a->state;
+    a->team_status[a->id] = a->get_status();
+  }
+}
+
+void Team::run_forced(int sel_local) {
+  prepare();
+  cuda_check(cudaMemcpy(dCtl.p, &ctl, sizeof(TeamCtl), cudaMemcpyHostToDevice), "H2D ctl");
+  RunArgs args{1, sel_local, 0, 0};
+  cuda_check(launch_team_run(T, args, grid, 0), "launch k_team_run");
+  ++launches;
+  cuda_check(cudaDeviceSynchronize(), "k_team_run");
+  read_back();
+}
+
+dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
+  dpgo_b200_run_result res{};
+  prepare();
+  for (Agent *a : agents) {
+    if (a->state != 2) fail(DPGO_B200_ERR_STATE, "team_run: every agent must be initialized in the global frame");
+    if (T.local_of_robot[a->id] < 0) fail(DPGO_B200_ERR_STATE, "team_run: inconsistent team");
+  }
+  if ((int)agents.size() != T.num_robots)
+    fail(DPGO_B200_ERR_STATE, "team_run needs every robot of the problem in the team (use iterate + exchange otherwise)");
+  for (Agent *a : agents)
+    if (!a->all_inbox_valid(false) || (a->P.acceleration && !a->all_inbox_valid(true)))
+      fail(DPGO_B200_ERR_MISSING, "team_run: neighbour poses missing; call team_exchange_all first");
+  int remaining = max_iters;
+  while (remaining > 0) {
+    cuda_check(cudaMemcpy(dCtl.p, &ctl, sizeof(TeamCtl), cudaMemcpyHostToDevice), "H2D ctl");
+    RunArgs args{remaining, -2, stop_on_terminate ? 1 : 0, 0};
+    cuda_check(cudaEventRecord(ev0, 0), "eventRecord");
+    cuda_check(launch_team_run(T, args, grid, 0), "launch k_team_run");
+    cuda_check(cudaEventRecord(ev1, 0), "eventRecord");
+    cuda_check(cudaEventSynchronize(ev1), "k_team_run");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    res.device_ms += ms;
+    res.kernel_launches++;
+    ++launches;
+    read_back();
+    res.iterations += ctl.iters_done;
+    remaining -= ctl.iters_done;
+    if (ctl.stop_reason == 2) {
+      gnc_update_all();
+      res.weight_updates++;
+      continue;
+    }
+    if (ctl.stop_reason == 1) res.terminated = 1;
+    break;
+  }
+  return res;
+}
+
+void Team::exchange_all() {
+  prepare();
+  // publish X (and Y) of every agent through the same publication lists the
+  // persistent kernel uses: a forced iteration count of zero does nothing, so
+  // use the dedicated kernel
+  cuda_check(launch_publish_all(T, grid, 0), "publish_all");
+  cuda_check(cudaDeviceSynchronize(), "publish_all");
+  for (Agent *a : agents) {
+    if (a->state != 2) continue;
+    a->outbox_stale = false;
+    for (Agent *o : agents) {
+      if (o == a) continue;
+      for (size_t s = 0; s < o->slot_key.size(); ++s)
+        if (o->slot_key[s].first == a->id) {
+          o->inbox_valid_reg[s] = 1;
+          if (a->P.acceleration) o->inbox_valid_aux[s] = 1;
+        }
+    }
+  }
+}
+
+// UPDATE_WEIGHT (src/PGOAgentROS.cpp:1211-1233): residual + GNC-TLS weight on the
+// device, ownership rule and Q / G / preconditioner rebuild on the host side.
+void Team::gnc_update_all() {
+  prepare();
+  for (Agent *a : agents) {
+    if (a->state != 2) continue;
+    const size_t L = a->lc_list.size();
+    if (L) {
+      LcDev Ld{(int)L, a->d_lc_src.p, a->d_lc_dst.p, a->d_lc_src_remote.p, a->d_lc_dst_remote.p, a->d_lc_mask.p,
+               a->d_lc_R.p, a->d_lc_t.p, a->d_lc_kappa.p, a->d_lc_tau.p, a->d_lc_weight.p, a->d_lc_residual.p};
+      cuda_check(launch_gnc_weights(Ld, a->r, a->dX.p, a->d_inbox_reg.p, a->P.gnc_barc * a->P.gnc_barc, a->mu,
+                                    a->P.cost_type, 0),
+                 "gnc_weights");
+      std::vector<double> w(L);
+      cuda_check(cudaMemcpy(w.data(), a->d_lc_weight.p, L * sizeof(double), cudaMemcpyDeviceToHost), "D2H weights");
+      for (size_t e = 0; e < L; ++e) a->lc_list[e]->weight = w[e];
+    }
+  }
+  // publishMeasurementWeights (:721-754) -> measurementWeightsCallback (:1315-1353)
+  for (Agent *a : agents)
+    for (const auto &m : a->slc) {
+      const int other = (m.r1 == a->id) ? m.r2 : m.r1;
+      if (other > a->id)
+        for (Agent *o : agents)
+          if (o->id == other) {
+            Meas *mm = o->find_measurement(m.r1, m.p1, m.r2, m.p2);
+            if (mm) {
+              mm->weight = m.weight;
+              mm->fixed = m.fixed;
+            }
+          }
+    }
+  for (Agent *a : agents) {
+    if (a->state != 2) continue;
+    if (a->P.cost_type == 5) a->mu *= a->P.gnc_mu_step;
+    a->weight_update_count++;
+    a->robust_inner_iter = 0;
+    a->values_dirty = a->precon_dirty = true;
+    const size_t bytes = (size_t)a->r * 4 * a->n * sizeof(double);
+    if (a->weight_update_count <= a->P.robust_opt_num_resets)
+      cuda_check(cudaMemcpy(a->dX.p, a->dXinit.p, bytes, cudaMemcpyDeviceToDevice), "reset X");
+    if (a->P.acceleration) {
+      cuda_check(cudaMemcpy(a->dV.p, a->dX.p, bytes, cudaMemcpyDeviceToDevice), "V = X");
+      cuda_check(cudaMemcpy(a->dY.p, a->dX.p, bytes, cudaMemcpyDeviceToDevice), "Y = X");
+    }
+  }
+  ctl.weight_update_count++;
+  ctl.robust_inner_iter = 0;
+  if (agents[0]->P.acceleration) ctl.gamma = ctl.alpha = 0;
+  team_dirty = true;
+  exchange_all();
+}
+
+double Team::global_cost() {
+  prepare();
+  std::map<int, std::vector<double>> X;
+  for (Agent *a : agents) {
+    std::vector<double> h((size_t)a->r * 4 * a->n);
+    cuda_check(cudaMemcpy(h.data(), a->dX.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H X");
+    X[a->id] = std::move(h);
+  }
+  const int r = agents[0]->r;
+  auto edge_cost = [&](const Meas &m, const double *Xi, const double *Xj) {
+    double rot = 0, tr = 0;
+    for (int c = 0; c < 3; ++c)
+      for (int a = 0; a < r; ++a) {
+        double s = -Xj[(size_t)c * r + a];
+        for (int k = 0; k < 3; ++k) s += Xi[(size_t)k * r + a] * m.R[c * 3 + k];
+        rot += s * s;
+      }
+    for (int a = 0; a < r; ++a) {
+      double s = Xj[(size_t)3 * r + a] - Xi[(size_t)3 * r + a];
+      for (int k = 0; k < 3; ++k) s -= Xi[(size_t)k * r + a] * m.t[k];
+      tr += s * s;
+    }
+    return m.weight * (m.kappa * rot + m.tau * tr);
+  };
+  double cost = 0;
+  for (Agent *a : agents) {
+    const double *Xa = X[a->id].data();
+    for (auto *vec : {&a->odom, &a->plc})
+      for (const auto &m : *vec) cost += edge_cost(m, Xa + (size_t)m.p1 * 4 * r, Xa + (size_t)m.p2 * 4 * r);
+    for (const auto &m : a->slc)
+      if (m.r1 == a->id && X.count(m.r2))
+        cost += edge_cost(m, Xa + (size_t)m.p1 * 4 * r, X[m.r2].data() + (size_t)m.p2 * 4 * r);
+  }
+  return cost;
+}
+
+}  // namespace dpgo

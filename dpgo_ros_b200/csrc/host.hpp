@@ -1,0 +1,191 @@
+// Host side of the B200 RBCD path: pose-graph bookkeeping, device data layout
+// construction and launch sequencing.  Mirrors the DPGO::PGOAgent call surface
+// that dpgo_ros drives; all arithmetic runs in the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/dpgo_b200.h"
+#include "kernels.h"
+
+namespace dpgo {
+
+struct Meas {
+  int r1, p1, r2, p2;
+  double R[9];  // column-major
+  double t[3];
+  double kappa, tau, weight;
+  bool fixed;
+};
+
+struct Error {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string &msg);
+void cuda_check(cudaError_t e, const char *what);
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count, bool zero = true) {
+    if (count != n) {
+      release();
+      if (count) cuda_check(cudaMalloc((void **)&p, count * sizeof(T)), "cudaMalloc");
+      n = count;
+    }
+    if (zero && n) cuda_check(cudaMemset(p, 0, n * sizeof(T)), "cudaMemset");
+  }
+  void upload(const std::vector<T> &h) {
+    alloc(h.size(), false);
+    if (n) cuda_check(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice), "H2D");
+  }
+};
+
+class Team;
+
+class Agent {
+ public:
+  Agent(int id, const dpgo_b200_params &p, int device);
+  ~Agent();
+
+  // ---- pose graph
+  void add_measurement(const Meas &m);
+  Meas *find_measurement(int r1, int p1, int r2, int p2);
+  std::vector<int> neighbors() const { return std::vector<int>(nbrs.begin(), nbrs.end()); }
+  std::vector<int> my_public_frames(int nbr) const;
+
+  // ---- lifecycle
+  void set_lifting_matrix(const double *Y);
+  void initialize(const double *T_rowmajor_or_null);
+  void initialize_in_global_frame(const double *Tw_rowmajor);
+  void reset();
+  bool iterate(bool do_opt);
+
+  // ---- exchange
+  int get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, int cap);
+  void update_neighbor_poses(int nbr, bool aux, const int *frames, const double *poses, int count);
+
+  // ---- status / GNC
+  dpgo_b200_status get_status() const;
+  bool should_terminate() const;
+  bool should_update_weights() const;
+  void update_measurement_weights();  // standalone (team of one) path
+  bool compute_residual(const Meas &m, double *res);
+  double robust_weight(double residual) const;
+
+  // ---- device structures
+  void ensure_device();   // allocate + build everything that is stale
+  void build_structure(); // graph topology -> CSR / slots / publication lists
+  void build_values();    // Q blocks, G blocks, LC arrays (weights) -> device
+  void build_preconditioner();
+  bool need_preconditioner() const { return P.method == 0 || P.rgd_use_preconditioner; }
+  AgentDev dev_view() const;
+  bool all_inbox_valid(bool aux) const;
+
+  // identity / params
+  int id;
+  dpgo_b200_params P;
+  int device;
+  int r;
+  Team *team = nullptr;        // the team that launches for this agent
+  std::unique_ptr<Team> own;   // implicit team of one
+  int local_index = 0;
+
+  // pose graph (host)
+  int n = 0;
+  std::vector<Meas> odom, plc, slc;
+  std::set<std::pair<std::pair<int, int>, std::pair<int, int>>> have;
+  std::set<int> nbrs;
+
+  // state machine
+  int state = 0, instance = 0, iter = 0;
+  bool have_lift = false;
+  double ylift[8 * 3];
+  std::vector<double> Tlocal;  // 12 n, column-major 3x4 per pose
+  dpgo_b200_opt_result opt{};
+  dpgo_b200_status status{};
+  std::map<int, dpgo_b200_status> team_status;
+  int weight_update_count = 0, robust_inner_iter = 0;
+  double mu;
+  bool publish_requested = false;
+  bool outbox_stale = true;  // outbox staging not yet filled by a publish
+
+  // neighbour slots
+  std::map<std::pair<int, int>, int> slot_of;  // (robot, frame) -> inbox slot
+  std::vector<std::pair<int, int>> slot_key;
+  std::vector<char> inbox_valid_reg, inbox_valid_aux;
+  // outbox staging (for neighbours that are not co-located): per neighbour offset into outbox arrays
+  std::map<int, std::pair<int, int>> outbox_range;  // nbr -> (first index, count)
+  int outbox_total = 0;
+
+  // dirtiness
+  bool structure_dirty = true, values_dirty = true, precon_dirty = true, wiring_dirty = true;
+
+  // device buffers
+  DevBuf<double> dX, dY, dV, dXinit;
+  DevBuf<int> d_q_rowptr, d_q_col, d_s_rowptr, d_s_slot, d_pub_rowptr;
+  DevBuf<double> d_q_val, d_s_val;
+  DevBuf<double> d_inbox_reg, d_inbox_aux, d_outbox_reg, d_outbox_aux;
+  DevBuf<double *> d_pub_dst_reg, d_pub_dst_aux;
+  DevBuf<double> dPinv;
+  DevBuf<double> dG, dRg, dRgT, dZ, dEta, dDlt0, dDlt1, dHd, dRv, dRvT, dX2, dX3, dRg2, dRg2T, dZeta, dS, dS2;
+  DevBuf<AgentStat> dStat;
+  // loop-closure arrays for the GNC kernel
+  DevBuf<int> d_lc_src, d_lc_dst;
+  DevBuf<unsigned char> d_lc_src_remote, d_lc_dst_remote, d_lc_mask;
+  DevBuf<double> d_lc_R, d_lc_t, d_lc_kappa, d_lc_tau, d_lc_weight, d_lc_residual;
+  std::vector<Meas *> lc_list;  // the measurements behind the LC arrays
+  // host copies of structure used for wiring
+  std::vector<int> h_pub_rowptr;
+  std::vector<std::pair<int, int>> h_pub_entries;  // (neighbour, my frame) per publication entry
+  std::vector<int> h_q_rowptr, h_q_col, h_s_rowptr, h_s_slot;
+};
+
+class Team {
+ public:
+  explicit Team(int device);
+  ~Team();
+  void add(Agent *a);
+  void remove(Agent *a);
+  void prepare();  // ensure every agent's device data + wiring + TeamDev are current
+  void exchange_all();
+  dpgo_b200_run_result run(int max_iters, bool stop_on_terminate);
+  // one iteration with a forced selection (standalone iterate path); returns kernel ms
+  void run_forced(int sel_local);
+  void gnc_update_all();
+  double global_cost();
+  void sync_ctl_from_agents();
+  void read_back();  // ctl + per-agent stats -> host
+
+  int device;
+  int grid = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<Agent *> agents;
+  TeamDev T{};
+  TeamCtl ctl{};
+  DevBuf<TeamCtl> dCtl;
+  DevBuf<unsigned> dBar;
+  DevBuf<double> dSlots;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool team_dirty = true;
+  int launches = 0;
+};
+
+}  // namespace dpgo

@@ -1,0 +1,47 @@
+// Host-visible launch interface of the sm_100a kernels (kernels.cu, dense_inverse.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device.cuh"
+
+namespace dpgo {
+
+struct RunArgs {
+  int max_iters;
+  int force_selected;  // -2: follow the RoundRobin schedule; -1: nobody optimises; >= 0: that local agent
+  int stop_on_terminate;
+  int leader;          // robot id whose turn triggers the termination / weight-update test
+};
+
+// non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel
+struct LcDev {
+  int count;
+  const int *src, *dst;                      // local pose index, or inbox slot when remote
+  const unsigned char *src_remote, *dst_remote;
+  const unsigned char *update_mask;          // 1: this agent owns the weight
+  const double *R, *t, *kappa, *tau;         // R column-major 3x3
+  double *weight, *residual;
+};
+
+long long kernel_launch_count();
+long long dense_inverse_launch_count();
+int max_coop_grid(int device);
+cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream);
+cudaError_t launch_eval(const AgentDev &A, const double *X, const double *inbox, double *egrad, double *rgrad,
+                        double *partials, int grid, cudaStream_t s);
+cudaError_t launch_hess(const AgentDev &A, const double *X, const double *V, double *out, int grid, cudaStream_t s);
+cudaError_t launch_transpose_rows(const double *V, double *VT, int r, int n4, cudaStream_t s);
+cudaError_t launch_precond(const AgentDev &A, const double *X, const double *V, const double *VT, double *out,
+                           int grid, cudaStream_t s);
+cudaError_t launch_manifold_op(int op, int r, int n, const double *A, const double *B, double *out, int grid,
+                               cudaStream_t s);
+cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s);
+cudaError_t launch_gnc_weights(const LcDev &L, int r, const double *X, const double *inbox, double barc_sq,
+                               double mu, int cost_type, cudaStream_t s);
+
+// dense_inverse.cu: P <- (blocks scattered) ; P <- P^-1 (SPD), N multiple of 32
+cudaError_t launch_scatter_blocks(double *P, size_t ld, const int *rowptr, const int *col, const double *val,
+                                  int n, double lambda, int npad, cudaStream_t s);
+cudaError_t spd_inverse(double *A, double *work, double *dinv, int N, int *d_info, cudaStream_t s);
+
+}  // namespace dpgo

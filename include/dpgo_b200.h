@@ -1,0 +1,173 @@
+/*
+ * dpgo_b200 -- C ABI of the B200-native RBCD hot path.
+ *
+ * This is the drop-in boundary under the DPGO::PGOAgent API surface that
+ * dpgo_ros's PGOAgentROS subclasses (include/dpgo_ros/PGOAgentROS.h:121).
+ * Every entry point names the reference call site whose arithmetic it
+ * replaces (paths relative to the reference repo).  Plain pointers and sizes
+ * only; every function returns 0 on success or a negative dpgo_b200_error.
+ * No exceptions cross this boundary.  There is NO CPU fallback: every compute
+ * call fails with DPGO_B200_ERR_CUDA when no CUDA device is usable.
+ *
+ * Array conventions
+ *   X, Y, V      r x 4n doubles, column-major; pose i = columns 4i..4i+3
+ *                ([Y_i | p_i], Y_i in St(3, r)) -- the layout of DPGO::Matrix X.
+ *   poses        count x (r*4) doubles, each pose r x 4 column-major.
+ *   R            m x 9 doubles, row-major 3x3 per measurement; t: m x 3.
+ *   T (SE(3))    n x 3 x 4 doubles, row-major per pose ([R | t]).
+ *   lifting Y    r x 3 doubles, column-major.
+ */
+#ifndef DPGO_B200_H
+#define DPGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dpgo_b200_agent_s *dpgo_b200_agent_t;
+typedef struct dpgo_b200_team_s *dpgo_b200_team_t;
+
+typedef enum {
+  DPGO_B200_OK = 0,
+  DPGO_B200_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  DPGO_B200_ERR_STATE = -2,     /* call not valid in the agent's current state */
+  DPGO_B200_ERR_CUDA = -3,      /* CUDA runtime failure (or no device) */
+  DPGO_B200_ERR_MISSING = -4,   /* neighbour pose / measurement not found */
+  DPGO_B200_ERR_NUMERIC = -5    /* factorisation failed (matrix not PD) */
+} dpgo_b200_error;
+
+/* PGOAgentParameters fields set in src/PGOAgentROSNode.cpp:72-232. */
+typedef struct {
+  int d, r, num_robots;                       /* :72 (d must be 3, :63; r >= d, :67) */
+  int method;                                 /* 0 RTR, 1 RGD (:82-93) */
+  double rgd_stepsize;                        /* :96 */
+  int rgd_use_preconditioner;                 /* :97 */
+  int rtr_iterations, rtr_tcg_iterations;     /* :98-99 */
+  double rtr_initial_radius, gradnorm_tol;    /* :100 */
+  int acceleration, restart_interval;         /* :126-130 */
+  int cost_type;                              /* 0 L2 ... 5 GNC_TLS (:178-188) */
+  double gnc_barc, gnc_mu_step, gnc_init_mu;  /* :202-211 */
+  int robust_opt_num_weight_updates, robust_opt_num_resets, robust_opt_inner_iters; /* :212-217 */
+  double robust_opt_min_convergence_ratio;    /* :214 */
+  int max_num_iters;                          /* :226-231 */
+  double rel_change_tol;                      /* :145 */
+  double precond_lambda;                      /* Q + lambda I regularisation of the preconditioner */
+} dpgo_b200_params;
+
+/* mLocalOptResult, read at src/PGOAgentROS.cpp:169-172 */
+typedef struct {
+  int success;
+  double f_init, f_opt, gradnorm_init, gradnorm_opt, relative_change;
+  int rtr_outer_iters, tcg_iters, rtr_rejections;
+} dpgo_b200_opt_result;
+
+/* PGOAgentStatus (src/utils.cpp:262-281); state: 0 WAIT_FOR_DATA, 1 WAIT_FOR_INITIALIZATION, 2 INITIALIZED */
+typedef struct {
+  int agent_id, state, instance_number, iteration_number, ready_to_terminate;
+  double relative_change;
+} dpgo_b200_status;
+
+typedef struct {
+  int iterations;      /* global iterations executed by this call */
+  int terminated;      /* leader's shouldTerminate() fired */
+  int weight_updates;  /* GNC weight updates performed inside this call */
+  float device_ms;     /* CUDA-event time of the persistent kernel launches */
+  int kernel_launches; /* number of kernels this call launched */
+} dpgo_b200_run_result;
+
+/* ---- library ------------------------------------------------------------- */
+const char *dpgo_b200_version(void);
+const char *dpgo_b200_last_error(void);
+int dpgo_b200_device_count(void);
+/* number of kernels launched by this library since load (bench.py gpu_launches) */
+long long dpgo_b200_kernel_launch_count(void);
+
+/* ---- agent lifecycle: PGOAgent(ID, params), src/PGOAgentROS.cpp:26 ---------- */
+int dpgo_b200_agent_create(int id, const dpgo_b200_params *params, int device, dpgo_b200_agent_t *out);
+int dpgo_b200_agent_destroy(dpgo_b200_agent_t a);
+int dpgo_b200_reset(dpgo_b200_agent_t a);                       /* PGOAgent::reset, :223 */
+
+/* addMeasurement, :277 and :1307 (duplicates are ignored like hasMeasurement, :276) */
+int dpgo_b200_add_measurements(dpgo_b200_agent_t a, int m, const int *r1, const int *p1, const int *r2,
+                               const int *p2, const double *R, const double *t, const double *kappa,
+                               const double *tau, const double *weight, const unsigned char *fixed);
+int dpgo_b200_num_poses(dpgo_b200_agent_t a);                   /* num_poses(), :285 */
+int dpgo_b200_iteration_number(dpgo_b200_agent_t a);            /* iteration_number(), :139 */
+int dpgo_b200_num_neighbors(dpgo_b200_agent_t a);               /* getNeighbors(), :663 */
+int dpgo_b200_get_neighbors(dpgo_b200_agent_t a, int *ids, int cap);
+/* PoseGraph counters read at :343-345 */
+int dpgo_b200_measurement_counts(dpgo_b200_agent_t a, int *odometry, int *private_lc, int *shared_lc);
+
+int dpgo_b200_set_lifting_matrix(dpgo_b200_agent_t a, const double *Y);   /* :928 */
+int dpgo_b200_get_lifting_matrix(dpgo_b200_agent_t a, double *Y);         /* :404 */
+int dpgo_b200_initialize(dpgo_b200_agent_t a, const double *T_local_or_null);   /* :348 */
+int dpgo_b200_initialize_in_global_frame(dpgo_b200_agent_t a, const double *T_world_robot); /* :353,358 */
+
+/* ---- the hot call: iterate(bool), :160 (true) and :1185 (false) -------------- */
+int dpgo_b200_iterate(dpgo_b200_agent_t a, int do_optimization);
+int dpgo_b200_get_opt_result(dpgo_b200_agent_t a, dpgo_b200_opt_result *out);   /* :169-172 */
+int dpgo_b200_get_status(dpgo_b200_agent_t a, dpgo_b200_status *out);           /* getStatus, :616 */
+int dpgo_b200_set_neighbor_status(dpgo_b200_agent_t a, const dpgo_b200_status *s);  /* :965 */
+int dpgo_b200_should_terminate(dpgo_b200_agent_t a);                            /* :208  (1/0, <0 error) */
+int dpgo_b200_should_update_measurement_weights(dpgo_b200_agent_t a);           /* :210 */
+
+/* which: 0 X, 1 Y (auxiliary), 2 V -- getX of the north star; host buffer r x 4n */
+int dpgo_b200_get_x(dpgo_b200_agent_t a, int which, double *out);
+int dpgo_b200_set_x(dpgo_b200_agent_t a, const double *X);
+
+/* ---- public-pose exchange with HOST buffers (a9) ----------------------------
+ * getSharedPoseDictWithNeighbor / getAuxSharedPoseDictWithNeighbor (:666-668)
+ * and updateNeighborPoses / updateAuxNeighborPoses (:1276-1278).              */
+int dpgo_b200_num_shared_poses(dpgo_b200_agent_t a, int neighbor);
+int dpgo_b200_get_shared_pose_dict(dpgo_b200_agent_t a, int neighbor, int aux, int *frame_ids, double *poses,
+                                   int cap, int *count);
+int dpgo_b200_update_neighbor_poses(dpgo_b200_agent_t a, int neighbor, int aux, const int *frame_ids,
+                                    const double *poses, int count);
+/* Same exchange with raw DEVICE buffers (NCCL / NVLink peer transport replacing
+ * the ROS MatrixMsg path): a packed outbox per neighbour, frame-id order of
+ * dpgo_b200_get_shared_pose_dict, and the matching inbox on the receiver.     */
+int dpgo_b200_outbox_device_ptr(dpgo_b200_agent_t a, int neighbor, int aux, void **dev_ptr, size_t *bytes);
+int dpgo_b200_inbox_device_ptr(dpgo_b200_agent_t a, int neighbor, int aux, void **dev_ptr, size_t *bytes);
+/* tell the agent that the inbox of `neighbor` was filled by an external transport */
+int dpgo_b200_mark_inbox_updated(dpgo_b200_agent_t a, int neighbor, int aux);
+
+/* ---- GNC-TLS (a8) -------------------------------------------------------------- */
+int dpgo_b200_update_measurement_weights(dpgo_b200_agent_t a);                  /* :1218 */
+int dpgo_b200_set_measurement_weight(dpgo_b200_agent_t a, int r1, int p1, int r2, int p2, double w,
+                                     int fixed);                               /* :1341 */
+int dpgo_b200_compute_measurement_residual(dpgo_b200_agent_t a, int r1, int p1, int r2, int p2,
+                                           double *residual);                  /* :1049 */
+double dpgo_b200_robust_weight(dpgo_b200_agent_t a, double residual);           /* mRobustCost.weight, :1050 */
+int dpgo_b200_clear_data_matrices(dpgo_b200_agent_t a);                         /* :1351 */
+/* loop-closure weights in insertion order: private LCs, then shared LCs */
+int dpgo_b200_get_lc_weights(dpgo_b200_agent_t a, double *out, int cap);
+int dpgo_b200_weight_update_count(dpgo_b200_agent_t a);                         /* mWeightUpdateCount, :193 */
+
+/* ---- problem-level evaluation on the device (parity hooks for a3/a5/a6) ------- */
+int dpgo_b200_eval(dpgo_b200_agent_t a, const double *X, double *f, double *egrad, double *rgrad);
+int dpgo_b200_hess(dpgo_b200_agent_t a, const double *X, const double *V, double *out);
+int dpgo_b200_precond(dpgo_b200_agent_t a, const double *X, const double *V, double *out);
+int dpgo_b200_manifold_project(int device, int r, int n, const double *M, double *out);
+int dpgo_b200_tangent_project(int device, int r, int n, const double *X, const double *Z, double *out);
+int dpgo_b200_retract(int device, int r, int n, const double *X, const double *xi, double *out);
+
+/* ---- team: co-located agents, device-side exchange and schedule ---------------
+ * Replays the wrapper's synchronous protocol (UPDATE token RoundRobin,
+ * :464-472; non-selected robots iterate(false), :1185; leader decides
+ * termination / weight update, :207-217) inside ONE persistent kernel.         */
+int dpgo_b200_team_create(int device, dpgo_b200_team_t *out);
+int dpgo_b200_team_destroy(dpgo_b200_team_t t);
+int dpgo_b200_team_add_agent(dpgo_b200_team_t t, dpgo_b200_agent_t a);
+int dpgo_b200_team_exchange_all(dpgo_b200_team_t t);   /* publishPublicPoses for every pair, :662-690 */
+int dpgo_b200_team_run(dpgo_b200_team_t t, int max_iters, int stop_on_terminate, dpgo_b200_run_result *out);
+double dpgo_b200_team_global_cost(dpgo_b200_team_t t, int *status);
+/* tuning knob: CTAs of the persistent kernel (0 = one per SM) */
+int dpgo_b200_team_set_grid(dpgo_b200_team_t t, int num_ctas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPGO_B200_H */

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Tolerances are written next to each assertion; the
+north-star bar is 1e-6 relative Frobenius error on the final iterate and an
+identical iteration count."""
+import numpy as np
+import pytest
+
+from dpgo_ros_b200 import agent as gpu
+from dpgo_ros_b200 import datasets
+from oracle import binding as orc
+from oracle import np_oracle as npo
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(1e-300, np.linalg.norm(np.asarray(b)))
+
+
+def random_point(r, n, seed):
+    rng = np.random.default_rng(seed)
+    return npo.manifold_project(rng.normal(size=(r, 4 * n)))
+
+
+# ------------------------------------------------------------------ manifold kernels (a5)
+@pytest.mark.parametrize("r", [3, 5, 6, 8])
+@pytest.mark.parametrize("n", [1, 7, 312, 5000])
+def test_manifold_ops(r, n):
+    from dpgo_ros_b200 import capi
+    import ctypes as C
+    L = capi.lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(100 * r + n)
+    X = random_point(r, n, r + n)
+    # near-manifold input (the hot-path case) and a far one (Jacobi path)
+    for scale in (0.05, 3.0):
+        M = np.asfortranarray(X + scale * rng.normal(size=X.shape))
+        out = np.zeros_like(M, order="F")
+        assert L.dpgo_b200_manifold_project(0, r, n, M.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        assert rel(out, orc.manifold_project(M)) < 1e-12
+    Z = np.asfortranarray(rng.normal(size=X.shape))
+    Xf = np.asfortranarray(X)
+    out = np.zeros_like(Xf, order="F")
+    assert L.dpgo_b200_tangent_project(0, r, n, Xf.ctypes.data_as(dp), Z.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+    ref = orc.tangent_project(Xf, Z)
+    assert rel(out, ref) < 1e-13
+    xi = np.asfortranarray(0.3 * ref)
+    assert L.dpgo_b200_retract(0, r, n, Xf.ctypes.data_as(dp), xi.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+    assert rel(out, orc.retract(Xf, xi)) < 1e-13
+
+
+def test_manifold_ops_empty():
+    from dpgo_ros_b200 import capi
+    import ctypes as C
+    L = capi.lib()
+    dp = C.POINTER(C.c_double)
+    M = np.zeros((5, 0), order="F")
+    assert L.dpgo_b200_manifold_project(0, 5, 0, M.ctypes.data_as(dp), M.ctypes.data_as(dp)) == 0
+
+
+# ------------------------------------------------------------------ cost / gradient / Hessian / preconditioner (a3, a4, a6)
+@pytest.mark.parametrize("name,robots,r", [("tinyGrid3D", 2, 5), ("smallGrid3D", 2, 5), ("smallGrid3D", 3, 6),
+                                           ("sphere2500", 8, 5)])
+def test_problem_level_parity(name, robots, r):
+    pb = datasets.load_g2o_problem(name, robots)
+    oteam = orc.OracleTeam(pb, r=r)
+    team, agents = gpu.make_team(pb, r=r)
+    for rid in range(robots):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-15
+        X = random_point(r, pb.n[rid], 10 + rid)
+        V = npo.tangent_project(X, np.random.default_rng(rid).normal(size=X.shape))
+        f, eg, rg = agents[rid].eval(X)
+        fo, ego, rgo = oteam.eval(rid, X)
+        assert abs(f - fo) <= 1e-12 * abs(fo)
+        assert rel(eg, ego) < 1e-13
+        assert rel(rg, rgo) < 1e-12
+        assert rel(agents[rid].hess(X, V), oteam.hess(rid, X, V)) < 1e-12
+        # explicit dense inverse vs sparse Cholesky solve: bounded by cond(Q + 0.1 I) * eps
+        assert rel(agents[rid].precond(X, V), oteam.precond(rid, X, V)) < 1e-9
+
+
+# ------------------------------------------------------------------ iterate parity (a1, a2, a7, a9, a10)
+def run_both(pb, iters, check_every=None, **kw):
+    oteam = orc.OracleTeam(pb, **kw)
+    team, agents = gpu.make_team(pb, **kw)
+    return oteam, team, agents
+
+
+@pytest.mark.parametrize("accel", [0, 1])
+def test_rgd_team_matches_oracle_smallgrid(small_problem, accel):
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=accel, restart_interval=7,
+              rel_change_tol=1e-9, max_num_iters=10000)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    for chunk in (1, 1, 3, 8, 17):
+        oteam.run(chunk, stop_on_terminate=False)
+        res = team.run(chunk, stop_on_terminate=False)
+        assert res.iterations == chunk
+        for rid in range(2):
+            assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-10, (chunk, rid)
+            if accel:
+                assert rel(agents[rid].getX(2), oteam.get_x(rid, 2)) < 1e-10
+    o = agents[1].localOptResult()
+    oo = oteam.opt_result(1)
+    assert abs(o.f_init - oo.f_init) < 1e-9 * abs(oo.f_init)
+    assert abs(o.f_opt - oo.f_opt) < 1e-9 * abs(oo.f_opt)
+    assert abs(o.gradnorm_init - oo.gradnorm_init) < 1e-8 * abs(oo.gradnorm_init)
+    assert abs(o.gradnorm_opt - oo.gradnorm_opt) < 1e-8 * abs(oo.gradnorm_opt)
+
+
+def test_rgd_without_preconditioner(small_problem):
+    kw = dict(r=5, method=1, rgd_stepsize=1e-3, rgd_use_preconditioner=0, acceleration=1, restart_interval=50,
+              rel_change_tol=1e-9)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    oteam.run(40, stop_on_terminate=False)
+    team.run(40, stop_on_terminate=False)
+    for rid in range(2):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-11
+
+
+def test_config2_sphere2500_rgd_nesterov_to_convergence(sphere8_problem):
+    """BASELINE config 2: sphere2500, 8 agents, RGD + Nesterov (restart 50), RoundRobin.
+    RGD values from launch/asapp_demo.launch:7-8 (stepsize 0.2, preconditioner on)."""
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=50,
+              rel_change_tol=0.1, max_num_iters=1000)
+    oteam, team, agents = run_both(sphere8_problem, 0, **kw)
+    ores = oteam.run(2000, threads=4)
+    res = team.run(2000)
+    assert ores.terminated and res.terminated
+    assert res.iterations == ores.iterations  # identical iteration-to-convergence count
+    for rid in range(8):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6  # north-star tolerance
+    assert abs(team.global_cost() - oteam.global_cost()) < 1e-8 * oteam.global_cost()
+
+
+def test_rtr_team_matches_oracle_smallgrid(small_problem):
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    for it in range(6):
+        oteam.run(1, stop_on_terminate=False)
+        team.run(1, stop_on_terminate=False)
+        for rid in range(2):
+            assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-8, (it, rid)
+        sel = it % 2
+        assert agents[sel].localOptResult().tcg_iters == oteam.opt_result(sel).tcg_iters
+
+
+def test_rtr_to_convergence_smallgrid(small_problem):
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    ores = oteam.run(1000)
+    res = team.run(1000)
+    assert ores.terminated and res.terminated
+    assert res.iterations == ores.iterations
+    for rid in range(2):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6
+
+
+def test_rtr_accelerated_matches_oracle(small_problem):
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2, acceleration=1, restart_interval=5)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    oteam.run(12, stop_on_terminate=False)
+    team.run(12, stop_on_terminate=False)
+    for rid in range(2):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-7
+
+
+def test_rtr_single_step_mode(small_problem):
+    kw = dict(r=5, method=0, rtr_iterations=1, gradnorm_tol=0.5, rel_change_tol=0.2)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    oteam.run(8, stop_on_terminate=False)
+    team.run(8, stop_on_terminate=False)
+    for rid in range(2):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-8
+
+
+# ------------------------------------------------------------------ standalone agents + host-buffer exchange (drop-in path)
+def test_standalone_agents_with_host_exchange(small_problem):
+    """The per-robot API PGOAgentROS uses: iterate() then getSharedPoseDictWithNeighbor /
+    updateNeighborPoses through host buffers (src/PGOAgentROS.cpp:160,1185,666-668,1276-1278)."""
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=6,
+              rel_change_tol=1e-9)
+    oteam = orc.OracleTeam(small_problem, **kw)
+    _, agents = gpu.make_team(small_problem, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=True)
+    N = 2
+    for it in range(15):
+        sel = it % N
+        for a in agents:
+            if a.id != sel:
+                a.iterate(False)
+        gpu.exchange_host(agents, accel=True, only=[a.id for a in agents if a.id != sel])
+        agents[sel].iterate(True)
+        gpu.exchange_host(agents, accel=True, only=[sel])
+        oteam.run(1, stop_on_terminate=False)
+        for rid in range(N):
+            assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-10, (it, rid)
+        assert agents[sel].iteration_number() == it + 1
+        st = agents[sel].getStatus()
+        assert abs(st.relative_change - oteam.status(sel).relative_change) < 1e-9
+
+
+def test_iterate_without_neighbor_poses_is_refused(small_problem):
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, acceleration=0)
+    _, agents = gpu.make_team(small_problem, colocate=False, **kw)
+    X0 = agents[0].getX()
+    agents[0].iterate(True)  # no neighbour poses yet: data matrices cannot be built
+    assert agents[0].iteration_number() == 1
+    assert rel(agents[0].getX(), X0) == 0.0
+    assert agents[0].localOptResult().success == 0
+
+
+# ------------------------------------------------------------------ GNC-TLS (a8)
+def test_gnc_residuals_and_weights(small_problem):
+    kw = dict(r=5, method=0, cost_type=5, gnc_barc=3.0, gnc_init_mu=1e-3)
+    oteam = orc.OracleTeam(small_problem, **kw)
+    team, agents = gpu.make_team(small_problem, **kw)
+    m = small_problem.robot_measurements(0)
+    lc = np.nonzero(~((m.r1 == m.r2) & (m.p1 + 1 == m.p2)))[0][:20]
+    for e in lc:
+        res = agents[0].computeMeasurementResidual(int(m.r1[e]), int(m.p1[e]), int(m.r2[e]), int(m.p2[e]))
+        assert res is not None and res >= 0
+        w = agents[0].robustWeight(res)
+        assert abs(w - orc.robust_weight(5, 3.0, 1e-3, res)) < 1e-12
+
+
+def test_gnc_team_run_matches_oracle(small_problem):
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2, cost_type=5, gnc_barc=3.0, gnc_mu_step=2.0,
+              gnc_init_mu=1e-5, robust_opt_num_weight_updates=3, robust_opt_num_resets=3, robust_opt_inner_iters=10,
+              max_num_iters=38)
+    oteam, team, agents = run_both(small_problem, 0, **kw)
+    ores = oteam.run(200)
+    res = team.run(200)
+    assert ores.terminated and res.terminated
+    assert res.iterations == ores.iterations
+    assert res.weight_updates == ores.weight_updates == 3
+    for rid in range(2):
+        assert np.max(np.abs(agents[rid].lcWeights() - oteam.lc_weights(rid))) < 1e-7
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6
