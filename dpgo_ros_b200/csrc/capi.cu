@@ -454,5 +454,42 @@ int dpgo_b200_team_set_grid(dpgo_b200_team_t h, int num_ctas) {
   API_END
 }
 
+// ---- diagnostics (not part of the reference surface) ---------------------------------
+int dpgo_b200_debug_barrier_bench(int device, int grid, int iters, int mode, float *ms) {
+  API_BEGIN
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  DevBuf<unsigned long long> bar;
+  DevBuf<double> slots, out;
+  bar.alloc(1);
+  slots.alloc((size_t)2 * grid * kRed);
+  out.alloc(1);
+  GridSync gs{bar.p, slots.p};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cuda_check(launch_barrier_bench(gs, 10, mode, out.p, grid, 0), "barrier_bench warmup");
+  cudaEventRecord(e0, 0);
+  cuda_check(launch_barrier_bench(gs, iters, mode, out.p, grid, 0), "barrier_bench");
+  cudaEventRecord(e1, 0);
+  cuda_check(cudaEventSynchronize(e1), "barrier_bench sync");
+  cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  API_END
+}
+int dpgo_b200_debug_team_profile(dpgo_b200_team_t h, int iters, int cta, long long *out /* iters*16 */) {
+  API_BEGIN
+  Team *t = TT(h);
+  t->prof_iters = iters;
+  t->prof_cta = cta;
+  t->dProf.alloc((size_t)iters * 16);
+  t->team_dirty = true;
+  t->run(iters, false);
+  cuda_check(cudaMemcpy(out, t->dProf.p, sizeof(long long) * iters * 16, cudaMemcpyDeviceToHost), "D2H prof");
+  t->prof_iters = 0;
+  t->team_dirty = true;
+  API_END
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

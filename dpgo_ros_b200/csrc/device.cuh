@@ -32,6 +32,15 @@ struct AgentDev {
   // linear term by output pose: G_j += inbox[slot] * val
   const int *s_rowptr, *s_slot;
   const double *s_val;
+  // ELL copies read by the hot phases: fixed-width slots per pose (-1 padded) + CSR overflow
+  const int *qe_col;      // [n][8]
+  const double *qe_val;   // [n][8][16]
+  const int *qo_rowptr, *qo_col;
+  const double *qo_val;
+  const int *se_slot;     // [n][4]
+  const double *se_val;   // [n][4][16]
+  const int *so_rowptr, *so_slot;
+  const double *so_val;
   // neighbour public poses (regular and auxiliary), r x 4 per slot
   double *inbox_reg, *inbox_aux;
   // publication lists, CSR by my pose: destinations of X (reg) and Y (aux)
@@ -71,9 +80,8 @@ struct TeamCtl {
 };
 
 struct GridSync {
-  unsigned *count;
-  unsigned *gen;
-  double *slots;  // [2][gridDim.x][kRed]
+  unsigned long long *counter;  // monotonically increasing arrival counter
+  double *slots;                // [2][gridDim.x][kRed]
 };
 
 struct TeamDev {
@@ -84,6 +92,9 @@ struct TeamDev {
   SolverParams p;
   GridSync gs;
   TeamCtl *ctl;
+  // optional phase timeline (debug): clock64() of one CTA's thread 0 at phase boundaries
+  long long *prof;
+  int prof_iters, prof_cta;
 };
 
 // ---------------------------------------------------------------------------
@@ -281,22 +292,42 @@ __device__ __forceinline__ void qf_row(double (&x)[4]) {
 
 // ---------------------------------------------------------------------------
 // grid-wide barrier + deterministic reduction (persistent cooperative kernel)
+//
+// One monotonically increasing 64-bit arrival counter (never reset: at kernel
+// start it is a multiple of gridDim.x plus the arrivals of faster CTAs, so the
+// epoch base is (value / gridDim.x) * gridDim.x).  Thread 0 of each CTA arrives
+// with a release reduction and polls with acquire loads -- no sequentially
+// consistent fences (the first version used three __threadfence() per barrier
+// and measured 2.2 us; see profiles/).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(const GridSync &gs) {
+struct BarState {
+  unsigned long long next;  // meaningful in thread 0 only
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void bar_init(const GridSync &gs, BarState &bs) {
+  bs.next = 0;
+  if (threadIdx.x == 0) {
+    const unsigned long long start = ld_acquire_u64(gs.counter);
+    bs.next = (start / gridDim.x) * gridDim.x + gridDim.x;
+  }
+}
+
+__device__ __forceinline__ void grid_barrier(const GridSync &gs, BarState &bs) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned *gen = gs.gen;
-    const unsigned g = *gen;
-    __threadfence();
-    if (atomicAdd(gs.count, 1u) == gridDim.x - 1) {
-      *((volatile unsigned *)gs.count) = 0u;
-      __threadfence();
-      atomicAdd(gs.gen, 1u);
-    } else {
-      while (*gen == g) {
-      }
+    red_release_add_u64(gs.counter, 1ull);
+    while (ld_acquire_u64(gs.counter) < bs.next) {
     }
-    __threadfence();
+    bs.next += gridDim.x;
   }
   __syncthreads();
 }
@@ -304,40 +335,41 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs) {
 // Sum `vals` over every thread of the grid; every thread gets the same totals,
 // summed in a fixed order (bitwise reproducible run to run).  Includes a grid
 // barrier, so it also orders global memory between phases.  `parity` flips on
-// every call (slot double-buffering).
+// every call (slot double-buffering: a fast CTA may start writing the next
+// reduction's slots while a slow one is still reading this one's).
 template <int K>
-__device__ __forceinline__ void grid_reduce(const GridSync &gs, int &parity, double (&vals)[K], double *sm) {
+__device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, int &parity, double (&vals)[K],
+                                            double *sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) vals[k] = wsum32(vals[k]);
-  __syncthreads();  // sm reuse
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) sm[warp * K + k] = vals[k];
   }
-  __syncthreads();
   double *slots = gs.slots + (size_t)parity * gridDim.x * kRed;
+  __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       double s = 0;
+#pragma unroll
       for (int w = 0; w < kThreads / 32; ++w) s += sm[w * K + k];
       slots[(size_t)blockIdx.x * kRed + k] = s;
     }
-  }
-  grid_barrier(gs);
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      double s = 0;
-      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&slots[(size_t)b * kRed + k]);
-      s = wsum32(s);
-      if (lane == 0) sm[k] = s;
+    red_release_add_u64(gs.counter, 1ull);
+    while (ld_acquire_u64(gs.counter) < bs.next) {
     }
+    bs.next += gridDim.x;
   }
   __syncthreads();
+  // every warp sums the per-CTA partials itself, in the same order
 #pragma unroll
-  for (int k = 0; k < K; ++k) vals[k] = sm[k];
+  for (int k = 0; k < K; ++k) {
+    double s = 0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&slots[(size_t)b * kRed + k]);
+    vals[k] = wsum32(s);
+  }
   parity ^= 1;
 }
 

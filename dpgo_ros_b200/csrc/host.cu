@@ -330,6 +330,34 @@ void Agent::build_values() {
     }
   }
   d_q_val.upload(qv);
+  {
+    // ELL(8) copy of Q + overflow
+    constexpr int W = 8;
+    std::vector<int> ec((size_t)n * W, -1), orp(n + 1, 0), oc;
+    std::vector<double> ev((size_t)n * W * 16, 0.0), ov;
+    for (int j = 0; j < n; ++j) {
+      int k = 0;
+      for (int e = h_q_rowptr[j]; e < h_q_rowptr[j + 1]; ++e, ++k) {
+        if (k < W) {
+          ec[(size_t)j * W + k] = h_q_col[e];
+          std::memcpy(&ev[((size_t)j * W + k) * 16], &qv[(size_t)e * 16], 16 * sizeof(double));
+        } else {
+          oc.push_back(h_q_col[e]);
+          ov.insert(ov.end(), qv.begin() + (size_t)e * 16, qv.begin() + (size_t)e * 16 + 16);
+        }
+      }
+      orp[j + 1] = (int)oc.size();
+    }
+    if (oc.empty()) {
+      oc.push_back(0);
+      ov.assign(16, 0.0);
+    }
+    d_qe_col.upload(ec);
+    d_qe_val.upload(ev);
+    d_qo_rowptr.upload(orp);
+    d_qo_col.upload(oc);
+    d_qo_val.upload(ov);
+  }
   // G blocks in the order of h_s_slot (per pose, slc order)
   std::vector<double> sv((size_t)h_s_slot.size() * 16, 0.0);
   {
@@ -352,6 +380,34 @@ void Agent::build_values() {
       }
   }
   d_s_val.upload(sv);
+  {
+    // ELL(4) copy of the neighbour term + overflow
+    constexpr int W = 4;
+    std::vector<int> ec((size_t)n * W, -1), orp(n + 1, 0), oc;
+    std::vector<double> ev((size_t)n * W * 16, 0.0), ov;
+    for (int j = 0; j < n; ++j) {
+      int k = 0;
+      for (int e = h_s_rowptr[j]; e < h_s_rowptr[j + 1]; ++e, ++k) {
+        if (k < W) {
+          ec[(size_t)j * W + k] = h_s_slot[e];
+          std::memcpy(&ev[((size_t)j * W + k) * 16], &sv[(size_t)e * 16], 16 * sizeof(double));
+        } else {
+          oc.push_back(h_s_slot[e]);
+          ov.insert(ov.end(), sv.begin() + (size_t)e * 16, sv.begin() + (size_t)e * 16 + 16);
+        }
+      }
+      orp[j + 1] = (int)oc.size();
+    }
+    if (oc.empty()) {
+      oc.push_back(0);
+      ov.assign(16, 0.0);
+    }
+    d_se_slot.upload(ec);
+    d_se_val.upload(ev);
+    d_so_rowptr.upload(orp);
+    d_so_slot.upload(oc);
+    d_so_val.upload(ov);
+  }
   // loop-closure arrays
   const size_t L = lc_list.size();
   std::vector<int> src(L), dst(L);
@@ -421,6 +477,8 @@ AgentDev Agent::dev_view() const {
   A.X = dX.p; A.Y = dY.p; A.V = dV.p; A.Xinit = dXinit.p;
   A.q_rowptr = d_q_rowptr.p; A.q_col = d_q_col.p; A.q_val = d_q_val.p;
   A.s_rowptr = d_s_rowptr.p; A.s_slot = d_s_slot.p; A.s_val = d_s_val.p;
+  A.qe_col = d_qe_col.p; A.qe_val = d_qe_val.p; A.qo_rowptr = d_qo_rowptr.p; A.qo_col = d_qo_col.p; A.qo_val = d_qo_val.p;
+  A.se_slot = d_se_slot.p; A.se_val = d_se_val.p; A.so_rowptr = d_so_rowptr.p; A.so_slot = d_so_slot.p; A.so_val = d_so_val.p;
   A.inbox_reg = d_inbox_reg.p; A.inbox_aux = d_inbox_aux.p;
   A.pub_rowptr = d_pub_rowptr.p; A.pub_dst_reg = d_pub_dst_reg.p; A.pub_dst_aux = d_pub_dst_aux.p;
   A.Pinv = dPinv.p;
@@ -741,13 +799,15 @@ void Team::prepare() {
   T.p.max_num_iters = P.max_num_iters;
   T.p.rel_change_tol = P.rel_change_tol;
   if (grid <= 0) grid = max_coop_grid(device);
-  dBar.alloc(2);
+  dBar.alloc(1);
   dSlots.alloc((size_t)2 * grid * kRed);
   dCtl.alloc(1);
-  T.gs.count = dBar.p;
-  T.gs.gen = dBar.p + 1;
+  T.gs.counter = dBar.p;
   T.gs.slots = dSlots.p;
   T.ctl = dCtl.p;
+  T.prof = prof_iters > 0 ? dProf.p : nullptr;
+  T.prof_iters = prof_iters;
+  T.prof_cta = prof_cta;
   team_dirty = false;
 }
 
@@ -780,7 +840,7 @@ void Team::read_back() {
 void Team::run_forced(int sel_local) {
   prepare();
   cuda_check(cudaMemcpy(dCtl.p, &ctl, sizeof(TeamCtl), cudaMemcpyHostToDevice), "H2D ctl");
-  RunArgs args{1, sel_local, 0, 0};
+  RunArgs args{1, sel_local, 0, 0, 0};
   cuda_check(launch_team_run(T, args, grid, 0), "launch k_team_run");
   ++launches;
   cuda_check(cudaDeviceSynchronize(), "k_team_run");
@@ -802,7 +862,7 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
   int remaining = max_iters;
   while (remaining > 0) {
     cuda_check(cudaMemcpy(dCtl.p, &ctl, sizeof(TeamCtl), cudaMemcpyHostToDevice), "H2D ctl");
-    RunArgs args{remaining, -2, stop_on_terminate ? 1 : 0, 0};
+    RunArgs args{remaining, -2, stop_on_terminate ? 1 : 0, 0, 0};
     cuda_check(cudaEventRecord(ev0, 0), "eventRecord");
     cuda_check(launch_team_run(T, args, grid, 0), "launch k_team_run");
     cuda_check(cudaEventRecord(ev1, 0), "eventRecord");

@@ -142,6 +142,9 @@ class Agent {
   DevBuf<double> dX, dY, dV, dXinit;
   DevBuf<int> d_q_rowptr, d_q_col, d_s_rowptr, d_s_slot, d_pub_rowptr;
   DevBuf<double> d_q_val, d_s_val;
+  // ELL(8) / ELL(4) copies + CSR overflow read by the hot phases
+  DevBuf<int> d_qe_col, d_qo_rowptr, d_qo_col, d_se_slot, d_so_rowptr, d_so_slot;
+  DevBuf<double> d_qe_val, d_qo_val, d_se_val, d_so_val;
   DevBuf<double> d_inbox_reg, d_inbox_aux, d_outbox_reg, d_outbox_aux;
   DevBuf<double *> d_pub_dst_reg, d_pub_dst_aux;
   DevBuf<double> dPinv;
@@ -181,11 +184,13 @@ class Team {
   TeamDev T{};
   TeamCtl ctl{};
   DevBuf<TeamCtl> dCtl;
-  DevBuf<unsigned> dBar;
+  DevBuf<unsigned long long> dBar;
   DevBuf<double> dSlots;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool team_dirty = true;
   int launches = 0;
+  DevBuf<long long> dProf;
+  int prof_iters = 0, prof_cta = 0;
 };
 
 }  // namespace dpgo

@@ -8,12 +8,21 @@
 //    wrapper's synchronous schedule (src/PGOAgentROS.cpp:160,1185,464-472,207-217).
 //  * single-op kernels backing the parity hooks (eval / hess / precond /
 //    manifold ops) and the GNC-TLS residual+weight kernel (a8).
-#include <cooperative_groups.h>
+#include <algorithm>
 
 #include "kernels.h"
 #include "phases.cuh"
 
 namespace dpgo {
+
+// dynamic shared memory layout of the persistent kernel:
+//   [ slab (slab_cap bytes) | staging tiles (32 groups) | zs (chunk poses x 32) ]
+struct SmemLayout {
+  double *slab;
+  size_t slab_cap;
+  double *stage;
+  double *zs;
+};
 
 // ---------------------------------------------------------------------------
 // pose-local vector phases used by tCG
@@ -142,14 +151,15 @@ __device__ __forceinline__ void phase_commit(const AgentDev &A, const double *X1
     const bool act = valid && it.a < r;
     double xn[4];
     ld4(X1 + (size_t)(valid ? j : 0) * 4 * r, r, it.a, act, xn);
-    finish_pose(A, valid ? j : 0, valid, it.a, xn, accel, restart, gamma, prel);
+    finish_pose(A, valid ? j : 0, valid, it.a, xn, accel, restart, gamma, nullptr, prel);
   }
 }
 
 // ---------------------------------------------------------------------------
 // RTR-tCG local solve (a2), ROPTLIB RTRNewton semantics as restated in
 // oracle/dpgo_oracle.cpp (rtrRun): every scalar decision is taken redundantly
-// by all threads from bit-identical reduced values.
+// by all threads from bit-identical reduced values.  The preconditioner slab
+// of this CTA stays resident in shared memory for the whole solve.
 // ---------------------------------------------------------------------------
 struct RtrOut {
   const double *x;  // final iterate
@@ -158,9 +168,10 @@ struct RtrOut {
 };
 
 template <int R>
-__device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParams &P, const GridSync &gs,
-                                            int &parity, const double *Xs, const double *inbox, double *zs,
-                                            double *red, double *sm) {
+__device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const SolverParams &P, const GridSync &gs,
+                                            BarState &bs, int &parity, const double *Xs, const double *inbox,
+                                            SlabState &ss, uint64_t *mbar, const SmemLayout &L, double *red,
+                                            double *sm) {
   RtrOut out;
   out.outer = out.tcg = out.rej = 0;
   const double *x1 = Xs;
@@ -170,8 +181,8 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParam
   double v[4];
   // gradient at the starting point (also assembles G)
   v[0] = v[1] = v[2] = v[3] = 0;
-  phase_grad(A, x1, inbox, true, S1, Rg1, Rg1T, nullptr, v[0], v[1]);
-  grid_reduce<2>(gs, parity, reinterpret_cast<double(&)[2]>(v), sm);
+  phase_grad(A, x1, inbox, true, S1, Rg1, Rg1T, nullptr, L.stage, v[0], v[1]);
+  grid_reduce<2>(gs, bs, parity, reinterpret_cast<double(&)[2]>(v), sm);
   double f1 = v[0], ngf = sqrt(v[1]);
   out.f_init = f1;
   out.gn_init = ngf;
@@ -187,16 +198,16 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParam
     const double *rsrc = Rg1, *rsrcT = Rg1T;
     const double norm_r0 = ngf;
     v[0] = 0;
-    phase_precond<R>(A, x1, rsrc, rsrcT, A.Z, A.dlt0, zs, red, v[0]);
-    grid_reduce<1>(gs, parity, reinterpret_cast<double(&)[1]>(v), sm);
+    phase_precond<R>(A, ai, x1, rsrc, rsrcT, A.Z, A.dlt0, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
+    grid_reduce<1>(gs, bs, parity, reinterpret_cast<double(&)[1]>(v), sm);
     double z_r = v[0], d_Pd = z_r, e_Pe = 0.0, e_Pd = 0.0;
     bool eta_zero = true;
     int status = 4;  // 0 negcurv, 1 exceeded, 2 lcon, 3 scon, 4 maxiter
     int j = 0;
     for (j = 0; j < P.rtr_tcg_iterations; ++j) {
       v[0] = 0;
-      phase_hess(A, x1, S1, A.dlt0, A.Hd, v[0]);
-      grid_reduce<1>(gs, parity, reinterpret_cast<double(&)[1]>(v), sm);
+      phase_hess(A, x1, S1, A.dlt0, A.Hd, L.stage, v[0]);
+      grid_reduce<1>(gs, bs, parity, reinterpret_cast<double(&)[1]>(v), sm);
       const double d_Hd = v[0];
       const double alpha = z_r / d_Hd;
       const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
@@ -211,7 +222,7 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParam
       v[0] = 0;
       phase_tcg_update(A, alpha, eta_zero, A.dlt0, A.Hd, rsrc, A.eta, A.rv, A.rvT, v[0]);
       eta_zero = false;
-      grid_reduce<1>(gs, parity, reinterpret_cast<double(&)[1]>(v), sm);
+      grid_reduce<1>(gs, bs, parity, reinterpret_cast<double(&)[1]>(v), sm);
       rsrc = A.rv;
       rsrcT = A.rvT;
       const double norm_r = sqrt(v[0]);
@@ -221,13 +232,13 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParam
         break;
       }
       v[0] = 0;
-      phase_precond<R>(A, x1, rsrc, rsrcT, A.Z, nullptr, zs, red, v[0]);
-      grid_reduce<1>(gs, parity, reinterpret_cast<double(&)[1]>(v), sm);
+      phase_precond<R>(A, ai, x1, rsrc, rsrcT, A.Z, nullptr, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
+      grid_reduce<1>(gs, bs, parity, reinterpret_cast<double(&)[1]>(v), sm);
       const double zold_rold = z_r;
       z_r = v[0];
       const double beta = z_r / zold_rold;
       phase_direction(A, beta, A.Z, A.dlt0);
-      grid_barrier(gs);
+      grid_barrier(gs, bs);
       e_Pd = beta * (e_Pd + alpha * d_Pd);
       d_Pd = z_r + beta * beta * d_Pd;
     }
@@ -235,15 +246,15 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParam
     if (eta_zero) {  // maxInner == 0: eta = 0
       phase_axpy_eta(A, 0.0, true, A.dlt0, A.eta);
     }
-    grid_barrier(gs);
+    grid_barrier(gs, bs);
     // ---------------- candidate, model decrease, ratio
     phase_retract(A, x1, A.eta, cand);
-    grid_barrier(gs);
+    grid_barrier(gs, bs);
     v[0] = v[1] = v[2] = v[3] = 0;
-    phase_grad(A, cand, inbox, false, S2, Rg2, Rg2T, nullptr, v[0], v[1]);
-    phase_hess(A, x1, S1, A.eta, A.zeta, v[2]);
+    phase_grad(A, cand, inbox, false, S2, Rg2, Rg2T, nullptr, L.stage, v[0], v[1]);
+    phase_hess(A, x1, S1, A.eta, A.zeta, L.stage, v[2]);
     phase_dot(A, A.eta, Rg1, v[3]);
-    grid_reduce<4>(gs, parity, v, sm);
+    grid_reduce<4>(gs, bs, parity, v, sm);
     const double f2 = v[0];
     const double rho = (f1 - f2) / (-(v[3] + 0.5 * v[2]));
     if (rho > 0.75) {
@@ -288,21 +299,37 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, const SolverParam
 template <int R>
 __global__ void __launch_bounds__(kThreads, 1)
     k_team_run(const __grid_constant__ TeamDev T, const __grid_constant__ RunArgs args) {
-  extern __shared__ double dyn_smem[];
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
   __shared__ double sm_red[64];
-  __shared__ double sm_slab[8 * 8 * 8];
-  double *zs = dyn_smem;
+  __shared__ double sm_slab[8 * 16 * 8];
+  __shared__ __align__(8) uint64_t mbar;
+  SmemLayout L;
+  L.slab = reinterpret_cast<double *>(dyn_smem_raw);
+  L.slab_cap = args.slab_cap;
+  L.stage = reinterpret_cast<double *>(dyn_smem_raw + args.slab_cap);
+  L.zs = L.stage + kGroupsPerCta * kStageStride;
   const SolverParams &P = T.p;
   const GridSync &gs = T.gs;
+  if (threadIdx.x == 0) mbar_init(&mbar);
+  __syncthreads();
+  SlabState ss{-1, 0u, 0};
+  BarState bs;
+  bar_init(gs, bs);
   // control state: identical in every thread
   TeamCtl c = *T.ctl;
   int parity = 0;
   const int N = T.num_robots;
   const bool accel = P.acceleration != 0;
+  const bool use_slab = (P.method == 0) || P.rgd_use_precond;
   int done = 0;
   int stop_reason = 0;
+  int pend_ai = -1;  // RGD: agent whose post-step statistics (fOpt, gradNormOpt) are still due
+#define PROF(k)                                                                                       \
+  if (T.prof && step < T.prof_iters && threadIdx.x == 0 && (int)blockIdx.x == T.prof_cta)             \
+    T.prof[step * 16 + (k)] = clock64();
   for (int step = 0; step < args.max_iters; ++step) {
     const int iter = c.iter + 1;
+    PROF(0)
     int sel_robot, sel_local;
     if (args.force_selected >= -1) {
       sel_local = args.force_selected;
@@ -317,42 +344,65 @@ __global__ void __launch_bounds__(kThreads, 1)
       gamma = (1.0 + sqrt(1.0 + 4.0 * (double)N * N * gamma * gamma)) / (2.0 * N);
       alpha = 1.0 / (gamma * N);
       phase_nesterov(T, sel_local, restart, alpha);
-      grid_barrier(gs);
+      PROF(1)
+      grid_barrier(gs, bs);
+      PROF(2)
     }
     if (sel_local >= 0) {
       const AgentDev &A = T.ag[sel_local];
       const bool use_aux = accel && !restart;
       const double *Xs = use_aux ? A.Y : A.X;
       const double *inbox = use_aux ? A.inbox_aux : A.inbox_reg;
+      if (use_slab) slab_prefetch(A, sel_local, ss, &mbar, L.slab, L.slab_cap);  // no-op when already in flight
       double v[4] = {0, 0, 0, 0};
-      double f_init, gn_init, f_opt, gn_opt;
-      int tcg = 0, outer = 0, rej = 0;
       double rel2;
       if (P.method == 1) {
-        // ---- RGD (a2): gradient, preconditioned step, retraction
-        phase_grad(A, Xs, inbox, true, nullptr, A.Rg, A.RgT, nullptr, v[0], v[1]);
-        grid_reduce<2>(gs, parity, reinterpret_cast<double(&)[2]>(v), sm_red);
-        f_init = v[0];
-        gn_init = sqrt(v[1]);
+        // ---- RGD (a2): gradient (+ the previous step's deferred statistics), preconditioned step
+        phase_grad(A, Xs, inbox, true, nullptr, A.Rg, A.RgT, nullptr, L.stage, v[0], v[1]);
+        if (pend_ai >= 0) {
+          const AgentDev &B = T.ag[pend_ai];
+          phase_grad(B, B.X2, nullptr, false, nullptr, nullptr, nullptr, nullptr, L.stage, v[2], v[3]);
+        }
+        PROF(3)
+        grid_reduce<4>(gs, bs, parity, v, sm_red);
+        PROF(4)
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+          A.stat->f_init = v[0];
+          A.stat->gn_init = sqrt(v[1]);
+          if (pend_ai >= 0) {
+            T.ag[pend_ai].stat->f_opt = v[2];
+            T.ag[pend_ai].stat->gn_opt = sqrt(v[3]);
+          }
+        }
         v[0] = 0;
-        phase_rgd_step<R>(A, P, Xs, accel, restart, gamma, zs, sm_slab, v[0]);
-        grid_reduce<1>(gs, parity, reinterpret_cast<double(&)[1]>(v), sm_red);
+        phase_rgd_step<R>(A, sel_local, P, Xs, accel, restart, gamma, ss, &mbar, L.slab, L.slab_cap, L.zs, sm_slab,
+                          A.X2, v[0]);
+        // the next agent's slab is fetched while the remaining phases run
+        if (use_slab && args.force_selected < -1) {
+          const int nxt = T.local_of_robot[(sel_robot + 1) % N];
+          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, &mbar, L.slab, L.slab_cap);
+        }
+        PROF(5)
+        grid_reduce<1>(gs, bs, parity, reinterpret_cast<double(&)[1]>(v), sm_red);
+        PROF(6)
         rel2 = v[0];
-        // statistics after optimisation: fOpt, gradNormOpt (mLocalOptResult, :169-172)
-        v[0] = v[1] = 0;
-        phase_grad(A, A.X, inbox, false, nullptr, nullptr, nullptr, nullptr, v[0], v[1]);
-        grid_reduce<2>(gs, parity, reinterpret_cast<double(&)[2]>(v), sm_red);
-        f_opt = v[0];
-        gn_opt = sqrt(v[1]);
+        pend_ai = sel_local;
       } else {
         // ---- RTR (a2)
-        const RtrOut ro = rtr_solve<R>(A, P, gs, parity, Xs, inbox, zs, sm_slab, sm_red);
-        f_init = ro.f_init; gn_init = ro.gn_init; f_opt = ro.f_opt; gn_opt = ro.gn_opt;
-        tcg = ro.tcg; outer = ro.outer; rej = ro.rej;
+        const RtrOut ro = rtr_solve<R>(A, sel_local, P, gs, bs, parity, Xs, inbox, ss, &mbar, L, sm_slab, sm_red);
         v[0] = 0;
         phase_commit(A, ro.x, accel, restart, gamma, v[0]);
-        grid_reduce<1>(gs, parity, reinterpret_cast<double(&)[1]>(v), sm_red);
+        if (args.force_selected < -1) {
+          const int nxt = T.local_of_robot[(sel_robot + 1) % N];
+          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, &mbar, L.slab, L.slab_cap);
+        }
+        grid_reduce<1>(gs, bs, parity, reinterpret_cast<double(&)[1]>(v), sm_red);
         rel2 = v[0];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+          AgentStat *st = A.stat;
+          st->f_init = ro.f_init; st->f_opt = ro.f_opt; st->gn_init = ro.gn_init; st->gn_opt = ro.gn_opt;
+          st->tcg_iters = ro.tcg; st->rtr_outer = ro.outer; st->rtr_rej = ro.rej;
+        }
       }
       const double relchange = sqrt(rel2 / A.n);
       const bool ready = !(relchange > P.rel_change_tol);
@@ -363,9 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (blockIdx.x == 0 && threadIdx.x == 0) {
         AgentStat *st = A.stat;
         st->relchange = relchange;
-        st->f_init = f_init; st->f_opt = f_opt; st->gn_init = gn_init; st->gn_opt = gn_opt;
-        st->ready = ready; st->optimized = 1;
-        st->tcg_iters = tcg; st->rtr_outer = outer; st->rtr_rej = rej;
+        st->ready = ready;
+        st->optimized = 1;
       }
     }
     if (restart) {
@@ -399,11 +448,42 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  if (pend_ai >= 0) {
+    // statistics of the last RGD step (mLocalOptResult.fOpt / gradNormOpt, src/PGOAgentROS.cpp:169-172)
+    const AgentDev &B = T.ag[pend_ai];
+    double v[2] = {0, 0};
+    phase_grad(B, B.X2, nullptr, false, nullptr, nullptr, nullptr, nullptr, L.stage, v[0], v[1]);
+    grid_reduce<2>(gs, bs, parity, v, sm_red);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      B.stat->f_opt = v[0];
+      B.stat->gn_opt = sqrt(v[1]);
+    }
+  }
+  if (ss.pending) slab_wait(&mbar, ss.parity);  // do not exit with a bulk copy in flight
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     c.stop_reason = stop_reason;
     c.iters_done = done;
     *T.ctl = c;
   }
+}
+
+// barrier / reduction micro-benchmark (diagnostics)
+__global__ void __launch_bounds__(kThreads, 1) k_barrier_bench(GridSync gs, int iters, int mode, double *out) {
+  __shared__ double sm[64];
+  int parity = 0;
+  BarState bs;
+  bar_init(gs, bs);
+  double v[2] = {1.0, 2.0};
+  for (int i = 0; i < iters; ++i) {
+    if (mode == 0) {
+      grid_barrier(gs, bs);
+    } else {
+      v[0] = 1.0;
+      v[1] = 2.0;
+      grid_reduce<2>(gs, bs, parity, v, sm);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = v[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -412,8 +492,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ AgentDev A, const double *X,
                                                    const double *inbox, double *egrad, double *rgrad,
                                                    double *partials /* [grid][2] */) {
+  __shared__ double stage[kGroupsPerCta * kStageStride];
   double pf = 0, pg2 = 0;
-  phase_grad(A, X, inbox, true, A.S, rgrad, A.RgT, egrad, pf, pg2);
+  phase_grad(A, X, inbox, true, A.S, rgrad, A.RgT, egrad, stage, pf, pg2);
   __shared__ double sm[2 * (kThreads / 32)];
   pf = wsum32(pf);
   pg2 = wsum32(pg2);
@@ -436,8 +517,9 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ Agent
 
 __global__ void __launch_bounds__(kThreads) k_hess(const __grid_constant__ AgentDev A, const double *X,
                                                    const double *V, double *out) {
+  __shared__ double stage[kGroupsPerCta * kStageStride];
   double p = 0;
-  phase_hess(A, X, A.S, V, out, p);
+  phase_hess(A, X, A.S, V, out, stage, p);
 }
 
 // rows of V (r x 4n col-major) -> VT ([r][4n])
@@ -451,11 +533,18 @@ __global__ void k_transpose_rows(const double *V, double *VT, int r, int n4) {
 
 template <int R>
 __global__ void __launch_bounds__(kThreads) k_precond(const __grid_constant__ AgentDev A, const double *X,
-                                                      const double *V, const double *VT, double *out) {
-  extern __shared__ double dyn_smem[];
-  __shared__ double sm_slab[8 * 8 * 8];
+                                                      const double *V, const double *VT, double *out,
+                                                      size_t slab_cap) {
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
+  __shared__ double sm_slab[8 * 16 * 8];
+  __shared__ __align__(8) uint64_t mbar;
+  double *slab = reinterpret_cast<double *>(dyn_smem_raw);
+  double *zs = reinterpret_cast<double *>(dyn_smem_raw + slab_cap);
+  if (threadIdx.x == 0) mbar_init(&mbar);
+  __syncthreads();
+  SlabState ss{-1, 0u, 0};
   double p = 0;
-  phase_precond<R>(A, X, V, VT, out, nullptr, dyn_smem, sm_slab, p);
+  phase_precond<R>(A, 0, X, V, VT, out, nullptr, ss, &mbar, slab, slab_cap, zs, sm_slab, p);
 }
 
 __global__ void __launch_bounds__(kThreads) k_manifold_op(int op, int r, int n, const double *Ain, const double *Bin,
@@ -558,15 +647,25 @@ __global__ void k_gnc_weights(LcDev L, int r, const double *X, const double *inb
 static long long g_launches = 0;
 long long kernel_launch_count() { return g_launches; }
 
-static size_t run_smem_bytes(const TeamDev &T, int grid) {
-  int chunk = 1;
-  for (int i = 0; i < T.num_local; ++i) chunk = max(chunk, (T.ag[i].n + grid - 1) / grid);
-  return (size_t)chunk * 32 * sizeof(double);
+constexpr size_t kMaxDynSmem = 227 * 1024 - 10 * 1024;  // leave room for the static arrays
+
+// slab capacity + total dynamic bytes for a team / agent
+static void smem_plan(int max_n, int grid, bool want_slab, size_t &slab_cap, size_t &total) {
+  const size_t chunk = (size_t)std::max(1, (max_n + grid - 1) / grid);
+  const size_t fixed = (size_t)kGroupsPerCta * kStageStride * sizeof(double) + chunk * 32 * sizeof(double);
+  slab_cap = 0;
+  if (want_slab && fixed + 16 * 1024 < kMaxDynSmem) slab_cap = ((kMaxDynSmem - fixed) / 128) * 128;
+  total = slab_cap + fixed;
 }
 
 template <int R>
-static cudaError_t launch_run_t(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
-  const size_t smem = run_smem_bytes(T, grid);
+static cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream) {
+  int max_n = 1;
+  for (int i = 0; i < T.num_local; ++i) max_n = std::max(max_n, T.ag[i].n);
+  const bool want_slab = (T.p.method == 0) || T.p.rgd_use_precond;
+  size_t slab_cap, smem;
+  smem_plan(max_n, grid, want_slab, slab_cap, smem);
+  args.slab_cap = slab_cap;
   cudaError_t err = cudaFuncSetAttribute(k_team_run<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   void *params[] = {(void *)&T, (void *)&args};
@@ -587,6 +686,11 @@ int max_coop_grid(int device) {
   return sms;
 }
 
+cudaError_t launch_barrier_bench(const GridSync &gs, int iters, int mode, double *out, int grid, cudaStream_t s) {
+  void *params[] = {(void *)&gs, (void *)&iters, (void *)&mode, (void *)&out};
+  return cudaLaunchCooperativeKernel((void *)k_barrier_bench, dim3(grid), dim3(kThreads), params, 0, s);
+}
+
 cudaError_t launch_eval(const AgentDev &A, const double *X, const double *inbox, double *egrad, double *rgrad,
                         double *partials, int grid, cudaStream_t s) {
   ++g_launches;
@@ -604,17 +708,25 @@ cudaError_t launch_transpose_rows(const double *V, double *VT, int r, int n4, cu
   k_transpose_rows<<<(total + 255) / 256, 256, 0, s>>>(V, VT, r, n4);
   return cudaGetLastError();
 }
+
+template <int R>
+static cudaError_t launch_precond_t(const AgentDev &A, const double *X, const double *V, const double *VT,
+                                    double *out, int grid, cudaStream_t s) {
+  const size_t chunk = (size_t)std::max(1, (A.n + grid - 1) / grid);
+  const size_t zs_bytes = chunk * 32 * sizeof(double);
+  size_t slab_cap = ((kMaxDynSmem - zs_bytes) / 128) * 128;
+  const size_t smem = slab_cap + zs_bytes;
+  cudaError_t err = cudaFuncSetAttribute(k_precond<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  k_precond<R><<<grid, kThreads, smem, s>>>(A, X, V, VT, out, slab_cap);
+  return cudaGetLastError();
+}
 cudaError_t launch_precond(const AgentDev &A, const double *X, const double *V, const double *VT, double *out,
                            int grid, cudaStream_t s) {
   ++g_launches;
-  const size_t smem = (size_t)((A.n + grid - 1) / grid) * 32 * sizeof(double);
-  if (A.r == 5)
-    k_precond<5><<<grid, kThreads, smem, s>>>(A, X, V, VT, out);
-  else if (A.r == 6)
-    k_precond<6><<<grid, kThreads, smem, s>>>(A, X, V, VT, out);
-  else
-    k_precond<8><<<grid, kThreads, smem, s>>>(A, X, V, VT, out);
-  return cudaGetLastError();
+  if (A.r == 5) return launch_precond_t<5>(A, X, V, VT, out, grid, s);
+  if (A.r == 6) return launch_precond_t<6>(A, X, V, VT, out, grid, s);
+  return launch_precond_t<8>(A, X, V, VT, out, grid, s);
 }
 cudaError_t launch_manifold_op(int op, int r, int n, const double *A, const double *B, double *out, int grid,
                                cudaStream_t s) {

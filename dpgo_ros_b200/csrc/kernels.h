@@ -11,6 +11,7 @@ struct RunArgs {
   int force_selected;  // -2: follow the RoundRobin schedule; -1: nobody optimises; >= 0: that local agent
   int stop_on_terminate;
   int leader;          // robot id whose turn triggers the termination / weight-update test
+  size_t slab_cap;     // bytes of shared memory reserved for the preconditioner slab (set by the launcher)
 };
 
 // non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel
@@ -35,6 +36,7 @@ cudaError_t launch_precond(const AgentDev &A, const double *X, const double *V, 
                            int grid, cudaStream_t s);
 cudaError_t launch_manifold_op(int op, int r, int n, const double *A, const double *B, double *out, int grid,
                                cudaStream_t s);
+cudaError_t launch_barrier_bench(const GridSync &gs, int iters, int mode, double *out, int grid, cudaStream_t s);
 cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s);
 cudaError_t launch_gnc_weights(const LcDev &L, int r, const double *X, const double *inbox, double barc_sq,
                                double mu, int cost_type, cudaStream_t s);

@@ -3,6 +3,16 @@
 // grid_barrier / grid_reduce in the persistent kernel (kernels.cu) or by kernel
 // boundaries in the single-op kernels that back the parity hooks.
 //
+// Everything here is latency-bound (a 312-pose agent is ~200 KB of work spread
+// over 148 SMs), so the code is organised around the number of DEPENDENT memory
+// round trips per phase (~600 cycles each to L2), not around bytes:
+//   * sparse phases read an ELL(8) copy of Q: slot columns and 4x4 blocks of a
+//     pose sit at fixed addresses, so a pose costs two trips (indices+blocks,
+//     then the gathered poses) instead of a CSR pointer chase per block;
+//   * the dense preconditioner slab of a CTA is fetched by ONE TMA bulk copy
+//     (cp.async.bulk -> shared memory, mbarrier completion) that is issued an
+//     iteration ahead, so its HBM/L2 latency is off the critical path.
+//
 // Reference call sites (relative to the reference repo): the arithmetic lives
 // in the un-vendored mit-acl/dpgo; what is cited is the wrapper line that
 // triggers it.  iterate(): src/PGOAgentROS.cpp:160,1185.
@@ -34,15 +44,22 @@ __device__ __forceinline__ void publish(const int *rowptr, double *const *dst, i
   const int e0 = rowptr[j], e1 = rowptr[j + 1];
   for (int e = e0; e < e1; ++e) st4(dst[e], r, a, act, x);
 }
+__device__ __forceinline__ void publish_range(int e0, int e1, double *const *dst, int r, int a, bool act,
+                                              const double (&x)[4]) {
+  for (int e = e0; e < e1; ++e) st4(dst[e], r, a, act, x);
+}
 
 // out_row(1x4) += x_row(1x4) * B(4x4 col-major)
-__device__ __forceinline__ void row_times_block(const double (&x)[4], const double *__restrict__ B, double (&acc)[4]) {
+__device__ __forceinline__ void row_times_block(const double (&x)[4], const double *B, double (&acc)[4]) {
 #pragma unroll
   for (int cp = 0; cp < 4; ++cp) {
     const double b0 = B[cp * 4 + 0], b1 = B[cp * 4 + 1], b2 = B[cp * 4 + 2], b3 = B[cp * 4 + 3];
     acc[cp] = fma(x[0], b0, fma(x[1], b1, fma(x[2], b2, fma(x[3], b3, acc[cp]))));
   }
 }
+
+// shuffle within the 8-lane group
+__device__ __forceinline__ int gshfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
 
 // ---------------------------------------------------------------------------
 // Phase A -- Nesterov bookkeeping of iterate() for every local agent (a7):
@@ -67,13 +84,18 @@ __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, 
     const bool act = valid && it.a < r;
     const size_t off = (size_t)j * 4 * r;
     double x[4], v[4], m[4];
+    int pe0 = 0, pe1 = 0;
+    if (valid) {
+      pe0 = A.pub_rowptr[j];
+      pe1 = A.pub_rowptr[j + 1];
+    }
     ld4(A.X + off, r, it.a, act, x);
     if (restart) {
       if (ai != sel_local && valid) {
         st4(A.V + off, r, it.a, act, x);
         st4(A.Y + off, r, it.a, act, x);
-        publish(A.pub_rowptr, A.pub_dst_aux, j, r, it.a, act, x);
-        publish(A.pub_rowptr, A.pub_dst_reg, j, r, it.a, act, x);
+        publish_range(pe0, pe1, A.pub_dst_aux, r, it.a, act, x);
+        publish_range(pe0, pe1, A.pub_dst_reg, r, it.a, act, x);
       }
       continue;
     }
@@ -88,28 +110,78 @@ __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, 
     stiefel_project_row(m);
     if (valid) {
       st4(A.Y + off, r, it.a, act, m);
-      publish(A.pub_rowptr, A.pub_dst_aux, j, r, it.a, act, m);
+      publish_range(pe0, pe1, A.pub_dst_aux, r, it.a, act, m);
       if (ai != sel_local) {
         st4(A.X + off, r, it.a, act, m);
-        publish(A.pub_rowptr, A.pub_dst_reg, j, r, it.a, act, m);
+        publish_range(pe0, pe1, A.pub_dst_reg, r, it.a, act, m);
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------
+// Sparse gather for one pose: acc += sum over the pose's ELL slots (and CSR
+// overflow) of  V_{col} * block.  Two dependent round trips: (slot columns +
+// blocks) then (gathered rows).  The 4x4 blocks are staged through a per-group
+// shared-memory tile because every lane needs all 16 entries of every block.
+//   W      : ELL width (8 for Q, 4 for the neighbour term)
+//   stage  : this group's staging tile, W*16 doubles
+// ---------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void ell_gather(const int *ell_col, const double *ell_val, const int *ovf_rowptr,
+                                           const int *ovf_col, const double *ovf_val, const double *Vsrc, int j,
+                                           bool valid, int r, int a, bool act, double *stage, double (&acc)[4]) {
+  // trip 1: my slot's column, my share of the blocks, the overflow range
+  const int mycol = (valid && a < W) ? ell_col[(size_t)j * W + a] : -1;
+  int o0 = 0, o1 = 0;
+  if (valid) {
+    o0 = ovf_rowptr[j];
+    o1 = ovf_rowptr[j + 1];
+  }
+  double2 bq[W];
+  const double2 *bsrc = reinterpret_cast<const double2 *>(ell_val + (size_t)(valid ? j : 0) * W * 16);
+#pragma unroll
+  for (int k = 0; k < W; ++k) bq[k] = valid ? bsrc[k * 8 + a] : make_double2(0.0, 0.0);
+  double2 *st2 = reinterpret_cast<double2 *>(stage);
+#pragma unroll
+  for (int k = 0; k < W; ++k) st2[k * 8 + a] = bq[k];
+  // trip 2: the gathered rows
+  double xi[W][4];
+  int cols[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    cols[k] = gshfl(mycol, k);
+    ld4(Vsrc + (size_t)(cols[k] >= 0 ? cols[k] : 0) * 4 * r, r, a, act && cols[k] >= 0, xi[k]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < W; ++k)
+    if (cols[k] >= 0) row_times_block(xi[k], stage + k * 16, acc);
+  __syncwarp();
+  // overflow (poses with more than W blocks): plain CSR walk
+  for (int e = o0; e < o1; ++e) {
+    double xo[4];
+    ld4(Vsrc + (size_t)ovf_col[e] * 4 * r, r, a, act, xo);
+    row_times_block(xo, ovf_val + (size_t)e * 16, acc);
+  }
+}
+
+constexpr int kStageStride = 8 * 16 + 4;  // doubles per group staging tile (+4: de-conflict the 4 groups of a warp)
+
+// ---------------------------------------------------------------------------
 // Cost / gradient (a3, a4): egrad = Xin Q + G, rgrad = Proj_Xin(egrad),
 // f = 0.5 <Xin Q, Xin> + <G, Xin>.  G is (re)assembled from the inbox when
 // build_g (a4: "G rebuilt every iteration", updateNeighborPoses :1276).
 // Writes G (if build_g), S = sym(Y^T egrad_Y) per pose, Rg and its row-major
-// copy RgT.  Accumulates partial f and |rgrad|^2 into part[0], part[1].
+// copy RgT.  Accumulates partial f and |rgrad|^2.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin,
-                                           const double *inbox, bool build_g, double *Sout,
-                                           double *Rgout, double *RgTout, double *egrad_out, double &pf, double &pg2) {
+__device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin, const double *inbox, bool build_g,
+                                           double *Sout, double *Rgout, double *RgTout, double *egrad_out,
+                                           double *stage_all, double &pf, double &pg2) {
   PoseIter it;
   const int n = A.n, r = A.r;
   const size_t n4 = (size_t)4 * n;
+  double *stage = stage_all + (size_t)it.lg * kStageStride;
   int j;
   while (it.next(n, j)) {
     const bool valid = j < n;
@@ -117,24 +189,12 @@ __device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin,
     const size_t off = (size_t)(valid ? j : 0) * 4 * r;
     double x[4], accq[4] = {0, 0, 0, 0}, accg[4] = {0, 0, 0, 0};
     ld4(Xin + off, r, it.a, act, x);
-    if (valid) {
-      const int e0 = A.q_rowptr[j], e1 = A.q_rowptr[j + 1];
-      for (int e = e0; e < e1; ++e) {
-        double xi[4];
-        ld4(Xin + (size_t)A.q_col[e] * 4 * r, r, it.a, act, xi);
-        row_times_block(xi, A.q_val + (size_t)e * 16, accq);
-      }
-      if (build_g) {
-        const int s0 = A.s_rowptr[j], s1 = A.s_rowptr[j + 1];
-        for (int e = s0; e < s1; ++e) {
-          double xi[4];
-          ld4(inbox + (size_t)A.s_slot[e] * 4 * r, r, it.a, act, xi);
-          row_times_block(xi, A.s_val + (size_t)e * 16, accg);
-        }
-        st4(A.G + off, r, it.a, act, accg);
-      } else {
-        ld4(A.G + off, r, it.a, act, accg);
-      }
+    if (!build_g) ld4(A.G + off, r, it.a, act, accg);
+    ell_gather<8>(A.qe_col, A.qe_val, A.qo_rowptr, A.qo_col, A.qo_val, Xin, j, valid, r, it.a, act, stage, accq);
+    if (build_g) {
+      ell_gather<4>(A.se_slot, A.se_val, A.so_rowptr, A.so_slot, A.so_val, inbox, j, valid, r, it.a, act, stage,
+                    accg);
+      st4(A.G + off, r, it.a, act, accg);
     }
     double eg[4];
 #pragma unroll
@@ -166,11 +226,11 @@ __device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin,
 //   H = Proj_Xbase( V Q - V_Y * S ),  S = sym(Y^T egrad_Y) cached per pose.
 // pvh accumulates <V, H>.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void phase_hess(const AgentDev &A, const double *Xbase,
-                                           const double *S, const double *Vin,
-                                           double *Hout, double &pvh) {
+__device__ __forceinline__ void phase_hess(const AgentDev &A, const double *Xbase, const double *S,
+                                           const double *Vin, double *Hout, double *stage_all, double &pvh) {
   PoseIter it;
   const int n = A.n, r = A.r;
+  double *stage = stage_all + (size_t)it.lg * kStageStride;
   int j;
   while (it.next(n, j)) {
     const bool valid = j < n;
@@ -181,15 +241,10 @@ __device__ __forceinline__ void phase_hess(const AgentDev &A, const double *Xbas
     ld4(Vin + off, r, it.a, act, v);
     Sym3 Sj = {0, 0, 0, 0, 0, 0};
     if (valid) {
-      const int e0 = A.q_rowptr[j], e1 = A.q_rowptr[j + 1];
-      for (int e = e0; e < e1; ++e) {
-        double vi[4];
-        ld4(Vin + (size_t)A.q_col[e] * 4 * r, r, it.a, act, vi);
-        row_times_block(vi, A.q_val + (size_t)e * 16, h);
-      }
       const double *s = S + (size_t)j * 6;
       Sj.a00 = s[0]; Sj.a01 = s[1]; Sj.a02 = s[2]; Sj.a11 = s[3]; Sj.a12 = s[4]; Sj.a22 = s[5];
     }
+    ell_gather<8>(A.qe_col, A.qe_val, A.qo_rowptr, A.qo_col, A.qo_val, Vin, j, valid, r, it.a, act, stage, h);
     sub_y_sym(v, Sj, h);
     tangent_project_row(x, h);
 #pragma unroll
@@ -199,94 +254,43 @@ __device__ __forceinline__ void phase_hess(const AgentDev &A, const double *Xbas
 }
 
 // ---------------------------------------------------------------------------
-// Dense preconditioner slab (a6):  Z[:, cols] = V * Pinv[:, cols] for the
-// columns of poses [p0, p0+np) -- this CTA's share.  V is read through its
-// row-major copy VT ([R][n4]) so lanes read consecutive q; Pinv is column-major
-// with leading dimension ldp, so the same holds for it.  Result goes to shared
-// memory zs[pose_local][c][8].  Thread q-strided accumulation, then a
-// reduce-scatter over the warp and a cross-warp sum.
+// Dense preconditioner (a6):  Z[:, cols] = V * Pinv[:, cols] for the columns
+// of this CTA's poses.  Pinv is column-major with leading dimension ldp, so a
+// CTA's slab (4 np consecutive columns) is ONE contiguous block -> one TMA bulk
+// copy into shared memory.
 // ---------------------------------------------------------------------------
-template <int R>
-__device__ __forceinline__ void dense_slab(const double *__restrict__ Pinv, size_t ldp,
-                                           const double *VT, int r, int n4, int p0, int np, double *zs,
-                                           double *red /* smem [8 warps][8 cols][8] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int sub = 0; sub < np; sub += 2) {
-    const int ncols = min(2, np - sub) * 4;
-    const size_t col0 = (size_t)4 * (p0 + sub);
-    double acc[R][8];
-#pragma unroll
-    for (int a = 0; a < R; ++a)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[a][c] = 0.0;
-    for (int q = threadIdx.x; q < n4; q += kThreads) {
-      double vr[R];
-#pragma unroll
-      for (int a = 0; a < R; ++a) vr[a] = (a < r) ? VT[(size_t)a * n4 + q] : 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c < ncols) {
-          const double pv = Pinv[(col0 + c) * ldp + q];
-#pragma unroll
-          for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[a], pv, acc[a][c]);
-        }
-      }
-    }
-    // reduce-scatter over the 8 columns (xor 1, 2, 4), then butterfly (8, 16)
-    double h4[R][4], h2[R][2], h1[R];
-    {
-      const bool hi = lane & 1;
-#pragma unroll
-      for (int a = 0; a < R; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double keep = hi ? acc[a][c + 4] : acc[a][c];
-          const double send = hi ? acc[a][c] : acc[a][c + 4];
-          h4[a][c] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-    }
-    {
-      const bool hi = lane & 2;
-#pragma unroll
-      for (int a = 0; a < R; ++a)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const double keep = hi ? h4[a][c + 2] : h4[a][c];
-          const double send = hi ? h4[a][c] : h4[a][c + 2];
-          h2[a][c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-    }
-    {
-      const bool hi = lane & 4;
-#pragma unroll
-      for (int a = 0; a < R; ++a) {
-        const double keep = hi ? h2[a][1] : h2[a][0];
-        const double send = hi ? h2[a][0] : h2[a][1];
-        double v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        h1[a] = v;
-      }
-    }
-    // lane l < 8 holds column ((l&1)<<2 | (l&2) | (l&4)>>2)
-    __syncthreads();  // red reuse
-    if (lane < 8) {
-      const int col = ((lane & 1) << 2) | (lane & 2) | ((lane & 4) >> 2);
-#pragma unroll
-      for (int a = 0; a < R; ++a) red[(warp * 8 + col) * 8 + a] = h1[a];
-    }
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      const int col = threadIdx.x >> 3, a = threadIdx.x & 7;
-      if (a < r && col < ncols) {
-        double s = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) s += red[(w * 8 + col) * 8 + a];
-        zs[((sub + (col >> 2)) * 4 + (col & 3)) * 8 + a] = s;
-      }
-    }
+struct SlabState {
+  int agent;        // local agent whose first sub-chunk is resident / in flight (-1: none)
+  unsigned parity;  // mbarrier phase parity of the next completion
+  int pending;      // a copy was issued and not yet waited for
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *mbar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// thread 0: arm the mbarrier and issue the bulk copy (bytes: multiple of 16)
+__device__ __forceinline__ void slab_issue(uint64_t *mbar, double *dst, const double *src, uint32_t bytes) {
+  const uint32_t mb = smem_u32(mbar), d = smem_u32(dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(src), "r"(bytes), "r"(mb)
+               : "memory");
+}
+__device__ __forceinline__ void slab_wait(uint64_t *mbar, unsigned parity) {
+  const uint32_t mb = smem_u32(mbar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mb), "r"(parity)
+        : "memory");
   }
-  __syncthreads();
 }
 
 // this CTA's balanced share of an agent's poses for the dense phase
@@ -296,19 +300,191 @@ __device__ __forceinline__ void cta_pose_chunk(int n, int &p0, int &np) {
   np = base + (b < rem ? 1 : 0);
   p0 = b * base + min(b, rem);
 }
+__device__ __forceinline__ size_t agent_ldp(const AgentDev &A) { return ((size_t)4 * A.n + 31) / 32 * 32; }
+// poses per resident sub-chunk for this agent (0: the slab does not fit -> global-load fallback)
+__device__ __forceinline__ int slab_poses(const AgentDev &A, int np, size_t slab_cap_bytes) {
+  const size_t per = (size_t)4 * agent_ldp(A) * sizeof(double);
+  return min(np, (int)(slab_cap_bytes / per));
+}
+
+// Prefetch the first sub-chunk of `A`'s slab (called by all threads of the CTA;
+// the previous contents of the buffer must no longer be needed).
+__device__ __forceinline__ void slab_prefetch(const AgentDev &A, int ai, SlabState &ss, uint64_t *mbar, double *slab,
+                                              size_t slab_cap_bytes) {
+  if (ss.agent == ai || A.Pinv == nullptr) return;
+  int p0, np;
+  cta_pose_chunk(A.n, p0, np);
+  const int pps = slab_poses(A, np, slab_cap_bytes);
+  if (ss.pending) {  // never leave an unobserved completion behind
+    slab_wait(mbar, ss.parity);
+    ss.parity ^= 1;
+    ss.pending = 0;
+  }
+  ss.agent = -1;
+  if (pps <= 0) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const size_t ldp = agent_ldp(A);
+    slab_issue(mbar, slab, A.Pinv + (size_t)4 * p0 * ldp, (uint32_t)((size_t)4 * pps * ldp * sizeof(double)));
+  }
+  ss.agent = ai;
+  ss.pending = 1;
+}
+
+// acc over one pass of <= 3 poses (12 columns) whose columns start at `cols`
+// (shared memory or global, column stride ld); result to zs[pose][c][8].
+template <int R>
+__device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const double *VT, int r, int n4, int npass,
+                                           double *zs, double *red /* [8 warps][16 cols][8] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ncols = npass * 4;
+  double acc[R][12];
+#pragma unroll
+  for (int a = 0; a < R; ++a)
+#pragma unroll
+    for (int c = 0; c < 12; ++c) acc[a][c] = 0.0;
+  for (int q = threadIdx.x; q < n4; q += kThreads) {
+    double vr[R], pv[12];
+#pragma unroll
+    for (int a = 0; a < R; ++a) vr[a] = (a < r) ? VT[(size_t)a * n4 + q] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) pv[c] = (c < ncols) ? cols[(size_t)c * ld + q] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 12; ++c)
+#pragma unroll
+      for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[a], pv[c], acc[a][c]);
+  }
+  // reduce-scatter over 16 (12 + 4 zero) columns: xor 1, 2, 4, 8 then butterfly 16
+  double h8[R][8], h4[R][4], h2[R][2], h1[R];
+  {
+    const bool hi = lane & 1;
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double up = (c + 8 < 12) ? acc[a][c + 8 < 12 ? c + 8 : 0] : 0.0;
+        const double keep = hi ? up : acc[a][c];
+        const double send = hi ? acc[a][c] : up;
+        h8[a][c] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+  }
+  {
+    const bool hi = lane & 2;
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double keep = hi ? h8[a][c + 4] : h8[a][c];
+        const double send = hi ? h8[a][c] : h8[a][c + 4];
+        h4[a][c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const double keep = hi ? h4[a][c + 2] : h4[a][c];
+        const double send = hi ? h4[a][c] : h4[a][c + 2];
+        h2[a][c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      const double keep = hi ? h2[a][1] : h2[a][0];
+      const double send = hi ? h2[a][0] : h2[a][1];
+      double v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      h1[a] = v;
+    }
+  }
+  // lane l < 16 holds column ((l&1)<<3 | (l&2)<<1 | (l&4)>>1 | (l&8)>>3)
+  __syncthreads();  // red reuse
+  if (lane < 16) {
+    const int col = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+#pragma unroll
+    for (int a = 0; a < R; ++a) red[(warp * 16 + col) * 8 + a] = h1[a];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x >> 3, a = threadIdx.x & 7;
+    if (a < r && col < ncols) {
+      double s = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) s += red[(w * 16 + col) * 8 + a];
+      zs[((col >> 2) * 4 + (col & 3)) * 8 + a] = s;
+    }
+  }
+}
+
+// Z slab of this CTA's chunk [p0, p0+np) into zs[pose_local][c][8].
+template <int R>
+__device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const double *VT, int p0, int np,
+                                           SlabState &ss, uint64_t *mbar, double *slab, size_t slab_cap_bytes,
+                                           double *zs, double *red) {
+  const int r = A.r, n4 = 4 * A.n;
+  const size_t ldp = agent_ldp(A);
+  const int pps = slab_poses(A, np, slab_cap_bytes);
+  if (pps <= 0) {
+    // slab larger than shared memory: stream the columns from global memory
+    for (int sub = 0; sub < np; sub += 3)
+      dense_pass<R>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(3, np - sub), zs + sub * 32, red);
+    __syncthreads();
+    return;
+  }
+  for (int s0 = 0; s0 < np; s0 += pps) {
+    const int cnt = min(pps, np - s0);
+    if (s0 == 0 && ss.agent == ai) {
+      if (ss.pending) {
+        slab_wait(mbar, ss.parity);
+        ss.parity ^= 1;
+        ss.pending = 0;
+      }
+    } else {
+      if (ss.pending) {
+        slab_wait(mbar, ss.parity);
+        ss.parity ^= 1;
+        ss.pending = 0;
+      }
+      __syncthreads();  // everyone is done with the previous contents
+      if (threadIdx.x == 0)
+        slab_issue(mbar, slab, A.Pinv + (size_t)4 * (p0 + s0) * ldp, (uint32_t)((size_t)4 * cnt * ldp * sizeof(double)));
+      slab_wait(mbar, ss.parity);
+      ss.parity ^= 1;
+      ss.agent = (s0 == 0) ? ai : -1;
+    }
+    for (int sub = 0; sub < cnt; sub += 3)
+      dense_pass<R>(slab + (size_t)4 * sub * ldp, ldp, VT, r, n4, min(3, cnt - sub), zs + (s0 + sub) * 32, red);
+  }
+  if (np > pps) ss.agent = -1;  // the buffer no longer holds sub-chunk 0
+  __syncthreads();
+}
 
 // ---------------------------------------------------------------------------
 // Commit a new iterate for pose j (group-collective): relative-change partial,
-// X <- xnew, publish, and the Nesterov V update (a7):
+// X <- xnew (and an optional copy for the deferred statistics pass), publish,
+// and the Nesterov V update (a7):
 //   V = proj(V + gamma (X+ - Y))    or, on restart iterations, V = Y = X+.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid, int a, const double (&xnew)[4],
-                                            bool accel, bool restart, double gamma, double &prel) {
+                                            bool accel, bool restart, double gamma, double *xcopy, double &prel) {
   const int r = A.r;
   const bool act = valid && a < r;
   const size_t off = (size_t)(valid ? j : 0) * 4 * r;
-  double xold[4];
+  double xold[4], y[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+  int pe0 = 0, pe1 = 0;
+  if (valid) {
+    pe0 = A.pub_rowptr[j];
+    pe1 = A.pub_rowptr[j + 1];
+  }
   ld4(A.X + off, r, a, act, xold);
+  if (accel && !restart) {
+    ld4(A.Y + off, r, a, act, y);
+    ld4(A.V + off, r, a, act, v);
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const double d = xnew[c] - xold[c];
@@ -316,19 +492,18 @@ __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid
   }
   if (valid) {
     st4(A.X + off, r, a, act, xnew);
-    publish(A.pub_rowptr, A.pub_dst_reg, j, r, a, act, xnew);
+    if (xcopy) st4(xcopy + off, r, a, act, xnew);
+    publish_range(pe0, pe1, A.pub_dst_reg, r, a, act, xnew);
   }
   if (accel) {
     if (restart) {
       if (valid) {
         st4(A.V + off, r, a, act, xnew);
         st4(A.Y + off, r, a, act, xnew);
-        publish(A.pub_rowptr, A.pub_dst_aux, j, r, a, act, xnew);
+        publish_range(pe0, pe1, A.pub_dst_aux, r, a, act, xnew);
       }
     } else {
-      double y[4], v[4], m[4];
-      ld4(A.Y + off, r, a, act, y);
-      ld4(A.V + off, r, a, act, v);
+      double m[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) m[c] = v[c] + gamma * (xnew[c] - y[c]);
       if (!valid) {
@@ -348,16 +523,16 @@ __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid
 // With the preconditioner the CTA first computes its dense slab.
 // ---------------------------------------------------------------------------
 template <int R>
-__device__ __forceinline__ void phase_rgd_step(const AgentDev &A, const SolverParams &P, const double *Xs,
-                                               bool accel, bool restart, double gamma, double *zs, double *red,
-                                               double &prel) {
+__device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const SolverParams &P, const double *Xs,
+                                               bool accel, bool restart, double gamma, SlabState &ss,
+                                               uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
+                                               double *red, double *xcopy, double &prel) {
   const int n = A.n, r = A.r;
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   if (P.rgd_use_precond) {
     int p0, np;
     cta_pose_chunk(n, p0, np);
-    const size_t ldp = ((size_t)4 * n + 31) / 32 * 32;
-    dense_slab<R>(A.Pinv, ldp, A.RgT, r, 4 * n, p0, np, zs, red);
+    dense_slab<R>(A, ai, A.RgT, p0, np, ss, mbar, slab, slab_cap, zs, red);
     for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
       const int k = k0 + lg;
       const bool valid = k < np;
@@ -375,7 +550,7 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, const SolverPa
         xn[0] = (a == 0); xn[1] = (a == 1); xn[2] = (a == 2);
       }
       qf_row(xn);
-      finish_pose(A, j, valid, a, xn, accel, restart, gamma, prel);
+      finish_pose(A, j, valid, a, xn, accel, restart, gamma, xcopy, prel);
     }
   } else {
     PoseIter it;
@@ -393,23 +568,23 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, const SolverPa
         xn[0] = (it.a == 0); xn[1] = (it.a == 1); xn[2] = (it.a == 2);
       }
       qf_row(xn);
-      finish_pose(A, j, valid, it.a, xn, accel, restart, gamma, prel);
+      finish_pose(A, valid ? j : 0, valid, it.a, xn, accel, restart, gamma, xcopy, prel);
     }
   }
 }
 
 // Z = Proj_Xbase( V Pinv ) for the whole agent (tCG preconditioner, a6).  Writes
-// Z (+ optional row-major copy) and optionally dlt = -Z; pzr accumulates <Z, Rin>.
+// Z and optionally dlt = -Z; pzr accumulates <Z, Rin>.
 template <int R>
-__device__ __forceinline__ void phase_precond(const AgentDev &A, const double *Xbase, const double *Rin,
-                                              const double *RinT, double *Zout, double *neg_out, double *zs,
+__device__ __forceinline__ void phase_precond(const AgentDev &A, int ai, const double *Xbase, const double *Rin,
+                                              const double *RinT, double *Zout, double *neg_out, SlabState &ss,
+                                              uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
                                               double *red, double &pzr) {
   const int n = A.n, r = A.r;
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   int p0, np;
   cta_pose_chunk(n, p0, np);
-  const size_t ldp = ((size_t)4 * n + 31) / 32 * 32;
-  dense_slab<R>(A.Pinv, ldp, RinT, r, 4 * n, p0, np, zs, red);
+  dense_slab<R>(A, ai, RinT, p0, np, ss, mbar, slab, slab_cap, zs, red);
   for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
     const int k = k0 + lg;
     const bool valid = k < np;
