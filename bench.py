@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- RBCD iterations/s on sphere2500 split over 8 agents (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle on the host cores
+
+One *step* = one global RBCD iteration of the synchronous schedule: the robot
+holding the UPDATE token runs iterate(true), every other robot iterate(false),
+public (+ auxiliary) poses are exchanged (src/PGOAgentROS.cpp:1161-1189,
+109-113).  Workload = BASELINE config 2: sphere2500.g2o, 8 agents, r = 5, RGD
+(stepsize 0.2, preconditioner on: launch/asapp_demo.launch:7-8) + Nesterov
+acceleration (restart 50), RoundRobin, odometry initial guess, fixed YLift.
+
+`value`  : all 8 agents resident on the GPU(s), the persistent kernel runs the K
+           steps with device-side exchange; timed with CUDA events inside the
+           library around the launches (on the launching stream).
+`e2e`    : the same K steps driven through the per-robot C ABI that PGOAgentROS
+           would call (iterate / getSharedPoseDictWithNeighbor / updateNeighborPoses)
+           with HOST buffers: every step's public poses cross PCIe both ways.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIG2 = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=50,
+               rel_change_tol=0.0, max_num_iters=10 ** 9)  # tolerance 0: the bench never stops early
+WORKLOAD = "sphere2500.g2o / 8 agents / r=5 / RGD(step 0.2, precond) + Nesterov(restart 50) / RoundRobin"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the bench runs."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(problem, r):
+    """Per-step algorithmic bytes, averaged over the RoundRobin cycle.
+
+    B_grad  = edges*128 + 2*n*r*4*8 + n_nbr_pub*r*4*8     per Riemannian-gradient evaluation
+    one RGD step of the selected agent = 2 B_grad (gradient at Y, statistics at X+) + B_precond
+    B_precond            = (4n)^2 * 8 + 2*n*r*4*8                      dense (r x 4n)(4n x 4n) product
+    Nesterov bookkeeping of ALL agents = sum_a 4 * n_a*r*4*8           read X, V; write Y, X (or V)
+    """
+    per_agent = []
+    for rid in range(problem.num_robots):
+        m = problem.robot_measurements(rid)
+        n = problem.n[rid]
+        shared = m.r1 != m.r2
+        nbr_pub = len({(int(a), int(b)) for a, b in zip(np.where(m.r1[shared] == rid, m.r2[shared], m.r1[shared]),
+                                                        np.where(m.r1[shared] == rid, m.p2[shared], m.p1[shared]))})
+        b_grad = len(m) * 128 + 2 * n * r * 4 * 8 + nbr_pub * r * 4 * 8
+        b_pre = (4 * n) ** 2 * 8 + 2 * n * r * 4 * 8
+        per_agent.append((b_grad, b_pre, n))
+    nest = sum(4 * n * r * 4 * 8 for _, _, n in per_agent)
+    step = [2 * bg + bp + nest for bg, bp, _ in per_agent]
+    return float(np.mean(step)), float(np.mean([bg for bg, _, _ in per_agent]))
+
+
+def cpu_reference(steps, warmup, threads=None, sample_note=True):
+    """The CPU arm: oracle/ (a port -- the reference's own arithmetic is not vendored) on the host cores."""
+    from dpgo_ros_b200 import datasets
+    from oracle import binding as orc
+    cores = os.cpu_count() or 1
+    threads = threads or min(8, cores)
+    pb = datasets.load_g2o_problem("sphere2500", 8)
+    team = orc.OracleTeam(pb, **CONFIG2)
+    if warmup:
+        team.run(warmup, threads=threads, stop_on_terminate=False)
+    res = team.run(steps, threads=threads, stop_on_terminate=False)
+    return dict(value=res.iterations / res.wall_seconds, seconds=res.wall_seconds, steps=res.iterations,
+                threads=threads, cores=cores, cost=team.global_cost())
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = args.steps
+    t0 = time.time()
+    r = cpu_reference(steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "rbcd_iters_per_sec", "value": r["value"], "unit": "iters/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "sphere2500.g2o",
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": r["value"], "unit": "iters/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{r['steps']} steps of the same workload, one OS thread per agent "
+                                   f"({r['threads']} threads on {r['cores']} host cores)"},
+        "e2e": {"value": r["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "final_cost_2f": r["cost"], "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def e2e_host_exchange(problem, steps, warmup, device):
+    """K steps through the per-robot C ABI with host-buffer exchange (the PGOAgentROS call sequence,
+    replayed natively by dpgo_b200_sync_driver_run with one OS thread per robot)."""
+    from dpgo_ros_b200 import agent as gpu
+    _, agents = gpu.make_team(problem, device=device, colocate=False, **CONFIG2)
+    gpu.exchange_host(agents, accel=True)
+    gpu.sync_driver_run(agents, warmup, True)
+    sec, _ = gpu.sync_driver_run(agents, steps, True)
+    payload = gpu.exchange_payload_bytes(agents, True)
+    X = [a.getX() for a in agents]
+    for a in agents:
+        a.close()
+    return steps / sec, float(payload), float(payload), X
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=3000, help="bounded CPU-baseline sample (steps)")
+    ap.add_argument("--e2e-steps", type=int, default=4000)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from dpgo_ros_b200 import dist
+        return dist.bench_multi_gpu(args, CONFIG2, WORKLOAD)
+
+    from dpgo_ros_b200 import agent as gpu
+    from dpgo_ros_b200 import capi, datasets
+
+    L = capi.lib()
+    if L.dpgo_b200_device_count() < 1:
+        print(json.dumps({"error": "no CUDA device: the RBCD path has no CPU fallback"}))
+        return 1
+    pb = datasets.load_g2o_problem("sphere2500", 8)
+    launches0 = L.dpgo_b200_kernel_launch_count()
+    team, agents = gpu.make_team(pb, device=local_rank, **CONFIG2)
+    with ClockSampler(local_rank) as clk:
+        # warm-up (also keeps the clocks up for the sampler): W steps, then ~1 s of back-to-back steps
+        team.run(args.warmup, stop_on_terminate=False)
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            team.run(2000, stop_on_terminate=False)
+        launches_before = L.dpgo_b200_kernel_launch_count()
+        res = team.run(args.steps, stop_on_terminate=False)   # <- the timed region (CUDA events inside)
+        launches_timed = L.dpgo_b200_kernel_launch_count() - launches_before
+        time.sleep(0.25)
+    assert res.iterations == args.steps
+    ms_per_step = res.device_ms / args.steps
+    value = 1e3 / ms_per_step
+    cost = team.global_cost()
+    # cold-L2 variant: one step per launch with a >L2 buffer rewritten between launches
+    cold_ms = None
+    try:
+        import torch
+        flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        tt = []
+        for _ in range(24):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            r1 = team.run(1, stop_on_terminate=False)
+            tt.append(r1.device_ms)
+        cold_ms = float(np.median(tt))
+        del flush
+    except Exception:
+        pass
+    team.close()
+    for a in agents:
+        a.close()
+
+    e2e_val, h2d, d2h, _ = e2e_host_exchange(pb, args.e2e_steps, max(3, min(args.warmup, 20)), local_rank)
+
+    peak, peak_src = load_peaks()
+    step_bytes, grad_bytes = algorithmic_bytes(pb, CONFIG2["r"])
+    achieved = step_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
+    cpu = cpu_reference(args.cpu_steps, 50)
+    line = {
+        "metric": "rbcd_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "sphere2500.g2o (reference data/, odometry initial guess)",
+        "config": {"workload": WORKLOAD, "agents_per_gpu": 8,
+                   "l2": "steady state: one persistent launch runs all K steps and re-reads the same ~105 MB "
+                         "(8 dense preconditioners + graph) every RoundRobin cycle, as the solver does; no flush "
+                         "inside the launch. cold_l2_ms_per_step = one step per launch after rewriting 512 MB"},
+        "cold_l2_ms_per_step": cold_ms,
+        "final_cost_2f": cost,
+        "gpu_launches": int(launches_timed),
+        "kernel_launches_total": int(L.dpgo_b200_kernel_launch_count() - launches0),
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "per-robot C ABI (iterate / getSharedPoseDict / updateNeighborPoses), host buffers, 8 agents"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_team_run<5> (persistent: all phases of all K steps)",
+                     "algorithmic_bytes_per_step": step_bytes, "b_grad_per_agent": grad_bytes,
+                     "note": "latency-bound by construction: the working set of a step is ~13 MB and L2-resident "
+                             "(SURVEY §8d caveat); frac is the effective algorithmic bandwidth"},
+        "cpu_baseline": {"value": cpu["value"], "unit": "iters/s", "cores": cpu["threads"], "kind": "port",
+                         "sample": f"{cpu['steps']} steps of the same workload on the oracle, one OS thread per "
+                                   f"agent ({cpu['threads']} threads, {cpu['cores']} host cores)"},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -322,3 +322,25 @@ def exchange_host(agents: List[PGOAgent], accel: bool, only: Optional[List[int]]
                 by_id[nb].updateNeighborPoses(a.id, fr, poses, True)
                 moved += 2 * poses.nbytes
     return moved
+
+
+def sync_driver_run(agents: List[PGOAgent], steps: int, accelerated: bool):
+    """Native replay of the wrapper's synchronous call sequence through the per-robot C ABI with host
+    buffers, one OS thread per robot (dpgo_b200_sync_driver_run).  Returns (seconds, terminated_at)."""
+    L = capi.lib()
+    arr = (C.c_void_p * len(agents))(*[a.h for a in agents])
+    sec = C.c_double()
+    nbytes = C.c_longlong()
+    term = C.c_int()
+    check(L.dpgo_b200_sync_driver_run(arr, len(agents), steps, int(accelerated), C.byref(sec), C.byref(nbytes),
+                                      C.byref(term)), "sync_driver_run")
+    return sec.value, term.value
+
+
+def exchange_payload_bytes(agents: List[PGOAgent], accelerated: bool) -> int:
+    """Bytes of public poses every robot publishes in one accelerated step (each pose r x 4 FP64)."""
+    total = 0
+    for a in agents:
+        for nb in a.getNeighbors():
+            total += a.L.dpgo_b200_num_shared_poses(a.h, nb) * a.r * 4 * 8 * (2 if accelerated else 1)
+    return total

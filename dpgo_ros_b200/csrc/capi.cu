@@ -225,7 +225,7 @@ int dpgo_b200_outbox_device_ptr(dpgo_b200_agent_t h, int nbr, int aux, void **pt
   a->team->prepare();
   auto it = a->outbox_range.find(nbr);
   if (it == a->outbox_range.end()) fail(DPGO_B200_ERR_MISSING, "not a neighbour");
-  *ptr = (aux ? a->d_outbox_aux.p : a->d_outbox_reg.p) + (size_t)it->second.first * 4 * a->r;
+  *ptr = (aux ? a->d_outbox_aux() : a->d_outbox_reg()) + (size_t)it->second.first * 4 * a->r;
   *bytes = (size_t)it->second.second * 4 * a->r * sizeof(double);
   API_END
 }
@@ -240,7 +240,7 @@ int dpgo_b200_inbox_device_ptr(dpgo_b200_agent_t h, int nbr, int aux, void **ptr
       ++cnt;
     }
   if (first < 0) fail(DPGO_B200_ERR_MISSING, "not a neighbour");
-  *ptr = (aux ? a->d_inbox_aux.p : a->d_inbox_reg.p) + (size_t)first * 4 * a->r;
+  *ptr = (aux ? a->d_inbox_aux() : a->d_inbox_reg()) + (size_t)first * 4 * a->r;
   *bytes = (size_t)cnt * 4 * a->r * sizeof(double);
   API_END
 }
@@ -318,7 +318,7 @@ int dpgo_b200_eval(dpgo_b200_agent_t h, const double *X, double *f, double *egra
   dR.alloc(cnt);
   dP.alloc((size_t)grid * 2);
   const AgentDev view = a->team->T.ag[a->local_index];
-  cuda_check(launch_eval(view, dX.p, a->d_inbox_reg.p, dE.p, dR.p, dP.p, grid, 0), "k_eval");
+  cuda_check(launch_eval(view, dX.p, a->d_inbox_reg(), dE.p, dR.p, dP.p, grid, 0), "k_eval");
   std::vector<double> part((size_t)grid * 2);
   cuda_check(cudaMemcpy(part.data(), dP.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H partials");
   if (f) {
@@ -347,7 +347,7 @@ int dpgo_b200_hess(dpgo_b200_agent_t h, const double *X, const double *V, double
   dH.alloc(cnt);
   dP.alloc((size_t)grid * 2);
   const AgentDev view = a->team->T.ag[a->local_index];
-  cuda_check(launch_eval(view, dX.p, a->d_inbox_reg.p, dE.p, dR.p, dP.p, grid, 0), "k_eval");
+  cuda_check(launch_eval(view, dX.p, a->d_inbox_reg(), dE.p, dR.p, dP.p, grid, 0), "k_eval");
   cuda_check(launch_hess(view, dX.p, dV.p, dH.p, grid, 0), "k_hess");
   cuda_check(cudaMemcpy(out, dH.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H hess");
   API_END
@@ -482,10 +482,11 @@ int dpgo_b200_debug_team_profile(dpgo_b200_team_t h, int iters, int cta, long lo
   Team *t = TT(h);
   t->prof_iters = iters;
   t->prof_cta = cta;
-  t->dProf.alloc((size_t)iters * 16);
+  t->dProf.alloc((size_t)4096 + 64);
   t->team_dirty = true;
   t->run(iters, false);
   cuda_check(cudaMemcpy(out, t->dProf.p, sizeof(long long) * iters * 16, cudaMemcpyDeviceToHost), "D2H prof");
+  cuda_check(cudaMemcpy(out + iters * 16, t->dProf.p + 4096, sizeof(long long) * 16, cudaMemcpyDeviceToHost), "D2H dbg");
   t->prof_iters = 0;
   t->team_dirty = true;
   API_END

@@ -53,6 +53,12 @@ Agent::~Agent() {
   if (team && team != own.get()) team->remove(this);
   if (own) own->agents.clear();
   team = nullptr;
+  free_pinned();
+}
+
+void Agent::free_pinned() {
+  if (h_inbox) cudaFreeHost(h_inbox);
+  h_inbox = nullptr;
 }
 
 void Agent::add_measurement(const Meas &m) {
@@ -269,15 +275,16 @@ void Agent::build_structure() {
   d_s_slot.upload(h_s_slot);
   d_pub_rowptr.upload(h_pub_rowptr);
   const size_t vec = (size_t)r * 4 * n;
-  d_inbox_reg.alloc((size_t)n_in * 4 * r);
-  d_inbox_aux.alloc((size_t)n_in * 4 * r);
-  d_outbox_reg.alloc((size_t)std::max(1, outbox_total) * 4 * r);
-  d_outbox_aux.alloc((size_t)std::max(1, outbox_total) * 4 * r);
+  d_inbox.alloc((size_t)2 * std::max(1, n_in) * 4 * r);
+  free_pinned();
+  cuda_check(cudaMallocHost((void **)&h_inbox, d_inbox.n * sizeof(double)), "cudaMallocHost");
+  std::memset(h_inbox, 0, d_inbox.n * sizeof(double));
+  inbox_dirty = false;
+  outbox_mirror_valid = false;
   for (auto *b : {&dG, &dRg, &dRgT, &dZ, &dEta, &dDlt0, &dDlt1, &dHd, &dRv, &dRvT, &dX2, &dX3, &dRg2, &dRg2T, &dZeta})
     b->alloc(vec);
   dS.alloc((size_t)6 * n);
   dS2.alloc((size_t)6 * n);
-  dStat.alloc(1);
   if (dX.n != vec) {  // not initialised yet: allocate so the views are valid
     dX.alloc(vec);
     dY.alloc(vec);
@@ -479,12 +486,12 @@ AgentDev Agent::dev_view() const {
   A.s_rowptr = d_s_rowptr.p; A.s_slot = d_s_slot.p; A.s_val = d_s_val.p;
   A.qe_col = d_qe_col.p; A.qe_val = d_qe_val.p; A.qo_rowptr = d_qo_rowptr.p; A.qo_col = d_qo_col.p; A.qo_val = d_qo_val.p;
   A.se_slot = d_se_slot.p; A.se_val = d_se_val.p; A.so_rowptr = d_so_rowptr.p; A.so_slot = d_so_slot.p; A.so_val = d_so_val.p;
-  A.inbox_reg = d_inbox_reg.p; A.inbox_aux = d_inbox_aux.p;
+  A.inbox_reg = d_inbox_reg(); A.inbox_aux = d_inbox_aux();
   A.pub_rowptr = d_pub_rowptr.p; A.pub_dst_reg = d_pub_dst_reg.p; A.pub_dst_aux = d_pub_dst_aux.p;
   A.Pinv = dPinv.p;
   A.G = dG.p; A.Rg = dRg.p; A.RgT = dRgT.p; A.Z = dZ.p; A.eta = dEta.p; A.dlt0 = dDlt0.p; A.dlt1 = dDlt1.p;
   A.Hd = dHd.p; A.rv = dRv.p; A.rvT = dRvT.p; A.X2 = dX2.p; A.X3 = dX3.p; A.Rg2 = dRg2.p; A.Rg2T = dRg2T.p;
-  A.zeta = dZeta.p; A.S = dS.p; A.S2 = dS2.p; A.stat = dStat.p;
+  A.zeta = dZeta.p; A.S = dS.p; A.S2 = dS2.p; A.stat = d_stat;
   return A;
 }
 
@@ -536,10 +543,10 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
     if (o->id == nbr) colocated = true;
   const size_t pb = (size_t)4 * r * sizeof(double);
   if (!colocated) {
-    if (outbox_stale) team->exchange_all();
+    if (outbox_stale || !outbox_mirror_valid) team->exchange_all();
     const auto rg = outbox_range.at(nbr);
-    const double *src = (aux ? d_outbox_aux.p : d_outbox_reg.p) + (size_t)rg.first * 4 * r;
-    cuda_check(cudaMemcpy(poses, src, pb * cnt, cudaMemcpyDeviceToHost), "D2H outbox");
+    const double *src = h_outbox + (aux ? (size_t)std::max(1, outbox_total) * 4 * r : 0) + (size_t)rg.first * 4 * r;
+    std::memcpy(poses, src, pb * cnt);
   } else {
     const double *base = aux ? dY.p : dX.p;
     for (int k = 0; k < cnt; ++k)
@@ -552,28 +559,16 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
 void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const double *poses, int count) {
   cuda_check(cudaSetDevice(device), "cudaSetDevice");
   if (structure_dirty) build_structure();
-  double *inbox = aux ? d_inbox_aux.p : d_inbox_reg.p;
+  // stage in pinned host memory; the next launch uploads the inbox with one async copy
+  double *inbox = h_inbox + (aux ? (size_t)slot_key.size() * 4 * r : 0);
   auto &valid = aux ? inbox_valid_aux : inbox_valid_reg;
   const size_t pb = (size_t)4 * r * sizeof(double);
-  int k = 0;
-  while (k < count) {
+  for (int k = 0; k < count; ++k) {
     auto it = slot_of.find({nbr, frames[k]});
-    if (it == slot_of.end()) {  // a pose this agent does not need: ignore
-      ++k;
-      continue;
-    }
-    // extend over a run of consecutive slots to batch the copy
-    int run = 1;
-    while (k + run < count) {
-      auto nx = slot_of.find({nbr, frames[k + run]});
-      if (nx == slot_of.end() || nx->second != it->second + run) break;
-      ++run;
-    }
-    cuda_check(cudaMemcpy(inbox + (size_t)it->second * 4 * r, poses + (size_t)k * 4 * r, pb * run,
-                          cudaMemcpyHostToDevice),
-               "H2D inbox");
-    for (int q = 0; q < run; ++q) valid[it->second + q] = 1;
-    k += run;
+    if (it == slot_of.end()) continue;  // a pose this agent does not need
+    std::memcpy(inbox + (size_t)it->second * 4 * r, poses + (size_t)k * 4 * r, pb);
+    valid[it->second] = 1;
+    inbox_dirty = true;
   }
 }
 
@@ -659,7 +654,7 @@ bool Agent::compute_residual(const Meas &m, double *res) {
   w.upload({m.weight});
   rs.alloc(1);
   LcDev L{1, src.p, dst.p, sr.p, dr.p, mask.p, R.p, t.p, ka.p, ta.p, w.p, rs.p};
-  cuda_check(launch_gnc_weights(L, r, dX.p, d_inbox_reg.p, P.gnc_barc * P.gnc_barc, mu, P.cost_type, 0),
+  cuda_check(launch_gnc_weights(L, r, dX.p, d_inbox_reg(), P.gnc_barc * P.gnc_barc, mu, P.cost_type, 0),
              "gnc_weights");
   cuda_check(cudaMemcpy(res, rs.p, sizeof(double), cudaMemcpyDeviceToHost), "D2H residual");
   return true;
@@ -672,6 +667,7 @@ Team::Team(int device_) : device(device_) {
   cuda_check(cudaSetDevice(device), "cudaSetDevice");
   cuda_check(cudaEventCreate(&ev0), "eventCreate");
   cuda_check(cudaEventCreate(&ev1), "eventCreate");
+  cuda_check(cudaStreamCreate(&stream), "streamCreate");  // blocking stream: ordered against legacy-stream setup work
 }
 
 Team::~Team() {
@@ -689,6 +685,9 @@ Team::~Team() {
   }
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+  if (d_result) cudaFree(d_result);
+  if (h_result) cudaFreeHost(h_result);
 }
 
 void Team::add(Agent *a) {
@@ -735,7 +734,9 @@ void Team::prepare() {
     a->ensure_device();
     if (a->wiring_dirty) rewire = true;
   }
+  flush_inboxes();
   if (!rewire) return;
+  layout_result();
   const int r = agents[0]->r;
   for (Agent *a : agents) {
     std::vector<double *> reg(a->h_pub_entries.size()), aux(a->h_pub_entries.size());
@@ -751,8 +752,8 @@ void Team::prepare() {
           // the peer does not hold this shared edge (measurements not synchronised): park in the outbox
           peer = nullptr;
         } else {
-          reg[e] = peer->d_inbox_reg.p + (size_t)it->second * 4 * r;
-          aux[e] = peer->d_inbox_aux.p + (size_t)it->second * 4 * r;
+          reg[e] = peer->d_inbox_reg() + (size_t)it->second * 4 * r;
+          aux[e] = peer->d_inbox_aux() + (size_t)it->second * 4 * r;
         }
       }
       if (!peer) {
@@ -760,8 +761,8 @@ void Team::prepare() {
         if (fr.empty()) fr = a->my_public_frames(b);
         const int idx = (int)(std::lower_bound(fr.begin(), fr.end(), f) - fr.begin());
         const size_t o = (size_t)(a->outbox_range.at(b).first + idx) * 4 * r;
-        reg[e] = a->d_outbox_reg.p + o;
-        aux[e] = a->d_outbox_aux.p + o;
+        reg[e] = a->d_outbox_reg() + o;
+        aux[e] = a->d_outbox_aux() + o;
       }
     }
     if (reg.empty()) {
@@ -799,23 +800,65 @@ void Team::prepare() {
   T.p.max_num_iters = P.max_num_iters;
   T.p.rel_change_tol = P.rel_change_tol;
   if (grid <= 0) grid = max_coop_grid(device);
-  dBar.alloc(1);
+  dBar.alloc(2);  // [0]: full-grid launches, [1]: small-grid (nobody optimises) launches
+  {
+    int total = 0;
+    for (Agent *a : agents) total += a->n;
+    small_grid = std::max(1, std::min(grid, (total + kGroupsPerCta - 1) / kGroupsPerCta));
+  }
   dSlots.alloc((size_t)2 * grid * kRed);
-  dCtl.alloc(1);
   T.gs.counter = dBar.p;
   T.gs.slots = dSlots.p;
-  T.ctl = dCtl.p;
+  T.ctl = reinterpret_cast<TeamCtl *>(d_result);
   T.prof = prof_iters > 0 ? dProf.p : nullptr;
   T.prof_iters = prof_iters;
   T.prof_cta = prof_cta;
   team_dirty = false;
 }
 
-void Team::read_back() {
-  cuda_check(cudaMemcpy(&ctl, dCtl.p, sizeof(TeamCtl), cudaMemcpyDeviceToHost), "D2H ctl");
+void Team::layout_result() {
+  auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
+  size_t off = up(64 + 128 * agents.size(), 256);
+  std::vector<size_t> offs;
   for (Agent *a : agents) {
-    AgentStat st;
-    cuda_check(cudaMemcpy(&st, a->dStat.p, sizeof(AgentStat), cudaMemcpyDeviceToHost), "D2H stat");
+    offs.push_back(off);
+    off += up(a->outbox_doubles() * sizeof(double), 256);
+  }
+  if (off != result_bytes) {
+    if (d_result) cudaFree(d_result);
+    if (h_result) cudaFreeHost(h_result);
+    d_result = h_result = nullptr;
+    cuda_check(cudaMalloc((void **)&d_result, off), "cudaMalloc result");
+    cuda_check(cudaMallocHost((void **)&h_result, off), "cudaMallocHost result");
+    result_bytes = off;
+  }
+  cuda_check(cudaMemset(d_result, 0, result_bytes), "cudaMemset result");
+  std::memset(h_result, 0, result_bytes);
+  for (size_t i = 0; i < agents.size(); ++i) {
+    Agent *a = agents[i];
+    a->d_stat = reinterpret_cast<AgentStat *>(d_result + 64 + 128 * i);
+    a->h_stat = reinterpret_cast<AgentStat *>(h_result + 64 + 128 * i);
+    a->d_outbox = reinterpret_cast<double *>(d_result + offs[i]);
+    a->h_outbox = reinterpret_cast<double *>(h_result + offs[i]);
+    a->outbox_stale = true;
+    a->outbox_mirror_valid = false;
+  }
+}
+
+void Team::flush_inboxes() {
+  for (Agent *a : agents)
+    if (a->inbox_dirty && a->d_inbox.n) {
+      cuda_check(cudaMemcpyAsync(a->d_inbox.p, a->h_inbox, a->d_inbox.n * sizeof(double), cudaMemcpyHostToDevice,
+                                 stream),
+                 "H2D inbox");
+      a->inbox_dirty = false;
+    }
+}
+
+void Team::read_back() {
+  ctl = *h_ctl();
+  for (Agent *a : agents) {
+    const AgentStat st = *a->h_stat;
     a->iter = ctl.iter;
     a->robust_inner_iter = ctl.robust_inner_iter;
     if (st.optimized) {
@@ -834,17 +877,37 @@ void Team::read_back() {
     a->status.iteration_number = a->iter;
     a->status.state = a->state;
     a->team_status[a->id] = a->get_status();
+    a->outbox_mirror_valid = true;
+    a->outbox_stale = false;
   }
+}
+
+// launch the persistent kernel (control state travels as a kernel argument), queue ONE read-back
+// copy of the result block [ctl | stats | outboxes], synchronise once
+void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, float *ms) {
+  RunArgs args = args_in;
+  args.ctl_in = ctl;
+  TeamDev Tl = T;
+  Tl.gs.counter = dBar.p + (use_grid == grid ? 0 : 1);
+  if (timed) cuda_check(cudaEventRecord(ev0, stream), "eventRecord");
+  if (args.force_selected == -1 && args.max_iters == 1)
+    cuda_check(launch_nesterov_only(Tl, args, use_grid, stream), "launch k_nesterov_only");
+  else
+    cuda_check(launch_team_run(Tl, args, use_grid, stream), "launch k_team_run");
+  if (timed) cuda_check(cudaEventRecord(ev1, stream), "eventRecord");
+  ++launches;
+  cuda_check(cudaMemcpyAsync(h_result, d_result, result_bytes, cudaMemcpyDeviceToHost, stream), "D2H result");
+  cuda_check(cudaStreamSynchronize(stream), "k_team_run");
+  if (timed && ms) cudaEventElapsedTime(ms, ev0, ev1);
+  read_back();
 }
 
 void Team::run_forced(int sel_local) {
   prepare();
-  cuda_check(cudaMemcpy(dCtl.p, &ctl, sizeof(TeamCtl), cudaMemcpyHostToDevice), "H2D ctl");
-  RunArgs args{1, sel_local, 0, 0, 0};
-  cuda_check(launch_team_run(T, args, grid, 0), "launch k_team_run");
-  ++launches;
-  cuda_check(cudaDeviceSynchronize(), "k_team_run");
-  read_back();
+  RunArgs args{};
+  args.max_iters = 1;
+  args.force_selected = sel_local;
+  launch_and_read(args, sel_local < 0 ? small_grid : grid, false, nullptr);
 }
 
 dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
@@ -861,18 +924,14 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
       fail(DPGO_B200_ERR_MISSING, "team_run: neighbour poses missing; call team_exchange_all first");
   int remaining = max_iters;
   while (remaining > 0) {
-    cuda_check(cudaMemcpy(dCtl.p, &ctl, sizeof(TeamCtl), cudaMemcpyHostToDevice), "H2D ctl");
-    RunArgs args{remaining, -2, stop_on_terminate ? 1 : 0, 0, 0};
-    cuda_check(cudaEventRecord(ev0, 0), "eventRecord");
-    cuda_check(launch_team_run(T, args, grid, 0), "launch k_team_run");
-    cuda_check(cudaEventRecord(ev1, 0), "eventRecord");
-    cuda_check(cudaEventSynchronize(ev1), "k_team_run");
+    RunArgs args{};
+    args.max_iters = remaining;
+    args.force_selected = -2;
+    args.stop_on_terminate = stop_on_terminate ? 1 : 0;
     float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1);
+    launch_and_read(args, grid, true, &ms);
     res.device_ms += ms;
     res.kernel_launches++;
-    ++launches;
-    read_back();
     res.iterations += ctl.iters_done;
     remaining -= ctl.iters_done;
     if (ctl.stop_reason == 2) {
@@ -891,11 +950,14 @@ void Team::exchange_all() {
   // publish X (and Y) of every agent through the same publication lists the
   // persistent kernel uses: a forced iteration count of zero does nothing, so
   // use the dedicated kernel
-  cuda_check(launch_publish_all(T, grid, 0), "publish_all");
-  cuda_check(cudaDeviceSynchronize(), "publish_all");
+  cuda_check(launch_publish_all(T, grid, stream), "publish_all");
+  cuda_check(cudaMemcpyAsync(h_result + 64, d_result + 64, result_bytes - 64, cudaMemcpyDeviceToHost, stream),
+             "D2H result");
+  cuda_check(cudaStreamSynchronize(stream), "publish_all");
   for (Agent *a : agents) {
     if (a->state != 2) continue;
     a->outbox_stale = false;
+    a->outbox_mirror_valid = true;
     for (Agent *o : agents) {
       if (o == a) continue;
       for (size_t s = 0; s < o->slot_key.size(); ++s)
@@ -917,7 +979,7 @@ void Team::gnc_update_all() {
     if (L) {
       LcDev Ld{(int)L, a->d_lc_src.p, a->d_lc_dst.p, a->d_lc_src_remote.p, a->d_lc_dst_remote.p, a->d_lc_mask.p,
                a->d_lc_R.p, a->d_lc_t.p, a->d_lc_kappa.p, a->d_lc_tau.p, a->d_lc_weight.p, a->d_lc_residual.p};
-      cuda_check(launch_gnc_weights(Ld, a->r, a->dX.p, a->d_inbox_reg.p, a->P.gnc_barc * a->P.gnc_barc, a->mu,
+      cuda_check(launch_gnc_weights(Ld, a->r, a->dX.p, a->d_inbox_reg(), a->P.gnc_barc * a->P.gnc_barc, a->mu,
                                     a->P.cost_type, 0),
                  "gnc_weights");
       std::vector<double> w(L);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <set>
@@ -145,11 +146,24 @@ class Agent {
   // ELL(8) / ELL(4) copies + CSR overflow read by the hot phases
   DevBuf<int> d_qe_col, d_qo_rowptr, d_qo_col, d_se_slot, d_so_rowptr, d_so_slot;
   DevBuf<double> d_qe_val, d_qo_val, d_se_val, d_so_val;
-  DevBuf<double> d_inbox_reg, d_inbox_aux, d_outbox_reg, d_outbox_aux;
+  // inbox / outbox: [reg | aux] contiguous on the device, mirrored in pinned host memory so the
+  // per-robot exchange API (getSharedPoseDict / updateNeighborPoses) costs one async copy per iterate
+  DevBuf<double> d_inbox;
+  double *d_inbox_reg() const { return d_inbox.p; }
+  double *d_inbox_aux() const { return d_inbox.p + (size_t)slot_key.size() * 4 * r; }
+  // outbox + AgentStat live in the owning team's result block (one D2H copy per launch)
+  double *d_outbox = nullptr, *h_outbox = nullptr;
+  AgentStat *d_stat = nullptr, *h_stat = nullptr;
+  size_t outbox_doubles() const { return (size_t)2 * std::max(1, outbox_total) * 4 * r; }
+  double *d_outbox_reg() const { return d_outbox; }
+  double *d_outbox_aux() const { return d_outbox + (size_t)std::max(1, outbox_total) * 4 * r; }
+  double *h_inbox = nullptr;  // pinned
+  bool inbox_dirty = false;      // host staging newer than the device inbox
+  bool outbox_mirror_valid = false;
+  void free_pinned();
   DevBuf<double *> d_pub_dst_reg, d_pub_dst_aux;
   DevBuf<double> dPinv;
   DevBuf<double> dG, dRg, dRgT, dZ, dEta, dDlt0, dDlt1, dHd, dRv, dRvT, dX2, dX3, dRg2, dRg2T, dZeta, dS, dS2;
-  DevBuf<AgentStat> dStat;
   // loop-closure arrays for the GNC kernel
   DevBuf<int> d_lc_src, d_lc_dst;
   DevBuf<unsigned char> d_lc_src_remote, d_lc_dst_remote, d_lc_mask;
@@ -180,10 +194,17 @@ class Team {
   int device;
   int grid = 0;
   cudaStream_t stream = nullptr;
+  // result block: [TeamCtl | AgentStat per agent | outbox per agent], device + pinned mirror
+  unsigned char *d_result = nullptr, *h_result = nullptr;
+  size_t result_bytes = 0;
+  TeamCtl *h_ctl() const { return reinterpret_cast<TeamCtl *>(h_result); }
+  void layout_result();
+  int small_grid = 1;
+  void flush_inboxes();
+  void launch_and_read(const RunArgs &args, int use_grid, bool timed, float *ms);
   std::vector<Agent *> agents;
   TeamDev T{};
   TeamCtl ctl{};
-  DevBuf<TeamCtl> dCtl;
   DevBuf<unsigned long long> dBar;
   DevBuf<double> dSlots;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -9,6 +9,7 @@
 //  * single-op kernels backing the parity hooks (eval / hess / precond /
 //    manifold ops) and the GNC-TLS residual+weight kernel (a8).
 #include <algorithm>
+#include <atomic>
 
 #include "kernels.h"
 #include "phases.cuh"
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   BarState bs;
   bar_init(gs, bs);
   // control state: identical in every thread
-  TeamCtl c = *T.ctl;
+  TeamCtl c = args.ctl_in;
   int parity = 0;
   const int N = T.num_robots;
   const bool accel = P.acceleration != 0;
@@ -463,6 +464,33 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     c.stop_reason = stop_reason;
     c.iters_done = done;
+    *T.ctl = c;
+  }
+}
+
+// iterate(false) of accelerated agents when nobody on this device optimises: a single pose-local
+// phase, so no grid barrier and no cooperative launch (src/PGOAgentROS.cpp:1185)
+__global__ void __launch_bounds__(kThreads) k_nesterov_only(const __grid_constant__ TeamDev T,
+                                                            const __grid_constant__ RunArgs args) {
+  TeamCtl c = args.ctl_in;
+  const int N = T.num_robots;
+  const int iter = c.iter + 1;
+  const bool accel = T.p.acceleration != 0;
+  const bool restart = accel && ((iter + 1) % T.p.restart_interval == 0);
+  double gamma = c.gamma, alpha = c.alpha;
+  if (accel) {
+    gamma = (1.0 + sqrt(1.0 + 4.0 * (double)N * N * gamma * gamma)) / (2.0 * N);
+    alpha = 1.0 / (gamma * N);
+    phase_nesterov(T, -1, restart, alpha);
+  }
+  if (restart) gamma = alpha = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c.gamma = gamma;
+    c.alpha = alpha;
+    c.iter = iter;
+    if (T.p.robust) c.robust_inner_iter++;
+    c.stop_reason = 0;
+    c.iters_done = 1;
     *T.ctl = c;
   }
 }
@@ -644,8 +672,8 @@ __global__ void k_gnc_weights(LcDev L, int r, const double *X, const double *inb
 // ---------------------------------------------------------------------------
 // host-side launch wrappers
 // ---------------------------------------------------------------------------
-static long long g_launches = 0;
-long long kernel_launch_count() { return g_launches; }
+static std::atomic<long long> g_launches{0};
+long long kernel_launch_count() { return g_launches.load(); }
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - 10 * 1024;  // leave room for the static arrays
 
@@ -666,8 +694,12 @@ static cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaSt
   size_t slab_cap, smem;
   smem_plan(max_n, grid, want_slab, slab_cap, smem);
   args.slab_cap = slab_cap;
-  cudaError_t err = cudaFuncSetAttribute(k_team_run<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
+  static std::atomic<size_t> configured{0};
+  if (smem > configured.load()) {
+    cudaError_t err = cudaFuncSetAttribute(k_team_run<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured.store(smem);
+  }
   void *params[] = {(void *)&T, (void *)&args};
   ++g_launches;
   return cudaLaunchCooperativeKernel((void *)k_team_run<R>, dim3(grid), dim3(kThreads), params, smem, stream);
@@ -678,6 +710,12 @@ cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cud
   if (r == 5) return launch_run_t<5>(T, args, grid, stream);
   if (r == 6) return launch_run_t<6>(T, args, grid, stream);
   return launch_run_t<8>(T, args, grid, stream);
+}
+
+cudaError_t launch_nesterov_only(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
+  ++g_launches;
+  k_nesterov_only<<<grid, kThreads, 0, stream>>>(T, args);
+  return cudaGetLastError();
 }
 
 int max_coop_grid(int device) {

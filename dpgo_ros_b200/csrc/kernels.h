@@ -12,6 +12,7 @@ struct RunArgs {
   int stop_on_terminate;
   int leader;          // robot id whose turn triggers the termination / weight-update test
   size_t slab_cap;     // bytes of shared memory reserved for the preconditioner slab (set by the launcher)
+  TeamCtl ctl_in;      // control state at entry (the kernel writes the exit state to TeamDev::ctl)
 };
 
 // non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel
@@ -28,6 +29,7 @@ long long kernel_launch_count();
 long long dense_inverse_launch_count();
 int max_coop_grid(int device);
 cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream);
+cudaError_t launch_nesterov_only(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream);
 cudaError_t launch_eval(const AgentDev &A, const double *X, const double *inbox, double *egrad, double *rgrad,
                         double *partials, int grid, cudaStream_t s);
 cudaError_t launch_hess(const AgentDev &A, const double *X, const double *V, double *out, int grid, cudaStream_t s);

@@ -68,10 +68,12 @@ __device__ __forceinline__ int gshfl(int v, int src) { return __shfl_sync(0xffff
 // Publishes Y (aux) and, for non-selected agents, X (reg) into the neighbours'
 // inboxes (a9: getAuxSharedPoseDictWithNeighbor :666 / updateAuxNeighborPoses :1278).
 // ---------------------------------------------------------------------------
+#define DBG(k) if (T.prof && threadIdx.x == 0 && (int)blockIdx.x == T.prof_cta) T.prof[4096 + (k)] = clock64();
 __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, bool restart, double alpha) {
   PoseIter it;
   const int total = T.pose_prefix[T.num_local];
   int item;
+  DBG(0)
   while (it.next(total, item)) {
     const bool valid = item < total;
     int ai = 0;
@@ -99,6 +101,7 @@ __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, 
       }
       continue;
     }
+    DBG(1)
     ld4(A.V + off, r, it.a, act, v);
 #pragma unroll
     for (int c = 0; c < 4; ++c) m[c] = (1.0 - alpha) * x[c] + alpha * v[c];
@@ -107,7 +110,11 @@ __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, 
       m[1] = (it.a == 1);
       m[2] = (it.a == 2);
     }
+    if (m[0] == 123.456) DBG(7)
+    DBG(2)
     stiefel_project_row(m);
+    if (m[0] == 123.456) DBG(7)
+    DBG(3)
     if (valid) {
       st4(A.Y + off, r, it.a, act, m);
       publish_range(pe0, pe1, A.pub_dst_aux, r, it.a, act, m);
@@ -116,7 +123,9 @@ __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, 
         publish_range(pe0, pe1, A.pub_dst_reg, r, it.a, act, m);
       }
     }
+    DBG(4)
   }
+  DBG(5)
 }
 
 // ---------------------------------------------------------------------------

@@ -167,6 +167,16 @@ double dpgo_b200_team_global_cost(dpgo_b200_team_t t, int *status);
 /* tuning knob: CTAs of the persistent kernel (0 = one per SM) */
 int dpgo_b200_team_set_grid(dpgo_b200_team_t t, int num_ctas);
 
+/* ---- host harness ------------------------------------------------------------------
+ * ROS-free replay of PGOAgentROS's synchronous per-iteration call sequence on N
+ * standalone agents, using ONLY the per-robot entry points above with HOST
+ * buffers (iterate, getSharedPoseDict, updateNeighborPoses, getStatus,
+ * shouldTerminate; src/PGOAgentROS.cpp:102-220, 1161-1189, 1255-1284), one OS
+ * thread per robot.  Runs `steps` global iterations; *terminated_at = first step
+ * (1-based) at which the leader's shouldTerminate() fired, or -1.               */
+int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int num_agents, int steps, int accelerated,
+                              double *seconds, long long *payload_bytes, int *terminated_at);
+
 #ifdef __cplusplus
 }
 #endif

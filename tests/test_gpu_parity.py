@@ -202,6 +202,22 @@ def test_standalone_agents_with_host_exchange(small_problem):
         assert abs(st.relative_change - oteam.status(sel).relative_change) < 1e-9
 
 
+@pytest.mark.parametrize("accel", [0, 1])
+def test_native_sync_driver_matches_oracle(sphere8_problem, accel):
+    """dpgo_b200_sync_driver_run: per-robot C ABI + host buffers + one thread per robot."""
+    kw = dict(r=5, method=1, rgd_stepsize=0.2 if accel else 0.05, rgd_use_preconditioner=1, acceleration=accel,
+              restart_interval=50, rel_change_tol=0.1, max_num_iters=1000)
+    oteam = orc.OracleTeam(sphere8_problem, **kw)
+    _, agents = gpu.make_team(sphere8_problem, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=bool(accel))
+    sec, term = gpu.sync_driver_run(agents, 60, bool(accel))
+    oteam.run(60, stop_on_terminate=False)
+    for rid in range(8):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, rid
+        assert agents[rid].iteration_number() == 60
+    assert sec > 0
+
+
 def test_iterate_without_neighbor_poses_is_refused(small_problem):
     kw = dict(r=5, method=1, rgd_stepsize=0.2, acceleration=0)
     _, agents = gpu.make_team(small_problem, colocate=False, **kw)

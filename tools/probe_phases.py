@@ -20,9 +20,10 @@ team.run(20, stop_on_terminate=False)
 names = ["start", "nesterov", "barrier", "grad", "reduce", "rgdstep", "reduce", "grad2", "reduce"]
 for cta in (0, 73, 147):
     iters = 12
-    buf = (C.c_longlong * (iters * 16))()
+    buf = (C.c_longlong * (iters * 16 + 16))()
     rc = L.dpgo_b200_debug_team_profile(team.h, iters, cta, buf)
-    a = np.array(buf[:]).reshape(iters, 16)
+    dbg = np.array(buf[iters * 16:]); print('   nesterov dbg deltas', np.diff(dbg[:6]))
+    a = np.array(buf[:iters * 16]).reshape(iters, 16)
     d = np.diff(a[:, :9], axis=1)
     print(f"cta {cta}: cycles per segment (median over {iters} iters), rc={rc}")
     for k in range(8):
