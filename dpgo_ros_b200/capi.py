@@ -90,7 +90,7 @@ def make_params(**kw) -> Params:
 def build(force: bool = False) -> str:
     """Compile the CUDA extension for sm_100a (nvcc cross-compiles without a GPU)."""
     csrc = os.path.join(_HERE, "csrc")
-    cmd = ["make", "-C", csrc, "-j4", "-s"] + (["-B"] if force else [])
+    cmd = ["make", "-C", csrc, "-j8", "-s"] + (["-B"] if force else [])
     subprocess.check_call(cmd)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("libdpgo_b200.so was not produced")

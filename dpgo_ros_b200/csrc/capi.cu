@@ -194,6 +194,7 @@ int dpgo_b200_set_x(dpgo_b200_agent_t h, const double *X) {
     cuda_check(cudaMemcpy(a->dV.p, X, bytes, cudaMemcpyHostToDevice), "H2D V");
     cuda_check(cudaMemcpy(a->dY.p, X, bytes, cudaMemcpyHostToDevice), "H2D Y");
     a->team->ctl.gamma = a->team->ctl.alpha = 0;
+    a->team->gamma_state = 0;
   }
   a->outbox_stale = true;
   API_END
@@ -467,9 +468,9 @@ int dpgo_b200_debug_barrier_bench(int device, int grid, int iters, int mode, flo
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  cuda_check(launch_barrier_bench(gs, 10, mode, out.p, grid, 0), "barrier_bench warmup");
+  cuda_check(launch_barrier_bench(gs, 10, mode, 0u, out.p, grid, 0), "barrier_bench warmup");
   cudaEventRecord(e0, 0);
-  cuda_check(launch_barrier_bench(gs, iters, mode, out.p, grid, 0), "barrier_bench");
+  cuda_check(launch_barrier_bench(gs, iters, mode, 10u, out.p, grid, 0), "barrier_bench");
   cudaEventRecord(e1, 0);
   cuda_check(cudaEventSynchronize(e1), "barrier_bench sync");
   cudaEventElapsedTime(ms, e0, e1);
@@ -486,7 +487,7 @@ int dpgo_b200_debug_team_profile(dpgo_b200_team_t h, int iters, int cta, long lo
   t->team_dirty = true;
   t->run(iters, false);
   cuda_check(cudaMemcpy(out, t->dProf.p, sizeof(long long) * iters * 16, cudaMemcpyDeviceToHost), "D2H prof");
-  cuda_check(cudaMemcpy(out + iters * 16, t->dProf.p + 4096, sizeof(long long) * 16, cudaMemcpyDeviceToHost), "D2H dbg");
+  cuda_check(cudaMemcpy(out + iters * 16, t->dProf.p + 4096, sizeof(long long) * 32, cudaMemcpyDeviceToHost), "D2H dbg");
   t->prof_iters = 0;
   t->team_dirty = true;
   API_END

@@ -11,6 +11,7 @@
 
 namespace dpgo {
 
+constexpr int kMaxGrid = 160;   // grid_sync polls at most 5 x 32 CTAs
 constexpr int kMaxLocal = 8;     // co-located agents per team / device
 constexpr int kMaxRobots = 64;   // robots in the whole problem
 constexpr int kThreads = 256;    // CTA size of every kernel here
@@ -77,11 +78,14 @@ struct TeamCtl {
   int weight_update_count, robust_inner_iter;
   int stop_reason;  // 0 ran out of max_iters, 1 terminate, 2 weight update requested
   int iters_done;
+  unsigned long long seq;  // completion flag: written last, after a system-scope fence (host polls it)
+  unsigned epoch;          // grid_sync epoch reached at kernel exit (carried into the next launch)
+  unsigned pad;
 };
 
 struct GridSync {
   unsigned long long *counter;  // monotonically increasing arrival counter
-  double *slots;                // [2][gridDim.x][kRed]
+  double *slots;                // [2][gridDim.x][kRed] reduction partials
 };
 
 struct TeamDev {
@@ -95,7 +99,16 @@ struct TeamDev {
   // optional phase timeline (debug): clock64() of one CTA's thread 0 at phase boundaries
   long long *prof;
   int prof_iters, prof_cta;
+  unsigned long long *done_counter;  // last-block-done counter of the non-cooperative kernels
+  double *defer;                     // [num_local][grid][warps][8] parked reporting partials
 };
+
+// relaxation rank: a compile-time constant in the persistent kernel (RC > 0) so that every pose
+// access becomes base + immediate offset; read from the agent only in the generic helper kernels
+template <int RC>
+__device__ __forceinline__ int rdim(const AgentDev &A) {
+  return RC ? RC : A.r;
+}
 
 // ---------------------------------------------------------------------------
 // 8-lane group primitives (all 32 lanes of the warp must call these)
@@ -296,12 +309,15 @@ __device__ __forceinline__ void qf_row(double (&x)[4]) {
 // One monotonically increasing 64-bit arrival counter (never reset: at kernel
 // start it is a multiple of gridDim.x plus the arrivals of faster CTAs, so the
 // epoch base is (value / gridDim.x) * gridDim.x).  Thread 0 of each CTA arrives
-// with a release reduction and polls with acquire loads -- no sequentially
-// consistent fences (the first version used three __threadfence() per barrier
-// and measured 2.2 us; see profiles/).
+// with a release reduction and polls ONE address with acquire loads.
+// Measured on B200 (148 CTAs): 2.2 us with three __threadfence() + atomicAdd,
+// 1.25 us with release/acquire (this version).  A flag-per-CTA variant with the
+// payload packed into the flags (NCCL-LL style) was tried and measured 2.4 us:
+// 148 CTAs polling 148 slots each congest the few L2 lines that hold them.
 // ---------------------------------------------------------------------------
 struct BarState {
   unsigned long long next;  // meaningful in thread 0 only
+  int parity;               // reduction slot parity (uniform)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
@@ -315,6 +331,7 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsig
 
 __device__ __forceinline__ void bar_init(const GridSync &gs, BarState &bs) {
   bs.next = 0;
+  bs.parity = 0;
   if (threadIdx.x == 0) {
     const unsigned long long start = ld_acquire_u64(gs.counter);
     bs.next = (start / gridDim.x) * gridDim.x + gridDim.x;
@@ -334,12 +351,11 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs, BarState &bs) {
 
 // Sum `vals` over every thread of the grid; every thread gets the same totals,
 // summed in a fixed order (bitwise reproducible run to run).  Includes a grid
-// barrier, so it also orders global memory between phases.  `parity` flips on
-// every call (slot double-buffering: a fast CTA may start writing the next
-// reduction's slots while a slow one is still reading this one's).
+// barrier, so it also orders global memory between phases.  Slots are double
+// buffered by parity: a fast CTA may start writing the next reduction's slots
+// while a slow one is still reading this one's.
 template <int K>
-__device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, int &parity, double (&vals)[K],
-                                            double *sm) {
+__device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, double (&vals)[K], double *sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) vals[k] = wsum32(vals[k]);
@@ -347,7 +363,7 @@ __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, in
 #pragma unroll
     for (int k = 0; k < K; ++k) sm[warp * K + k] = vals[k];
   }
-  double *slots = gs.slots + (size_t)parity * gridDim.x * kRed;
+  double *slots = gs.slots + (size_t)bs.parity * gridDim.x * kRed;
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -370,7 +386,7 @@ __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, in
     for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&slots[(size_t)b * kRed + k]);
     vals[k] = wsum32(s);
   }
-  parity ^= 1;
+  bs.parity ^= 1;
 }
 
 }  // namespace dpgo

@@ -4,6 +4,7 @@
 #include "host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -172,6 +173,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
   state = 2;
   status.state = 2;
   team->ctl.gamma = team->ctl.alpha = 0;
+  team->gamma_state = 0;
   team->team_dirty = true;
   outbox_stale = true;
 }
@@ -191,7 +193,10 @@ void Agent::reset() {
   mu = P.gnc_init_mu;
   opt = dpgo_b200_opt_result{};
   if (team) {
+    const unsigned ep = team->ctl.epoch;
     team->ctl = TeamCtl{};
+    team->ctl.epoch = ep;
+    team->gamma_state = 0;
     team->team_dirty = true;
   }
 }
@@ -686,7 +691,6 @@ Team::~Team() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
-  if (d_result) cudaFree(d_result);
   if (h_result) cudaFreeHost(h_result);
 }
 
@@ -696,7 +700,12 @@ void Team::add(Agent *a) {
   if (!agents.empty() && (agents[0]->r != a->r || agents[0]->P.num_robots != a->P.num_robots))
     fail(DPGO_B200_ERR_INVALID, "agents of one team must share r and num_robots");
   if (a->team && a->team != this && a->team != a->own.get()) a->team->remove(a);
-  if (agents.empty() && a->own && a->own.get() != this) ctl = a->own->ctl;
+  if (agents.empty() && a->own && a->own.get() != this) {
+    const unsigned ep = ctl.epoch;
+    ctl = a->own->ctl;
+    ctl.epoch = ep;
+    gamma_state = a->own->gamma_state;
+  }
   if (a->own && a->own.get() != this) a->own->agents.clear();
   a->team = this;
   a->local_index = (int)agents.size();
@@ -800,19 +809,22 @@ void Team::prepare() {
   T.p.max_num_iters = P.max_num_iters;
   T.p.rel_change_tol = P.rel_change_tol;
   if (grid <= 0) grid = max_coop_grid(device);
-  dBar.alloc(2);  // [0]: full-grid launches, [1]: small-grid (nobody optimises) launches
+  dBar.alloc(3);  // [0]: full-grid launches, [1]: small-grid launches, [2]: last-block-done counter
   {
     int total = 0;
     for (Agent *a : agents) total += a->n;
     small_grid = std::max(1, std::min(grid, (total + kGroupsPerCta - 1) / kGroupsPerCta));
   }
   dSlots.alloc((size_t)2 * grid * kRed);
+  dDefer.alloc((size_t)agents.size() * grid * (kThreads / 32) * 8);
   T.gs.counter = dBar.p;
   T.gs.slots = dSlots.p;
+  T.defer = dDefer.p;
   T.ctl = reinterpret_cast<TeamCtl *>(d_result);
   T.prof = prof_iters > 0 ? dProf.p : nullptr;
   T.prof_iters = prof_iters;
   T.prof_cta = prof_cta;
+  T.done_counter = dBar.p + 2;
   team_dirty = false;
 }
 
@@ -825,14 +837,16 @@ void Team::layout_result() {
     off += up(a->outbox_doubles() * sizeof(double), 256);
   }
   if (off != result_bytes) {
-    if (d_result) cudaFree(d_result);
+    cuda_check(cudaDeviceSynchronize(), "sync before result realloc");
     if (h_result) cudaFreeHost(h_result);
     d_result = h_result = nullptr;
-    cuda_check(cudaMalloc((void **)&d_result, off), "cudaMalloc result");
-    cuda_check(cudaMallocHost((void **)&h_result, off), "cudaMallocHost result");
+    // zero-copy: the kernels write control state, statistics and outboxes straight into mapped
+    // pinned host memory, so the per-robot API needs no D2H copy call after a launch
+    cuda_check(cudaHostAlloc((void **)&h_result, off, cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc");
+    cuda_check(cudaHostGetDevicePointer((void **)&d_result, h_result, 0), "cudaHostGetDevicePointer");
     result_bytes = off;
   }
-  cuda_check(cudaMemset(d_result, 0, result_bytes), "cudaMemset result");
+  cuda_check(cudaDeviceSynchronize(), "sync before result reset");
   std::memset(h_result, 0, result_bytes);
   for (size_t i = 0; i < agents.size(); ++i) {
     Agent *a = agents[i];
@@ -886,9 +900,36 @@ void Team::read_back() {
 // copy of the result block [ctl | stats | outboxes], synchronise once
 void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, float *ms) {
   RunArgs args = args_in;
+  args.seq = ++seq;
+  // Nesterov sequences (a7): gamma_k = (1 + sqrt(1 + 4 N^2 gamma_{k-1}^2)) / 2N, alpha_k = 1 / (gamma_k N),
+  // reset on restart iterations ((iter + 1) % restartInterval == 0)
+  const dpgo_b200_params &P = agents[0]->P;
+  const int N = P.num_robots;
+  args.gamma_tab = nullptr;
+  if (P.acceleration) {
+    const int K = args.max_iters;
+    h_gamma_tab.resize(K);
+    h_gamma_state.resize(K);
+    double g = gamma_state;
+    for (int i = 0; i < K; ++i) {
+      g = next_gamma(g, N);
+      h_gamma_tab[i] = make_double2(g, 1.0 / (g * N));
+      if ((ctl.iter + i + 2) % P.restart_interval == 0) g = 0;  // restart after this iteration
+      h_gamma_state[i] = g;
+    }
+    if (K == 1) {
+      args.gamma0 = h_gamma_tab[0].x;
+      args.alpha0 = h_gamma_tab[0].y;
+    } else {
+      dGammaTab.alloc(std::max<size_t>(dGammaTab.n, (size_t)K), false);
+      cuda_check(cudaMemcpyAsync(dGammaTab.p, h_gamma_tab.data(), sizeof(double2) * K, cudaMemcpyHostToDevice, stream),
+                 "H2D gamma table");
+      args.gamma_tab = dGammaTab.p;
+    }
+  }
+  ctl.gamma = gamma_state;
   args.ctl_in = ctl;
-  TeamDev Tl = T;
-  Tl.gs.counter = dBar.p + (use_grid == grid ? 0 : 1);
+  const TeamDev &Tl = T;
   if (timed) cuda_check(cudaEventRecord(ev0, stream), "eventRecord");
   if (args.force_selected == -1 && args.max_iters == 1)
     cuda_check(launch_nesterov_only(Tl, args, use_grid, stream), "launch k_nesterov_only");
@@ -896,10 +937,29 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
     cuda_check(launch_team_run(Tl, args, use_grid, stream), "launch k_team_run");
   if (timed) cuda_check(cudaEventRecord(ev1, stream), "eventRecord");
   ++launches;
-  cuda_check(cudaMemcpyAsync(h_result, d_result, result_bytes, cudaMemcpyDeviceToHost, stream), "D2H result");
-  cuda_check(cudaStreamSynchronize(stream), "k_team_run");
-  if (timed && ms) cudaEventElapsedTime(ms, ev0, ev1);
+  if (timed) {
+    cuda_check(cudaEventSynchronize(ev1), "k_team_run");
+    if (ms) cudaEventElapsedTime(ms, ev0, ev1);
+  }
+  wait_result(args.seq);
   read_back();
+  if (P.acceleration && ctl.iters_done > 0) gamma_state = h_gamma_state[ctl.iters_done - 1];
+  ctl.gamma = gamma_state;
+}
+
+// completion: poll the sequence number the kernel publishes (after a system-scope fence) in the
+// mapped result block -- cheaper than a stream synchronisation for 10-us kernels
+void Team::wait_result(unsigned long long expect) {
+  volatile TeamCtl *c = reinterpret_cast<volatile TeamCtl *>(h_result);
+  unsigned spins = 0;
+  while (c->seq != expect) {
+    if ((++spins & 0x3fff) == 0) {
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) cuda_check(q, "k_team_run");
+      if (q == cudaSuccess && c->seq != expect) fail(DPGO_B200_ERR_CUDA, "kernel finished without publishing its result");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
 }
 
 void Team::run_forced(int sel_local) {
@@ -925,7 +985,7 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
   int remaining = max_iters;
   while (remaining > 0) {
     RunArgs args{};
-    args.max_iters = remaining;
+    args.max_iters = std::min(remaining, 1 << 16);
     args.force_selected = -2;
     args.stop_on_terminate = stop_on_terminate ? 1 : 0;
     float ms = 0;
@@ -951,8 +1011,6 @@ void Team::exchange_all() {
   // persistent kernel uses: a forced iteration count of zero does nothing, so
   // use the dedicated kernel
   cuda_check(launch_publish_all(T, grid, stream), "publish_all");
-  cuda_check(cudaMemcpyAsync(h_result + 64, d_result + 64, result_bytes - 64, cudaMemcpyDeviceToHost, stream),
-             "D2H result");
   cuda_check(cudaStreamSynchronize(stream), "publish_all");
   for (Agent *a : agents) {
     if (a->state != 2) continue;
@@ -1017,7 +1075,10 @@ void Team::gnc_update_all() {
   }
   ctl.weight_update_count++;
   ctl.robust_inner_iter = 0;
-  if (agents[0]->P.acceleration) ctl.gamma = ctl.alpha = 0;
+  if (agents[0]->P.acceleration) {
+    ctl.gamma = ctl.alpha = 0;
+    gamma_state = 0;
+  }
   team_dirty = true;
   exchange_all();
 }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <set>
@@ -197,6 +198,8 @@ class Team {
   // result block: [TeamCtl | AgentStat per agent | outbox per agent], device + pinned mirror
   unsigned char *d_result = nullptr, *h_result = nullptr;
   size_t result_bytes = 0;
+  unsigned long long seq = 0;
+  void wait_result(unsigned long long expect);
   TeamCtl *h_ctl() const { return reinterpret_cast<TeamCtl *>(h_result); }
   void layout_result();
   int small_grid = 1;
@@ -207,6 +210,12 @@ class Team {
   TeamCtl ctl{};
   DevBuf<unsigned long long> dBar;
   DevBuf<double> dSlots;
+  DevBuf<double> dDefer;
+  DevBuf<double2> dGammaTab;
+  std::vector<double2> h_gamma_tab;
+  std::vector<double> h_gamma_state;
+  double gamma_state = 0;  // Nesterov gamma after the last executed iteration (0 after a restart)
+  static double next_gamma(double g, int N) { return (1.0 + std::sqrt(1.0 + 4.0 * N * N * g * g)) / (2.0 * N); }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool team_dirty = true;
   int launches = 0;

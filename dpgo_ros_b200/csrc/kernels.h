@@ -13,6 +13,11 @@ struct RunArgs {
   int leader;          // robot id whose turn triggers the termination / weight-update test
   size_t slab_cap;     // bytes of shared memory reserved for the preconditioner slab (set by the launcher)
   TeamCtl ctl_in;      // control state at entry (the kernel writes the exit state to TeamDev::ctl)
+  unsigned long long seq;  // completion sequence number the kernel publishes in TeamCtl::seq
+  // Nesterov sequences are produced on the host (one arithmetic for every path): per-iteration
+  // (gamma_t, alpha_t) table for multi-iteration launches, or the single pair below
+  const double2 *gamma_tab;
+  double gamma0, alpha0;
 };
 
 // non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel
@@ -38,7 +43,8 @@ cudaError_t launch_precond(const AgentDev &A, const double *X, const double *V, 
                            int grid, cudaStream_t s);
 cudaError_t launch_manifold_op(int op, int r, int n, const double *A, const double *B, double *out, int grid,
                                cudaStream_t s);
-cudaError_t launch_barrier_bench(const GridSync &gs, int iters, int mode, double *out, int grid, cudaStream_t s);
+cudaError_t launch_barrier_bench(const GridSync &gs, int iters, int mode, unsigned epoch0, double *out, int grid,
+                                 cudaStream_t s);
 cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s);
 cudaError_t launch_gnc_weights(const LcDev &L, int r, const double *X, const double *inbox, double barc_sq,
                                double mu, int cost_type, cudaStream_t s);

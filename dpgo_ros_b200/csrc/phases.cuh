@@ -21,19 +21,33 @@
 
 namespace dpgo {
 
+// debug timeline (diagnostics): clock64() marks of CTA 0 / thread 0, enabled by launch_set_dbg()
+static __device__ long long *g_dbg = nullptr;
+#define DBG(k) do { if (g_dbg && threadIdx.x == 0 && blockIdx.x == 0) g_dbg[(k)] = clock64(); } while (0)
+
 // ---- pose -> 8-lane-group mapping --------------------------------------------
 // item (pose) = blockIdx.x + gridDim.x * (local_group + 32 k): consecutive poses
 // land on different SMs so a 300-pose agent is spread over the whole chip.
 struct PoseIter {
   int a;       // row handled by this lane
-  int lg;      // local group id 0..31
+  int lg;      // local group id 0..31 (absolute: also selects the staging tile)
   int k;       // loop counter
-  __device__ __forceinline__ PoseIter() : a(threadIdx.x & 7), lg(threadIdx.x >> 3), k(0) {}
+  int lgp;     // group id within the participating warp subset (< 0: this warp sits the phase out)
+  int gpc;     // participating groups per CTA
+  __device__ __forceinline__ PoseIter() : a(threadIdx.x & 7), lg(threadIdx.x >> 3), k(0), lgp(threadIdx.x >> 3),
+                                          gpc(kGroupsPerCta) {}
+  // restrict the phase to warps [warp_lo, warp_lo + warp_cnt) so two independent phases can run side by side
+  __device__ __forceinline__ PoseIter(int warp_lo, int warp_cnt)
+      : a(threadIdx.x & 7), lg(threadIdx.x >> 3), k(0), gpc(4 * warp_cnt) {
+    const int w = (int)(threadIdx.x >> 5) - warp_lo;
+    lgp = (w >= 0 && w < warp_cnt) ? lg - 4 * warp_lo : -1;
+  }
   // warp-uniform "any lane of my warp still has work" + my item
   __device__ __forceinline__ bool next(int total, int &item) {
-    const int g0 = (lg & ~3) + 32 * k;  // first group of my warp at this step
+    if (lgp < 0) return false;
+    const int g0 = (lgp & ~3) + gpc * k;  // first group of my warp at this step
     if ((int)blockIdx.x + (int)gridDim.x * g0 >= total) return false;
-    item = (int)blockIdx.x + (int)gridDim.x * (lg + 32 * k);
+    item = (int)blockIdx.x + (int)gridDim.x * (lgp + gpc * k);
     ++k;
     return true;
   }
@@ -68,64 +82,86 @@ __device__ __forceinline__ int gshfl(int v, int src) { return __shfl_sync(0xffff
 // Publishes Y (aux) and, for non-selected agents, X (reg) into the neighbours'
 // inboxes (a9: getAuxSharedPoseDictWithNeighbor :666 / updateAuxNeighborPoses :1278).
 // ---------------------------------------------------------------------------
-#define DBG(k) if (T.prof && threadIdx.x == 0 && (int)blockIdx.x == T.prof_cta) T.prof[4096 + (k)] = clock64();
+// per-pose body (group-collective)
+template <int RC>
+__device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, bool valid, int a, int sel_local,
+                                              bool restart, double alpha) {
+  const AgentDev &A = T.ag[ai];
+  const int r = rdim<RC>(A);
+  const bool act = valid && a < r;
+  const size_t off = (size_t)j * 4 * r;
+  double x[4], v[4], m[4];
+  int pe0 = 0, pe1 = 0;
+  if (valid) {
+    pe0 = A.pub_rowptr[j];
+    pe1 = A.pub_rowptr[j + 1];
+  }
+  ld4(A.X + off, r, a, act, x);
+  if (restart) {
+    if (ai != sel_local && valid) {
+      st4(A.V + off, r, a, act, x);
+      st4(A.Y + off, r, a, act, x);
+      publish_range(pe0, pe1, A.pub_dst_aux, r, a, act, x);
+      publish_range(pe0, pe1, A.pub_dst_reg, r, a, act, x);
+    }
+    return;
+  }
+  ld4(A.V + off, r, a, act, v);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) m[c] = (1.0 - alpha) * x[c] + alpha * v[c];
+  if (!valid) {  // keep idle groups on the fast path of sym3_invsqrt
+    m[0] = (a == 0);
+    m[1] = (a == 1);
+    m[2] = (a == 2);
+  }
+  stiefel_project_row(m);
+  if (valid) {
+    st4(A.Y + off, r, a, act, m);
+    publish_range(pe0, pe1, A.pub_dst_aux, r, a, act, m);
+    if (ai != sel_local) {
+      st4(A.X + off, r, a, act, m);
+      publish_range(pe0, pe1, A.pub_dst_reg, r, a, act, m);
+    }
+  }
+}
+
+// pose -> group by PoseIter (stand-alone kernels)
+template <int RC>
 __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, bool restart, double alpha) {
   PoseIter it;
   const int total = T.pose_prefix[T.num_local];
   int item;
-  DBG(0)
   while (it.next(total, item)) {
     const bool valid = item < total;
     int ai = 0;
     if (valid) {
       while (item >= T.pose_prefix[ai + 1]) ++ai;
     }
-    const AgentDev &A = T.ag[ai];
-    const int j = valid ? item - T.pose_prefix[ai] : 0;
-    const int r = A.r;
-    const bool act = valid && it.a < r;
-    const size_t off = (size_t)j * 4 * r;
-    double x[4], v[4], m[4];
-    int pe0 = 0, pe1 = 0;
-    if (valid) {
-      pe0 = A.pub_rowptr[j];
-      pe1 = A.pub_rowptr[j + 1];
-    }
-    ld4(A.X + off, r, it.a, act, x);
-    if (restart) {
-      if (ai != sel_local && valid) {
-        st4(A.V + off, r, it.a, act, x);
-        st4(A.Y + off, r, it.a, act, x);
-        publish_range(pe0, pe1, A.pub_dst_aux, r, it.a, act, x);
-        publish_range(pe0, pe1, A.pub_dst_reg, r, it.a, act, x);
-      }
-      continue;
-    }
-    DBG(1)
-    ld4(A.V + off, r, it.a, act, v);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) m[c] = (1.0 - alpha) * x[c] + alpha * v[c];
-    if (!valid) {  // keep idle groups on the fast path of sym3_invsqrt
-      m[0] = (it.a == 0);
-      m[1] = (it.a == 1);
-      m[2] = (it.a == 2);
-    }
-    if (m[0] == 123.456) DBG(7)
-    DBG(2)
-    stiefel_project_row(m);
-    if (m[0] == 123.456) DBG(7)
-    DBG(3)
-    if (valid) {
-      st4(A.Y + off, r, it.a, act, m);
-      publish_range(pe0, pe1, A.pub_dst_aux, r, it.a, act, m);
-      if (ai != sel_local) {
-        st4(A.X + off, r, it.a, act, m);
-        publish_range(pe0, pe1, A.pub_dst_reg, r, it.a, act, m);
-      }
-    }
-    DBG(4)
+    nesterov_pose<RC>(T, ai, valid ? item - T.pose_prefix[ai] : 0, valid, it.a, sel_local, restart, alpha);
   }
-  DBG(5)
+}
+
+// Per-CTA pose ownership used by the persistent kernel: CTA b owns the balanced chunk
+// [p0, p0+np) of EVERY local agent, for the Nesterov phase and for the dense step alike, so a
+// pose's X / V / Y are always written and then re-read by the same CTA (no grid sync needed
+// between the end of one iteration and the Nesterov phase of the next).
+struct ChunkTable {
+  int p0[kMaxLocal], np[kMaxLocal], prefix[kMaxLocal + 1];
+};
+template <int RC>
+__device__ __forceinline__ void phase_nesterov_chunk(const TeamDev &T, const ChunkTable &ct, int sel_local,
+                                                     bool restart, double alpha) {
+  const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
+  const int total = ct.prefix[T.num_local];
+  for (int base = 0; base < total; base += kGroupsPerCta) {
+    const int item = base + lg;
+    const bool valid = item < total;
+    int ai = 0;
+    if (valid) {
+      while (item >= ct.prefix[ai + 1]) ++ai;
+    }
+    nesterov_pose<RC>(T, ai, valid ? ct.p0[ai] + item - ct.prefix[ai] : 0, valid, a, sel_local, restart, alpha);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -154,6 +190,7 @@ __device__ __forceinline__ void ell_gather(const int *ell_col, const double *ell
   double2 *st2 = reinterpret_cast<double2 *>(stage);
 #pragma unroll
   for (int k = 0; k < W; ++k) st2[k * 8 + a] = bq[k];
+  DBG(W == 8 ? 1 : 5);
   // trip 2: the gathered rows
   double xi[W][4];
   int cols[W];
@@ -163,10 +200,14 @@ __device__ __forceinline__ void ell_gather(const int *ell_col, const double *ell
     ld4(Vsrc + (size_t)(cols[k] >= 0 ? cols[k] : 0) * 4 * r, r, a, act && cols[k] >= 0, xi[k]);
   }
   __syncwarp();
+  if (xi[0][0] == 123.456) DBG(15);
+  DBG(W == 8 ? 2 : 6);
 #pragma unroll
   for (int k = 0; k < W; ++k)
     if (cols[k] >= 0) row_times_block(xi[k], stage + k * 16, acc);
   __syncwarp();
+  if (acc[0] == 123.456) DBG(15);
+  DBG(W == 8 ? 3 : 7);
   // overflow (poses with more than W blocks): plain CSR walk
   for (int e = o0; e < o1; ++e) {
     double xo[4];
@@ -184,11 +225,13 @@ constexpr int kStageStride = 8 * 16 + 4;  // doubles per group staging tile (+4:
 // Writes G (if build_g), S = sym(Y^T egrad_Y) per pose, Rg and its row-major
 // copy RgT.  Accumulates partial f and |rgrad|^2.
 // ---------------------------------------------------------------------------
+template <int RC>
 __device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin, const double *inbox, bool build_g,
                                            double *Sout, double *Rgout, double *RgTout, double *egrad_out,
-                                           double *stage_all, double &pf, double &pg2) {
-  PoseIter it;
-  const int n = A.n, r = A.r;
+                                           double *stage_all, double &pf, double &pg2, int warp_lo = 0,
+                                           int warp_cnt = kThreads / 32) {
+  PoseIter it(warp_lo, warp_cnt);
+  const int n = A.n, r = rdim<RC>(A);
   const size_t n4 = (size_t)4 * n;
   double *stage = stage_all + (size_t)it.lg * kStageStride;
   int j;
@@ -197,6 +240,7 @@ __device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin,
     const bool act = valid && it.a < r;
     const size_t off = (size_t)(valid ? j : 0) * 4 * r;
     double x[4], accq[4] = {0, 0, 0, 0}, accg[4] = {0, 0, 0, 0};
+    DBG(0);
     ld4(Xin + off, r, it.a, act, x);
     if (!build_g) ld4(A.G + off, r, it.a, act, accg);
     ell_gather<8>(A.qe_col, A.qe_val, A.qo_rowptr, A.qo_col, A.qo_val, Xin, j, valid, r, it.a, act, stage, accq);
@@ -212,8 +256,11 @@ __device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin,
       pf += (0.5 * accq[c] + accg[c]) * x[c];
     }
     if (egrad_out) st4(egrad_out + off, r, it.a, act, eg);
+    DBG(8);
     const Sym3 S = sym_ytz(x, eg);
     sub_y_sym(x, S, eg);
+    if (eg[0] == 123.456) DBG(15);
+    DBG(9);
 #pragma unroll
     for (int c = 0; c < 4; ++c) pg2 += eg[c] * eg[c];
     if (valid) {
@@ -235,10 +282,11 @@ __device__ __forceinline__ void phase_grad(const AgentDev &A, const double *Xin,
 //   H = Proj_Xbase( V Q - V_Y * S ),  S = sym(Y^T egrad_Y) cached per pose.
 // pvh accumulates <V, H>.
 // ---------------------------------------------------------------------------
+template <int RC>
 __device__ __forceinline__ void phase_hess(const AgentDev &A, const double *Xbase, const double *S,
                                            const double *Vin, double *Hout, double *stage_all, double &pvh) {
   PoseIter it;
-  const int n = A.n, r = A.r;
+  const int n = A.n, r = rdim<RC>(A);
   double *stage = stage_all + (size_t)it.lg * kStageStride;
   int j;
   while (it.next(n, j)) {
@@ -340,29 +388,52 @@ __device__ __forceinline__ void slab_prefetch(const AgentDev &A, int ai, SlabSta
   ss.pending = 1;
 }
 
-// acc over one pass of <= 3 poses (12 columns) whose columns start at `cols`
+// columns (poses x 4) one thread accumulates per pass: 12 while the R x 12 accumulator fits the
+// register file next to the prefetched V^T values, 8 for the larger ranks
+template <int R>
+struct DensePassCols {
+  static constexpr int value = (R <= 6) ? 12 : 8;
+};
+
+// acc over one pass of <= DensePassCols/4 poses whose columns start at `cols`
 // (shared memory or global, column stride ld); result to zs[pose][c][8].
 template <int R>
 __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const double *VT, int r, int n4, int npass,
                                            double *zs, double *red /* [8 warps][16 cols][8] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncols = npass * 4;
-  double acc[R][12];
+  constexpr int NC = DensePassCols<R>::value;  // columns held per thread (register budget)
+  double acc[R][NC];
 #pragma unroll
   for (int a = 0; a < R; ++a)
 #pragma unroll
-    for (int c = 0; c < 12; ++c) acc[a][c] = 0.0;
-  for (int q = threadIdx.x; q < n4; q += kThreads) {
-    double vr[R], pv[12];
+    for (int c = 0; c < NC; ++c) acc[a][c] = 0.0;
+  // q-strided accumulation; the V^T values of a whole chunk of q-iterations are requested up front
+  // (one L2 round trip per chunk instead of one per iteration)
+  constexpr int QC = (R <= 5) ? 3 : 2;
+  for (int q0 = threadIdx.x; q0 < n4; q0 += kThreads * QC) {
+    double vr[QC][R];
 #pragma unroll
-    for (int a = 0; a < R; ++a) vr[a] = (a < r) ? VT[(size_t)a * n4 + q] : 0.0;
+    for (int i = 0; i < QC; ++i) {
+      const int q = q0 + kThreads * i;
 #pragma unroll
-    for (int c = 0; c < 12; ++c) pv[c] = (c < ncols) ? cols[(size_t)c * ld + q] : 0.0;
+      for (int a = 0; a < R; ++a) vr[i][a] = (a < r && q < n4) ? VT[(size_t)a * n4 + q] : 0.0;
+    }
 #pragma unroll
-    for (int c = 0; c < 12; ++c)
+    for (int i = 0; i < QC; ++i) {
+      const int q = q0 + kThreads * i;
+      if (q < n4) {
 #pragma unroll
-      for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[a], pv[c], acc[a][c]);
+        for (int c = 0; c < NC; ++c) {
+          const double pv = (c < ncols) ? cols[(size_t)c * ld + q] : 0.0;
+#pragma unroll
+          for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[i][a], pv, acc[a][c]);
+        }
+      }
+    }
   }
+  if (acc[0][0] == 123.456) DBG(31);
+  DBG(17);
   // reduce-scatter over 16 (12 + 4 zero) columns: xor 1, 2, 4, 8 then butterfly 16
   double h8[R][8], h4[R][4], h2[R][2], h1[R];
   {
@@ -371,7 +442,7 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
     for (int a = 0; a < R; ++a)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const double up = (c + 8 < 12) ? acc[a][c + 8 < 12 ? c + 8 : 0] : 0.0;
+        const double up = (c + 8 < NC) ? acc[a][c + 8 < NC ? c + 8 : 0] : 0.0;
         const double keep = hi ? up : acc[a][c];
         const double send = hi ? acc[a][c] : up;
         h8[a][c] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
@@ -410,6 +481,8 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
       h1[a] = v;
     }
   }
+  if (h1[0] == 123.456) DBG(31);
+  DBG(18);
   // lane l < 16 holds column ((l&1)<<3 | (l&2)<<1 | (l&4)>>1 | (l&8)>>3)
   __syncthreads();  // red reuse
   if (lane < 16) {
@@ -434,13 +507,14 @@ template <int R>
 __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const double *VT, int p0, int np,
                                            SlabState &ss, uint64_t *mbar, double *slab, size_t slab_cap_bytes,
                                            double *zs, double *red) {
-  const int r = A.r, n4 = 4 * A.n;
+  const int r = rdim<R>(A), n4 = 4 * A.n;
   const size_t ldp = agent_ldp(A);
   const int pps = slab_poses(A, np, slab_cap_bytes);
   if (pps <= 0) {
     // slab larger than shared memory: stream the columns from global memory
-    for (int sub = 0; sub < np; sub += 3)
-      dense_pass<R>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(3, np - sub), zs + sub * 32, red);
+    constexpr int NPP = DensePassCols<R>::value / 4;
+    for (int sub = 0; sub < np; sub += NPP)
+      dense_pass<R>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(NPP, np - sub), zs + sub * 32, red);
     __syncthreads();
     return;
   }
@@ -465,8 +539,10 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
       ss.parity ^= 1;
       ss.agent = (s0 == 0) ? ai : -1;
     }
-    for (int sub = 0; sub < cnt; sub += 3)
-      dense_pass<R>(slab + (size_t)4 * sub * ldp, ldp, VT, r, n4, min(3, cnt - sub), zs + (s0 + sub) * 32, red);
+    DBG(16);
+    constexpr int NPP = DensePassCols<R>::value / 4;
+    for (int sub = 0; sub < cnt; sub += NPP)
+      dense_pass<R>(slab + (size_t)4 * sub * ldp, ldp, VT, r, n4, min(NPP, cnt - sub), zs + (s0 + sub) * 32, red);
   }
   if (np > pps) ss.agent = -1;  // the buffer no longer holds sub-chunk 0
   __syncthreads();
@@ -478,9 +554,10 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
 // and the Nesterov V update (a7):
 //   V = proj(V + gamma (X+ - Y))    or, on restart iterations, V = Y = X+.
 // ---------------------------------------------------------------------------
+template <int RC>
 __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid, int a, const double (&xnew)[4],
                                             bool accel, bool restart, double gamma, double *xcopy, double &prel) {
-  const int r = A.r;
+  const int r = rdim<RC>(A);
   const bool act = valid && a < r;
   const size_t off = (size_t)(valid ? j : 0) * 4 * r;
   double xold[4], y[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
@@ -536,12 +613,23 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
                                                bool accel, bool restart, double gamma, SlabState &ss,
                                                uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
                                                double *red, double *xcopy, double &prel) {
-  const int n = A.n, r = A.r;
+  const int n = A.n, r = rdim<R>(A);
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   if (P.rgd_use_precond) {
     int p0, np;
     cta_pose_chunk(n, p0, np);
+    // warm L1 with what the epilogue of this phase reads (state of my poses, publication ranges)
+    if (lg < np && a < 2) {
+      const size_t off = (size_t)(p0 + lg) * 4 * r + a * 16;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.X + off));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.V + off));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.Y + off));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.pub_rowptr + p0 + lg));
+    }
+    DBG(20);
+    // poses of this CTA's chunk are processed by group k (same ownership as phase_nesterov_chunk)
     dense_slab<R>(A, ai, A.RgT, p0, np, ss, mbar, slab, slab_cap, zs, red);
+    DBG(19);
     for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
       const int k = k0 + lg;
       const bool valid = k < np;
@@ -552,6 +640,8 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
 #pragma unroll
       for (int c = 0; c < 4; ++c) z[c] = act ? zs[((valid ? k : 0) * 4 + c) * 8 + a] : 0.0;
       tangent_project_row(y, z);
+      if (z[0] == 123.456) DBG(31);
+      DBG(21);
       double xn[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) xn[c] = y[c] - P.rgd_stepsize * z[c];
@@ -559,7 +649,10 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
         xn[0] = (a == 0); xn[1] = (a == 1); xn[2] = (a == 2);
       }
       qf_row(xn);
-      finish_pose(A, j, valid, a, xn, accel, restart, gamma, xcopy, prel);
+      if (xn[0] == 123.456) DBG(31);
+      DBG(22);
+      finish_pose<R>(A, j, valid, a, xn, accel, restart, gamma, xcopy, prel);
+      DBG(23);
     }
   } else {
     PoseIter it;
@@ -577,7 +670,7 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
         xn[0] = (it.a == 0); xn[1] = (it.a == 1); xn[2] = (it.a == 2);
       }
       qf_row(xn);
-      finish_pose(A, valid ? j : 0, valid, it.a, xn, accel, restart, gamma, xcopy, prel);
+      finish_pose<R>(A, valid ? j : 0, valid, it.a, xn, accel, restart, gamma, xcopy, prel);
     }
   }
 }
@@ -589,7 +682,7 @@ __device__ __forceinline__ void phase_precond(const AgentDev &A, int ai, const d
                                               const double *RinT, double *Zout, double *neg_out, SlabState &ss,
                                               uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
                                               double *red, double &pzr) {
-  const int n = A.n, r = A.r;
+  const int n = A.n, r = rdim<R>(A);
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   int p0, np;
   cta_pose_chunk(n, p0, np);

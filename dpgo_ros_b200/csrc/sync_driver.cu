@@ -8,6 +8,8 @@
 //                   publishStatus (:183), leader: shouldTerminate (:208)
 // One OS thread per robot stands in for the one-process-per-robot deployment.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -104,25 +106,38 @@ extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int s
     }
   };
 
+  const bool prof = getenv("DPGO_B200_DRIVER_PROFILE") != nullptr;
+  double tp[6] = {0, 0, 0, 0, 0, 0};
+  auto now = [] { return std::chrono::high_resolution_clock::now(); };
+  auto since = [](std::chrono::high_resolution_clock::time_point t) {
+    return std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t).count();
+  };
   auto worker = [&](int a) {
     for (int s = 0; s < steps; ++s) {
       const int sel = (start_iter + s) % N;
+      auto t = now();
       if (accelerated) {
         if (a != sel) {
           if (dpgo_b200_iterate(agents[a], 0)) err.store(-1);
+          if (prof && a == (sel + 1) % N) tp[0] += since(t);
           pack(a);
         }
         bar.wait();
+        if (prof && a == 0) { tp[1] += since(t); t = now(); }
         deliver(a, sel, /*except=*/true);  // everything except the selected robot's (not sent yet)
         bar.wait();
+        if (prof && a == 0) { tp[2] += since(t); t = now(); }
       } else if (a != sel) {
         if (dpgo_b200_iterate(agents[a], 0)) err.store(-1);
       }
       if (a == sel) {
+        auto t2 = now();
         if (dpgo_b200_iterate(agents[a], 1)) err.store(-1);
+        if (prof) tp[3] += since(t2);
         pack(a);
       }
       bar.wait();
+      if (prof && a == 0) { tp[4] += since(t); t = now(); }
       deliver(a, sel, /*except=*/false);  // only the selected robot's poses
       if (a == 0) {
         // publishStatus: the leader hears everyone; shouldTerminate on the leader's own turn
@@ -150,6 +165,10 @@ extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int s
   worker(0);
   for (auto &t : th) t.join();
   const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  if (prof)
+    fprintf(stderr, "[sync_driver] per step (us): iterate(false) %.1f | phase1 %.1f | deliver %.1f | iterate(true) %.1f | phase3 %.1f | total %.1f\n",
+            tp[0] / steps * 1e6, tp[1] / steps * 1e6, tp[2] / steps * 1e6, tp[3] / steps * 1e6, tp[4] / steps * 1e6,
+            dt / steps * 1e6);
   if (seconds) *seconds = dt;
   if (payload_bytes) *payload_bytes = bytes.load();
   if (terminated_at) *terminated_at = term.load();

@@ -1,0 +1,601 @@
+// The persistent cooperative kernel k_team_run<R> and its launcher; instantiated once per
+// relaxation rank in team_run_r<R>.cu so the instantiations compile in parallel.
+#pragma once
+#include <algorithm>
+#include <atomic>
+
+#include "kernels.h"
+#include "phases.cuh"
+
+namespace dpgo {
+
+void count_launch();
+
+// dynamic shared memory layout of the persistent kernel:
+//   [ slab (slab_cap bytes) | staging tiles (32 groups) | zs (chunk poses x 32) ]
+struct SmemLayout {
+  double *slab;
+  size_t slab_cap;
+  double *stage;
+  double *zs;
+};
+
+// ---------------------------------------------------------------------------
+// pose-local vector phases used by tCG
+// ---------------------------------------------------------------------------
+// eta (+)= alpha * dlt ;  r = rsrc + alpha * Hd (also row-major copy) ; partial |r|^2
+template <int RC>
+__device__ __forceinline__ void phase_tcg_update(const AgentDev &A, double alpha, bool eta_zero, const double *dlt,
+                                                 const double *Hd, const double *rsrc, double *eta, double *rv,
+                                                 double *rvT, double &prr) {
+  PoseIter it;
+  const int n = A.n, r = rdim<RC>(A);
+  const size_t n4 = (size_t)4 * n;
+  int j;
+  while (it.next(n, j)) {
+    const bool valid = j < n;
+    const bool act = valid && it.a < r;
+    if (!act) continue;
+    const size_t off = (size_t)j * 4 * r;
+    double d[4], h[4], rs[4], e[4];
+    ld4(dlt + off, r, it.a, act, d);
+    ld4(Hd + off, r, it.a, act, h);
+    ld4(rsrc + off, r, it.a, act, rs);
+    if (eta_zero) {
+      e[0] = e[1] = e[2] = e[3] = 0.0;
+    } else {
+      ld4(eta + off, r, it.a, act, e);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      e[c] += alpha * d[c];
+      rs[c] += alpha * h[c];
+      prr += rs[c] * rs[c];
+      rvT[(size_t)it.a * n4 + 4 * j + c] = rs[c];
+    }
+    st4(eta + off, r, it.a, act, e);
+    st4(rv + off, r, it.a, act, rs);
+  }
+}
+
+// eta (+)= tau * dlt  (trust-region boundary / negative curvature exit)
+template <int RC>
+__device__ __forceinline__ void phase_axpy_eta(const AgentDev &A, double tau, bool eta_zero, const double *dlt,
+                                               double *eta) {
+  PoseIter it;
+  const int n = A.n, r = rdim<RC>(A);
+  int j;
+  while (it.next(n, j)) {
+    const bool act = j < n && it.a < r;
+    if (!act) continue;
+    const size_t off = (size_t)j * 4 * r;
+    double d[4], e[4];
+    ld4(dlt + off, r, it.a, act, d);
+    if (eta_zero) {
+      e[0] = e[1] = e[2] = e[3] = 0.0;
+    } else {
+      ld4(eta + off, r, it.a, act, e);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) e[c] += tau * d[c];
+    st4(eta + off, r, it.a, act, e);
+  }
+}
+
+// dlt = -z + beta * dlt
+template <int RC>
+__device__ __forceinline__ void phase_direction(const AgentDev &A, double beta, const double *Z, double *dlt) {
+  PoseIter it;
+  const int n = A.n, r = rdim<RC>(A);
+  int j;
+  while (it.next(n, j)) {
+    const bool act = j < n && it.a < r;
+    if (!act) continue;
+    const size_t off = (size_t)j * 4 * r;
+    double z[4], d[4];
+    ld4(Z + off, r, it.a, act, z);
+    ld4(dlt + off, r, it.a, act, d);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) d[c] = -z[c] + beta * d[c];
+    st4(dlt + off, r, it.a, act, d);
+  }
+}
+
+// out = Retr_x(eta)  (group-collective)
+template <int RC>
+__device__ __forceinline__ void phase_retract(const AgentDev &A, const double *X1, const double *eta, double *out) {
+  PoseIter it;
+  const int n = A.n, r = rdim<RC>(A);
+  int j;
+  while (it.next(n, j)) {
+    const bool valid = j < n;
+    const bool act = valid && it.a < r;
+    const size_t off = (size_t)(valid ? j : 0) * 4 * r;
+    double x[4], e[4];
+    ld4(X1 + off, r, it.a, act, x);
+    ld4(eta + off, r, it.a, act, e);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] += e[c];
+    if (!valid) {
+      x[0] = (it.a == 0); x[1] = (it.a == 1); x[2] = (it.a == 2);
+    }
+    qf_row(x);
+    if (valid) st4(out + off, r, it.a, act, x);
+  }
+}
+
+template <int RC>
+__device__ __forceinline__ void phase_dot(const AgentDev &A, const double *U, const double *W, double &p) {
+  PoseIter it;
+  const int n = A.n, r = rdim<RC>(A);
+  int j;
+  while (it.next(n, j)) {
+    const bool act = j < n && it.a < r;
+    if (!act) continue;
+    const size_t off = (size_t)j * 4 * r;
+    double u[4], w[4];
+    ld4(U + off, r, it.a, act, u);
+    ld4(W + off, r, it.a, act, w);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p += u[c] * w[c];
+  }
+}
+
+// commit x1 as the agent's new X (RTR epilogue); chunk ownership like every writer of X / V / Y
+template <int RC>
+__device__ __forceinline__ void phase_commit(const AgentDev &A, const double *X1, bool accel, bool restart,
+                                             double gamma, double &prel) {
+  const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
+  int p0, np;
+  cta_pose_chunk(A.n, p0, np);
+  for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
+    const int k = k0 + lg;
+    const bool valid = k < np;
+    const int j = p0 + (valid ? k : 0);
+    const int r = rdim<RC>(A);
+    const bool act = valid && a < r;
+    double xn[4];
+    ld4(X1 + (size_t)j * 4 * r, r, a, act, xn);
+    finish_pose<RC>(A, j, valid, a, xn, accel, restart, gamma, nullptr, prel);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// RTR-tCG local solve (a2), ROPTLIB RTRNewton semantics as restated in
+// oracle/dpgo_oracle.cpp (rtrRun): every scalar decision is taken redundantly
+// by all threads from bit-identical reduced values.  The preconditioner slab
+// of this CTA stays resident in shared memory for the whole solve.
+// ---------------------------------------------------------------------------
+struct RtrOut {
+  const double *x;  // final iterate
+  double f_init, gn_init, f_opt, gn_opt;
+  int outer, tcg, rej;
+};
+
+template <int R>
+__device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const SolverParams &P, const GridSync &gs,
+                                            BarState &bs, const double *Xs, const double *inbox, SlabState &ss,
+                                            uint64_t *mbar, const SmemLayout &L, double *red, double *sm) {
+  RtrOut out;
+  out.outer = out.tcg = out.rej = 0;
+  const double *x1 = Xs;
+  double *cand = A.X2;
+  double *Rg1 = A.Rg, *Rg1T = A.RgT, *S1 = A.S;
+  double *Rg2 = A.Rg2, *Rg2T = A.Rg2T, *S2 = A.S2;
+  double v[4];
+  // gradient at the starting point (also assembles G)
+  v[0] = v[1] = v[2] = v[3] = 0;
+  phase_grad<R>(A, x1, inbox, true, S1, Rg1, Rg1T, nullptr, L.stage, v[0], v[1]);
+  grid_reduce<2>(gs, bs, reinterpret_cast<double(&)[2]>(v), sm);
+  double f1 = v[0], ngf = sqrt(v[1]);
+  out.f_init = f1;
+  out.gn_init = ngf;
+  const bool single = (P.rtr_iterations == 1);
+  double Delta = P.rtr_initial_radius;
+  double maxDelta = single ? Delta : 5.0 * P.rtr_initial_radius;
+  int iter = 0, shrink = 0;
+  bool stop = false;
+  const double theta = 1.0, kappa = 0.1;
+  while (true) {
+    if (!single && (stop || iter >= P.rtr_iterations)) break;
+    // ---------------- tCG
+    const double *rsrc = Rg1, *rsrcT = Rg1T;
+    const double norm_r0 = ngf;
+    v[0] = 0;
+    phase_precond<R>(A, ai, x1, rsrc, rsrcT, A.Z, A.dlt0, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
+    grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
+    double z_r = v[0], d_Pd = z_r, e_Pe = 0.0, e_Pd = 0.0;
+    bool eta_zero = true;
+    int status = 4;  // 0 negcurv, 1 exceeded, 2 lcon, 3 scon, 4 maxiter
+    int j = 0;
+    for (j = 0; j < P.rtr_tcg_iterations; ++j) {
+      v[0] = 0;
+      phase_hess<R>(A, x1, S1, A.dlt0, A.Hd, L.stage, v[0]);
+      grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
+      const double d_Hd = v[0];
+      const double alpha = z_r / d_Hd;
+      const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+      if (d_Hd <= 0 || e_Pe_new >= Delta * Delta) {
+        const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
+        phase_axpy_eta<R>(A, tau, eta_zero, A.dlt0, A.eta);
+        eta_zero = false;
+        status = (d_Hd <= 0) ? 0 : 1;
+        break;
+      }
+      e_Pe = e_Pe_new;
+      v[0] = 0;
+      phase_tcg_update<R>(A, alpha, eta_zero, A.dlt0, A.Hd, rsrc, A.eta, A.rv, A.rvT, v[0]);
+      eta_zero = false;
+      grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
+      rsrc = A.rv;
+      rsrcT = A.rvT;
+      const double norm_r = sqrt(v[0]);
+      const double tempnum = pow(norm_r0, theta);
+      if (norm_r <= norm_r0 * fmin(tempnum, kappa)) {
+        status = (kappa < tempnum) ? 2 : 3;
+        break;
+      }
+      v[0] = 0;
+      phase_precond<R>(A, ai, x1, rsrc, rsrcT, A.Z, nullptr, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
+      grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
+      const double zold_rold = z_r;
+      z_r = v[0];
+      const double beta = z_r / zold_rold;
+      phase_direction<R>(A, beta, A.Z, A.dlt0);
+      grid_barrier(gs, bs);
+      e_Pd = beta * (e_Pd + alpha * d_Pd);
+      d_Pd = z_r + beta * beta * d_Pd;
+    }
+    out.tcg += min(j + 1, P.rtr_tcg_iterations);
+    if (eta_zero) {  // maxInner == 0: eta = 0
+      phase_axpy_eta<R>(A, 0.0, true, A.dlt0, A.eta);
+    }
+    grid_barrier(gs, bs);
+    // ---------------- candidate, model decrease, ratio
+    phase_retract<R>(A, x1, A.eta, cand);
+    grid_barrier(gs, bs);
+    v[0] = v[1] = v[2] = v[3] = 0;
+    phase_grad<R>(A, cand, inbox, false, S2, Rg2, Rg2T, nullptr, L.stage, v[0], v[1]);
+    phase_hess<R>(A, x1, S1, A.eta, A.zeta, L.stage, v[2]);
+    phase_dot<R>(A, A.eta, Rg1, v[3]);
+    grid_reduce<4>(gs, bs, v, sm);
+    const double f2 = v[0];
+    const double rho = (f1 - f2) / (-(v[3] + 0.5 * v[2]));
+    if (rho > 0.75) {
+      if (status == 0 || status == 1) Delta = fmin(2.0 * Delta, maxDelta);
+    } else if (rho < 0.25) {
+      Delta = 0.25 * Delta;
+    }
+    const bool accept =
+        (rho > 0.1) || (fabs(f1 - f2) / (fabs(f1) + 1.0) < 1.4901161193847656e-08 && f2 < f1);
+    ++iter;
+    out.outer++;
+    if (accept) {
+      x1 = cand;
+      cand = (cand == A.X2) ? A.X3 : A.X2;
+      f1 = f2;
+      ngf = sqrt(v[1]);
+      double *t;
+      t = Rg1; Rg1 = Rg2; Rg2 = t;
+      t = Rg1T; Rg1T = Rg2T; Rg2T = t;
+      t = S1; S1 = S2; S2 = t;
+    } else {
+      out.rej++;
+    }
+    stop = ngf < P.gradnorm_tol;
+    if (single) {
+      // single-step mode: shrink the radius until the step is accepted
+      if (accept) break;
+      if (shrink > 10) break;  // give up: x1 is still the starting point
+      Delta = maxDelta = maxDelta / 4.0;
+      ++shrink;
+    }
+  }
+  out.x = x1;
+  out.f_opt = f1;
+  out.gn_opt = ngf;
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// deferred reporting sums.  Values nobody needs on the critical path (fInit,
+// gradNormInit, fOpt, gradNormOpt of mLocalOptResult, and the relative change
+// between leader turns) are NOT grid-reduced when they are produced: every warp
+// parks its partial in defer[agent][cta][warp][q] and the totals are formed
+// (fixed order) when somebody can observe them -- at the leader's turn
+// (shouldTerminate, src/PGOAgentROS.cpp:208) and at kernel exit.
+//   q: 0 f_init, 1 |grad_init|^2, 2 f_opt, 3 |grad_opt|^2, 4 |X+ - X|^2
+// ---------------------------------------------------------------------------
+constexpr int kDeferQ = 8;
+__device__ __forceinline__ double *defer_slot(const TeamDev &T, int ai) {
+  return T.defer + (((size_t)ai * gridDim.x + blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5)) * kDeferQ;
+}
+__device__ __forceinline__ void defer_store(const TeamDev &T, int ai, int q, double partial) {
+  partial = wsum32(partial);
+  if ((threadIdx.x & 31) == 0) defer_slot(T, ai)[q] = partial;
+}
+// total of quantity q of agent ai over the whole grid (warp-collective, same order everywhere)
+__device__ __forceinline__ double defer_total(const TeamDev &T, int ai, int q) {
+  const int lane = threadIdx.x & 31;
+  const int entries = (int)gridDim.x * (kThreads / 32);
+  const double *base = T.defer + (size_t)ai * entries * kDeferQ + q;
+  double s = 0;
+  for (int e = lane; e < entries; e += 32) s += __ldcg(base + (size_t)e * kDeferQ);
+  return wsum32(s);
+}
+
+// ---------------------------------------------------------------------------
+// the persistent kernel
+// ---------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1)
+    k_team_run(const __grid_constant__ TeamDev T, const __grid_constant__ RunArgs args) {
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
+  __shared__ double sm_red[64];
+  __shared__ double sm_slab[8 * 16 * 8];
+  __shared__ double sm_rel[kMaxLocal];
+  __shared__ ChunkTable chunks;
+  __shared__ __align__(8) uint64_t mbar;
+  SmemLayout L;
+  L.slab = reinterpret_cast<double *>(dyn_smem_raw);
+  L.slab_cap = args.slab_cap;
+  L.stage = reinterpret_cast<double *>(dyn_smem_raw + args.slab_cap);
+  L.zs = L.stage + kGroupsPerCta * kStageStride;
+  const SolverParams &P = T.p;
+  const GridSync &gs = T.gs;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) g_dbg = T.prof ? T.prof + 4096 : nullptr;
+    mbar_init(&mbar);
+    chunks.prefix[0] = 0;
+    for (int i = 0; i < T.num_local; ++i) {
+      cta_pose_chunk(T.ag[i].n, chunks.p0[i], chunks.np[i]);
+      chunks.prefix[i + 1] = chunks.prefix[i] + chunks.np[i];
+    }
+  }
+  __syncthreads();
+  SlabState ss{-1, 0u, 0};
+  TeamCtl c = args.ctl_in;  // control state: identical in every thread
+  BarState bs;
+  bar_init(gs, bs);
+  const int N = T.num_robots;
+  const bool accel = P.acceleration != 0;
+  const bool use_slab = (P.method == 0) || P.rgd_use_precond;
+  const bool schedule = args.force_selected < -1;
+  int done = 0;
+  int stop_reason = 0;
+  int pend_ai = -1;        // RGD: agent whose post-step statistics (fOpt, gradNormOpt) are still due
+  unsigned touched = 0;    // local agents with deferred sums newer than their AgentStat
+  unsigned rel_due = 0;    // local agents whose relative change has not been totalled yet
+#define PROF(k)                                                                                       \
+  if (T.prof && step < T.prof_iters && threadIdx.x == 0 && (int)blockIdx.x == T.prof_cta)             \
+    T.prof[step * 16 + (k)] = clock64();
+  for (int step = 0; step < args.max_iters; ++step) {
+    const int iter = c.iter + 1;
+    PROF(0)
+    int sel_robot, sel_local;
+    if (!schedule) {
+      sel_local = args.force_selected;
+      sel_robot = sel_local >= 0 ? T.ag[sel_local].id : -1;
+    } else {
+      sel_robot = c.selected;
+      sel_local = T.local_of_robot[sel_robot];
+    }
+    const bool restart = accel && ((iter + 1) % P.restart_interval == 0);
+    // Nesterov sequences come from the host (same arithmetic on every path): gamma_t, alpha_t
+    double gamma = 0, alpha = 0;
+    if (accel) {
+      const double2 ga = args.gamma_tab ? args.gamma_tab[step] : make_double2(args.gamma0, args.alpha0);
+      gamma = ga.x;
+      alpha = ga.y;
+      __syncthreads();  // X / V / Y of my chunk were last written by other threads of this CTA
+      phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha);
+      PROF(1)
+      grid_barrier(gs, bs);
+      PROF(2)
+    }
+    if (sel_local >= 0) {
+      const AgentDev &A = T.ag[sel_local];
+      const bool use_aux = accel && !restart;
+      const double *Xs = use_aux ? A.Y : A.X;
+      const double *inbox = use_aux ? A.inbox_aux : A.inbox_reg;
+      if (use_slab) slab_prefetch(A, sel_local, ss, &mbar, L.slab, L.slab_cap);  // no-op when already in flight
+      if (P.method == 1) {
+        // ---- RGD (a2): gradient (+ the previous step's deferred statistics), preconditioned step
+        // the two gradient passes are independent: warps 0-3 take the step's gradient, warps 4-7 the
+        // deferred statistics of the previous step (both fit: <= 4 groups of 16 per CTA are busy)
+        const bool split = pend_ai >= 0 && A.n <= 16 * (int)gridDim.x && T.ag[pend_ai].n <= 16 * (int)gridDim.x;
+        double pf = 0, pg2 = 0;
+        phase_grad<R>(A, Xs, inbox, true, nullptr, A.Rg, A.RgT, nullptr, L.stage, pf, pg2, 0, split ? 4 : 8);
+        defer_store(T, sel_local, 0, pf);
+        defer_store(T, sel_local, 1, pg2);
+        if (pend_ai >= 0) {
+          const AgentDev &B = T.ag[pend_ai];
+          double qf = 0, qg2 = 0;
+          phase_grad<R>(B, B.X2, nullptr, false, nullptr, nullptr, nullptr, nullptr, L.stage, qf, qg2,
+                        split ? 4 : 0, split ? 4 : 8);
+          defer_store(T, pend_ai, 2, qf);
+          defer_store(T, pend_ai, 3, qg2);
+          pend_ai = -1;
+        }
+        PROF(3)
+        grid_barrier(gs, bs);
+        PROF(4)
+        double prel = 0;
+        phase_rgd_step<R>(A, sel_local, P, Xs, accel, restart, gamma, ss, &mbar, L.slab, L.slab_cap, L.zs, sm_slab,
+                          A.X2, prel);
+        defer_store(T, sel_local, 4, prel);
+        // the next agent's slab is fetched while the following phases run
+        if (use_slab && schedule) {
+          const int nxt = T.local_of_robot[(sel_robot + 1) % N];
+          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, &mbar, L.slab, L.slab_cap);
+        }
+        PROF(5)
+        pend_ai = sel_local;
+        touched |= 1u << sel_local;
+        rel_due |= 1u << sel_local;
+        if (!accel) grid_barrier(gs, bs);  // plain RBCD has no Nesterov phase (and its sync) before the next gradient
+        PROF(6)
+      } else {
+        // ---- RTR (a2)
+        const RtrOut ro = rtr_solve<R>(A, sel_local, P, gs, bs, Xs, inbox, ss, &mbar, L, sm_slab, sm_red);
+        double v[1] = {0};
+        phase_commit<R>(A, ro.x, accel, restart, gamma, v[0]);
+        if (schedule) {
+          const int nxt = T.local_of_robot[(sel_robot + 1) % N];
+          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, &mbar, L.slab, L.slab_cap);
+        }
+        grid_reduce<1>(gs, bs, v, sm_red);
+        const double relchange = sqrt(v[0] / A.n);
+        const bool ready = !(relchange > P.rel_change_tol);
+        if (ready)
+          c.ready_mask |= (1ull << sel_robot);
+        else
+          c.ready_mask &= ~(1ull << sel_robot);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+          AgentStat *st = A.stat;
+          st->f_init = ro.f_init; st->f_opt = ro.f_opt; st->gn_init = ro.gn_init; st->gn_opt = ro.gn_opt;
+          st->tcg_iters = ro.tcg; st->rtr_outer = ro.outer; st->rtr_rej = ro.rej;
+          st->relchange = relchange;
+          st->ready = ready;
+          st->optimized = 1;
+        }
+      }
+    }
+    c.iter = iter;
+    if (P.robust) c.robust_inner_iter++;
+    ++done;
+    if (schedule) {
+      c.selected = (sel_robot + 1) % N;  // RoundRobin, src/PGOAgentROS.cpp:464-472
+      if (sel_robot == args.leader) {    // leader decides, :207-217
+        if (rel_due) {
+          // total the parked relative changes of every agent that stepped since the last turn
+          grid_barrier(gs, bs);
+          if ((threadIdx.x >> 5) == 0) {
+            for (int ai = 0; ai < T.num_local; ++ai)
+              if (rel_due & (1u << ai)) {
+                const double t = defer_total(T, ai, 4);
+                if (threadIdx.x == 0) sm_rel[ai] = t;
+              }
+          }
+          __syncthreads();
+          for (int ai = 0; ai < T.num_local; ++ai)
+            if (rel_due & (1u << ai)) {
+              const double relchange = sqrt(sm_rel[ai] / T.ag[ai].n);
+              const int rid = T.ag[ai].id;
+              if (!(relchange > P.rel_change_tol))
+                c.ready_mask |= (1ull << rid);
+              else
+                c.ready_mask &= ~(1ull << rid);
+            }
+          rel_due = 0;
+        }
+        const unsigned long long all = (N >= 64) ? ~0ull : ((1ull << N) - 1ull);
+        bool terminate;
+        if (iter > P.max_num_iters)
+          terminate = true;
+        else if (P.robust && c.weight_update_count < P.robust_num_weight_updates)
+          terminate = false;
+        else
+          terminate = (c.ready_mask & all) == all;
+        if (terminate) {
+          stop_reason = 1;
+          if (args.stop_on_terminate) break;
+        } else if (P.robust && c.weight_update_count < P.robust_num_weight_updates &&
+                   (c.robust_inner_iter >= P.robust_inner_iters || (c.ready_mask & all) == all)) {
+          stop_reason = 2;
+          break;
+        }
+      }
+    }
+  }
+  // ---- epilogue: everything that was deferred becomes observable now
+  grid_barrier(gs, bs);
+  if (pend_ai >= 0) {
+    // statistics of the last RGD step (mLocalOptResult.fOpt / gradNormOpt, src/PGOAgentROS.cpp:169-172)
+    const AgentDev &B = T.ag[pend_ai];
+    double qf = 0, qg2 = 0;
+    phase_grad<R>(B, B.X2, nullptr, false, nullptr, nullptr, nullptr, nullptr, L.stage, qf, qg2);
+    defer_store(T, pend_ai, 2, qf);
+    defer_store(T, pend_ai, 3, qg2);
+    grid_barrier(gs, bs);
+  }
+  if (touched && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
+    for (int ai = 0; ai < T.num_local; ++ai)
+      if (touched & (1u << ai)) {
+        double t[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) t[q] = defer_total(T, ai, q);
+        if (threadIdx.x == 0) {
+          AgentStat *st = T.ag[ai].stat;
+          const double relchange = sqrt(t[4] / T.ag[ai].n);
+          st->f_init = t[0]; st->gn_init = sqrt(t[1]); st->f_opt = t[2]; st->gn_opt = sqrt(t[3]);
+          st->relchange = relchange;
+          st->ready = !(relchange > P.rel_change_tol);
+          st->optimized = 1;
+          st->tcg_iters = 0; st->rtr_outer = 0; st->rtr_rej = 0;
+        }
+      }
+  }
+  // the ready bits of agents that stepped after the last leader turn (uniform: every thread needs c)
+  if (rel_due) {
+    if ((threadIdx.x >> 5) == 0) {
+      for (int ai = 0; ai < T.num_local; ++ai)
+        if (rel_due & (1u << ai)) {
+          const double t = defer_total(T, ai, 4);
+          if (threadIdx.x == 0) sm_rel[ai] = t;
+        }
+    }
+    __syncthreads();
+    for (int ai = 0; ai < T.num_local; ++ai)
+      if (rel_due & (1u << ai)) {
+        const double relchange = sqrt(sm_rel[ai] / T.ag[ai].n);
+        const int rid = T.ag[ai].id;
+        if (!(relchange > P.rel_change_tol))
+          c.ready_mask |= (1ull << rid);
+        else
+          c.ready_mask &= ~(1ull << rid);
+      }
+  }
+  if (ss.pending) slab_wait(&mbar, ss.parity);  // do not exit with a bulk copy in flight
+  grid_barrier(gs, bs);  // every CTA's result-block writes (outboxes, stats) are ordered before the flag
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c.stop_reason = stop_reason;
+    c.iters_done = done;
+    c.seq = 0;
+    *T.ctl = c;
+    __threadfence_system();
+    reinterpret_cast<volatile TeamCtl *>(T.ctl)->seq = args.seq;
+  }
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024 - 11 * 1024;  // leave room for the static arrays
+
+// slab capacity + total dynamic bytes for a team / agent
+static void smem_plan(int max_n, int grid, bool want_slab, size_t &slab_cap, size_t &total) {
+  const size_t chunk = (size_t)std::max(1, (max_n + grid - 1) / grid);
+  const size_t fixed = (size_t)kGroupsPerCta * kStageStride * sizeof(double) + chunk * 32 * sizeof(double);
+  slab_cap = 0;
+  if (want_slab && fixed + 16 * 1024 < kMaxDynSmem) slab_cap = ((kMaxDynSmem - fixed) / 128) * 128;
+  total = slab_cap + fixed;
+}
+
+template <int R>
+cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream) {
+  int max_n = 1;
+  for (int i = 0; i < T.num_local; ++i) max_n = std::max(max_n, T.ag[i].n);
+  const bool want_slab = (T.p.method == 0) || T.p.rgd_use_precond;
+  size_t slab_cap, smem;
+  smem_plan(max_n, grid, want_slab, slab_cap, smem);
+  args.slab_cap = slab_cap;
+  static std::atomic<size_t> configured{0};
+  if (smem > configured.load()) {
+    cudaError_t err = cudaFuncSetAttribute(k_team_run<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured.store(smem);
+  }
+  void *params[] = {(void *)&T, (void *)&args};
+  count_launch();
+  return cudaLaunchCooperativeKernel((void *)k_team_run<R>, dim3(grid), dim3(kThreads), params, smem, stream);
+}
+
+}  // namespace dpgo

@@ -20,9 +20,11 @@ team.run(20, stop_on_terminate=False)
 names = ["start", "nesterov", "barrier", "grad", "reduce", "rgdstep", "reduce", "grad2", "reduce"]
 for cta in (0, 73, 147):
     iters = 12
-    buf = (C.c_longlong * (iters * 16 + 16))()
+    buf = (C.c_longlong * (iters * 16 + 32))()
     rc = L.dpgo_b200_debug_team_profile(team.h, iters, cta, buf)
-    dbg = np.array(buf[iters * 16:]); print('   nesterov dbg deltas', np.diff(dbg[:6]))
+    dbg = np.array(buf[iters * 16:])
+    print('   grad marks 0..9 (cycles from mark 0):', [int(x - dbg[0]) for x in dbg[:10]])
+    print('   dense marks 20,16,17,18,19,21,22,23 (from 20):', [int(dbg[k] - dbg[20]) for k in (20, 16, 17, 18, 19, 21, 22, 23)])
     a = np.array(buf[:iters * 16]).reshape(iters, 16)
     d = np.diff(a[:, :9], axis=1)
     print(f"cta {cta}: cycles per segment (median over {iters} iters), rc={rc}")
