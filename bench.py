@@ -237,6 +237,10 @@ def main():
 
     peak, peak_src = load_peaks()
     step_bytes, grad_bytes = algorithmic_bytes(pb, CONFIG2["r"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tpath):  # dram__bytes_read+write of one `ncu --set full` capture, per step
+        traffic = json.load(open(tpath))["traffic_bytes_per_step"] * args.steps
     achieved = step_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
     cpu = cpu_reference(args.cpu_steps, 50)
     line = {
@@ -255,7 +259,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "per-robot C ABI (iterate / getSharedPoseDict / updateNeighborPoses), host buffers, 8 agents"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "kernel": "k_team_run<5> (persistent: all phases of all K steps)",
                      "algorithmic_bytes_per_step": step_bytes, "b_grad_per_agent": grad_bytes,
                      "note": "latency-bound by construction: the working set of a step is ~13 MB and L2-resident "
