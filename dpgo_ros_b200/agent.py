@@ -272,6 +272,10 @@ class Team:
         check(st.value, "team_global_cost")
         return float(c)
 
+    def step(self, selected_robot: int, mode: int = 0) -> None:
+        """One global iteration for the local agents of a partial team (multi-GPU); see dpgo_b200_team_step."""
+        check(self.L.dpgo_b200_team_step(self.h, selected_robot, mode), "team_step")
+
     def set_grid(self, num_ctas: int) -> None:
         check(self.L.dpgo_b200_team_set_grid(self.h, num_ctas), "team_set_grid")
 

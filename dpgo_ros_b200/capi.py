@@ -77,7 +77,7 @@ SYMBOLS = [
     "dpgo_b200_precond", "dpgo_b200_manifold_project", "dpgo_b200_tangent_project", "dpgo_b200_retract",
     "dpgo_b200_team_create", "dpgo_b200_team_destroy", "dpgo_b200_team_add_agent",
     "dpgo_b200_team_exchange_all", "dpgo_b200_team_run", "dpgo_b200_team_global_cost", "dpgo_b200_team_set_grid",
-    "dpgo_b200_sync_driver_run",
+    "dpgo_b200_sync_driver_run", "dpgo_b200_team_step",
 ]
 
 
@@ -155,6 +155,7 @@ def lib():
     L.dpgo_b200_team_global_cost.restype = C.c_double
     L.dpgo_b200_team_global_cost.argtypes = [vp, ip]
     L.dpgo_b200_team_set_grid.argtypes = [vp, C.c_int]
+    L.dpgo_b200_team_step.argtypes = [vp, C.c_int, C.c_int]
     L.dpgo_b200_sync_driver_run.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, dp, C.POINTER(C.c_longlong), ip]
     _LIB = L
     return L

@@ -408,7 +408,15 @@ int dpgo_b200_team_create(int device, dpgo_b200_team_t *out) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
     fail(DPGO_B200_ERR_CUDA, "no usable CUDA device (the RBCD path has no CPU fallback)");
-  *out = new dpgo_b200_team_s{new Team(device)};
+  Team *t = new Team(device);
+  t->device_outbox = true;
+  *out = new dpgo_b200_team_s{t};
+  API_END
+}
+int dpgo_b200_team_step(dpgo_b200_team_t h, int selected_robot, int mode) {
+  API_BEGIN
+  if (mode < 0 || mode > 2) fail(DPGO_B200_ERR_INVALID, "team_step: mode must be 0, 1 or 2");
+  TT(h)->step(selected_robot, mode);
   API_END
 }
 int dpgo_b200_team_destroy(dpgo_b200_team_t h) {

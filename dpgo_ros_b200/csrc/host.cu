@@ -550,8 +550,11 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
   if (!colocated) {
     if (outbox_stale || !outbox_mirror_valid) team->exchange_all();
     const auto rg = outbox_range.at(nbr);
-    const double *src = h_outbox + (aux ? (size_t)std::max(1, outbox_total) * 4 * r : 0) + (size_t)rg.first * 4 * r;
-    std::memcpy(poses, src, pb * cnt);
+    const size_t o = (aux ? (size_t)std::max(1, outbox_total) * 4 * r : 0) + (size_t)rg.first * 4 * r;
+    if (h_outbox)
+      std::memcpy(poses, h_outbox + o, pb * cnt);
+    else
+      cuda_check(cudaMemcpy(poses, d_outbox + o, pb * cnt, cudaMemcpyDeviceToHost), "D2H outbox");
   } else {
     const double *base = aux ? dY.p : dX.p;
     for (int k = 0; k < cnt; ++k)
@@ -832,10 +835,17 @@ void Team::layout_result() {
   auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
   size_t off = up(64 + 128 * agents.size(), 256);
   std::vector<size_t> offs;
+  size_t dev_doubles = 0;
   for (Agent *a : agents) {
-    offs.push_back(off);
-    off += up(a->outbox_doubles() * sizeof(double), 256);
+    if (device_outbox) {
+      offs.push_back(dev_doubles);
+      dev_doubles += up(a->outbox_doubles(), 32);
+    } else {
+      offs.push_back(off);
+      off += up(a->outbox_doubles() * sizeof(double), 256);
+    }
   }
+  if (device_outbox) dOutboxAll.alloc(std::max<size_t>(dev_doubles, 32));
   if (off != result_bytes) {
     cuda_check(cudaDeviceSynchronize(), "sync before result realloc");
     if (h_result) cudaFreeHost(h_result);
@@ -852,8 +862,13 @@ void Team::layout_result() {
     Agent *a = agents[i];
     a->d_stat = reinterpret_cast<AgentStat *>(d_result + 64 + 128 * i);
     a->h_stat = reinterpret_cast<AgentStat *>(h_result + 64 + 128 * i);
-    a->d_outbox = reinterpret_cast<double *>(d_result + offs[i]);
-    a->h_outbox = reinterpret_cast<double *>(h_result + offs[i]);
+    if (device_outbox) {
+      a->d_outbox = dOutboxAll.p + offs[i];
+      a->h_outbox = nullptr;
+    } else {
+      a->d_outbox = reinterpret_cast<double *>(d_result + offs[i]);
+      a->h_outbox = reinterpret_cast<double *>(h_result + offs[i]);
+    }
     a->outbox_stale = true;
     a->outbox_mirror_valid = false;
   }
@@ -917,9 +932,12 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
       if ((ctl.iter + i + 2) % P.restart_interval == 0) g = 0;  // restart after this iteration
       h_gamma_state[i] = g;
     }
-    if (K == 1) {
-      args.gamma0 = h_gamma_tab[0].x;
-      args.alpha0 = h_gamma_tab[0].y;
+    if (args.mode == 2) {  // second half of a split iteration: the sequences were advanced by the first half
+      args.gamma0 = last_gamma_use;
+      args.alpha0 = last_alpha_use;
+    } else if (K == 1) {
+      args.gamma0 = last_gamma_use = h_gamma_tab[0].x;
+      args.alpha0 = last_alpha_use = h_gamma_tab[0].y;
     } else {
       dGammaTab.alloc(std::max<size_t>(dGammaTab.n, (size_t)K), false);
       cuda_check(cudaMemcpyAsync(dGammaTab.p, h_gamma_tab.data(), sizeof(double2) * K, cudaMemcpyHostToDevice, stream),
@@ -931,7 +949,7 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
   args.ctl_in = ctl;
   const TeamDev &Tl = T;
   if (timed) cuda_check(cudaEventRecord(ev0, stream), "eventRecord");
-  if (args.force_selected == -1 && args.max_iters == 1)
+  if ((args.force_selected == -1 || args.mode == 1) && args.max_iters == 1 && args.mode != 2)
     cuda_check(launch_nesterov_only(Tl, args, use_grid, stream), "launch k_nesterov_only");
   else
     cuda_check(launch_team_run(Tl, args, use_grid, stream), "launch k_team_run");
@@ -943,7 +961,7 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
   }
   wait_result(args.seq);
   read_back();
-  if (P.acceleration && ctl.iters_done > 0) gamma_state = h_gamma_state[ctl.iters_done - 1];
+  if (P.acceleration && ctl.iters_done > 0 && args.mode != 2) gamma_state = h_gamma_state[ctl.iters_done - 1];
   ctl.gamma = gamma_state;
 }
 
@@ -968,6 +986,39 @@ void Team::run_forced(int sel_local) {
   args.max_iters = 1;
   args.force_selected = sel_local;
   launch_and_read(args, sel_local < 0 ? small_grid : grid, false, nullptr);
+}
+
+// One global iteration for the LOCAL agents of a team that holds only part of the robots
+// (multi-GPU): mode 0 = whole iterate; mode 1 = Nesterov half (everyone's Y, non-selected X = Y,
+// publication) ; mode 2 = the selected robot's local solve, after the neighbours' poses of this
+// iteration arrived (the gate of src/PGOAgentROS.cpp:136-149).
+void Team::step(int selected_robot, int mode) {
+  prepare();
+  const dpgo_b200_params &P = agents[0]->P;
+  int sel_local = -1;
+  for (size_t i = 0; i < agents.size(); ++i)
+    if (agents[i]->id == selected_robot) sel_local = (int)i;
+  if (mode == 2 && sel_local < 0) return;
+  if (!P.acceleration && sel_local < 0) {  // plain RBCD: iterate(false) only counts
+    if (mode != 2) {
+      ctl.iter++;
+      if (P.cost_type != 0) ctl.robust_inner_iter++;
+      for (Agent *a : agents) {
+        a->iter = ctl.iter;
+        a->robust_inner_iter = ctl.robust_inner_iter;
+      }
+    }
+    return;
+  }
+  if (!P.acceleration && mode == 1) {  // nothing to do before the exchange; the solve half counts the iteration
+    return;
+  }
+  RunArgs args{};
+  args.max_iters = 1;
+  args.force_selected = sel_local;
+  args.mode = P.acceleration ? mode : 0;
+  const bool small = (args.mode == 1) || sel_local < 0;
+  launch_and_read(args, small ? small_grid : grid, false, nullptr);
 }
 
 dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {

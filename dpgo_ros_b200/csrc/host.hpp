@@ -199,6 +199,12 @@ class Team {
   unsigned char *d_result = nullptr, *h_result = nullptr;
   size_t result_bytes = 0;
   unsigned long long seq = 0;
+  // explicit (multi-agent / multi-GPU) teams keep the outboxes in DEVICE memory so that NCCL / peer
+  // copies can read them; the implicit team of a stand-alone agent keeps them in the mapped host block
+  bool device_outbox = false;
+  DevBuf<double> dOutboxAll;
+  double last_gamma_use = 0, last_alpha_use = 0;
+  void step(int selected_robot, int mode);
   void wait_result(unsigned long long expect);
   TeamCtl *h_ctl() const { return reinterpret_cast<TeamCtl *>(h_result); }
   void layout_result();

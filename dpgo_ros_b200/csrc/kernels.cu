@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kThreads) k_nesterov_only(const __grid_constan
   const int iter = c.iter + 1;
   const bool accel = T.p.acceleration != 0;
   const bool restart = accel && ((iter + 1) % T.p.restart_interval == 0);
-  if (accel) phase_nesterov<0>(T, -1, restart, args.alpha0);
+  if (accel) phase_nesterov<0>(T, args.force_selected, restart, args.alpha0);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();

@@ -18,6 +18,9 @@ struct RunArgs {
   // (gamma_t, alpha_t) table for multi-iteration launches, or the single pair below
   const double2 *gamma_tab;
   double gamma0, alpha0;
+  // single-iteration split used when the public poses cross GPUs between the two halves:
+  //   0 full iterate, 1 Nesterov phase only (iteration counter advances), 2 local solve only
+  int mode;
 };
 
 // non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (T.prof && step < T.prof_iters && threadIdx.x == 0 && (int)blockIdx.x == T.prof_cta)             \
     T.prof[step * 16 + (k)] = clock64();
   for (int step = 0; step < args.max_iters; ++step) {
-    const int iter = c.iter + 1;
+    const int iter = (args.mode == 2) ? c.iter : c.iter + 1;
     PROF(0)
     int sel_robot, sel_local;
     if (!schedule) {
@@ -387,11 +387,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       const double2 ga = args.gamma_tab ? args.gamma_tab[step] : make_double2(args.gamma0, args.alpha0);
       gamma = ga.x;
       alpha = ga.y;
-      __syncthreads();  // X / V / Y of my chunk were last written by other threads of this CTA
-      phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha);
-      PROF(1)
-      grid_barrier(gs, bs);
-      PROF(2)
+      if (args.mode != 2) {
+        __syncthreads();  // X / V / Y of my chunk were last written by other threads of this CTA
+        phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha);
+        PROF(1)
+        grid_barrier(gs, bs);
+        PROF(2)
+      }
     }
     if (sel_local >= 0) {
       const AgentDev &A = T.ag[sel_local];
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
     c.iter = iter;
-    if (P.robust) c.robust_inner_iter++;
+    if (P.robust && args.mode != 2) c.robust_inner_iter++;
     ++done;
     if (schedule) {
       c.selected = (sel_robot + 1) % N;  // RoundRobin, src/PGOAgentROS.cpp:464-472

@@ -163,6 +163,12 @@ int dpgo_b200_team_destroy(dpgo_b200_team_t t);
 int dpgo_b200_team_add_agent(dpgo_b200_team_t t, dpgo_b200_agent_t a);
 int dpgo_b200_team_exchange_all(dpgo_b200_team_t t);   /* publishPublicPoses for every pair, :662-690 */
 int dpgo_b200_team_run(dpgo_b200_team_t t, int max_iters, int stop_on_terminate, dpgo_b200_run_result *out);
+/* One global iteration for a team that holds only PART of the robots (one team per GPU).
+ * mode 0: whole iterate of every local agent (selected_robot optimises if it is local);
+ * mode 1: Nesterov half -- Y of every local agent, X = Y for the non-selected, outboxes filled;
+ * mode 2: the selected robot's local solve, to be called after its neighbours' poses of this
+ *         iteration were delivered (the gate of src/PGOAgentROS.cpp:136-149).               */
+int dpgo_b200_team_step(dpgo_b200_team_t t, int selected_robot, int mode);
 double dpgo_b200_team_global_cost(dpgo_b200_team_t t, int *status);
 /* tuning knob: CTAs of the persistent kernel (0 = one per SM) */
 int dpgo_b200_team_set_grid(dpgo_b200_team_t t, int num_ctas);

@@ -255,3 +255,65 @@ def test_gnc_team_run_matches_oracle(small_problem):
     for rid in range(2):
         assert np.max(np.abs(agents[rid].lcWeights() - oteam.lc_weights(rid))) < 1e-7
         assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6
+
+
+# ------------------------------------------------------------------ partial teams (the multi-GPU path, emulated on one device)
+@pytest.mark.parametrize("accel,method", [(1, 1), (0, 1), (1, 0)])
+def test_partial_teams_with_device_buffer_exchange(sphere8_problem, accel, method):
+    """Two explicit teams hold robots 0-3 and 4-7 (what two ranks would hold); public poses move as raw
+    device buffers (outbox -> inbox device pointers), the split Nesterov / solve step of dpgo_b200_team_step
+    gives the selected robot its neighbours' poses of the same iteration (src/PGOAgentROS.cpp:136-149)."""
+    import torch
+    from dpgo_ros_b200 import dist as ddist
+
+    pb = sphere8_problem
+    kw = dict(r=5, method=method, rgd_stepsize=0.2 if accel else 0.05, rgd_use_preconditioner=1, acceleration=accel,
+              restart_interval=6, gradnorm_tol=0.5, rel_change_tol=0.0, max_num_iters=10 ** 6)
+    oteam = orc.OracleTeam(pb, **kw)
+    P = gpu.make_params(num_robots=8, **kw)
+    yl = datasets.fixed_lifting_matrix(5)
+    eye = np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1)
+    teams, agents = [], {}
+    for rk in range(2):
+        tm = gpu.Team(0)
+        for rid in ddist.robots_of_rank(8, 2, rk):
+            ag = gpu.PGOAgent(rid, P, 0)
+            ag.addMeasurements(pb.robot_measurements(rid))
+            ag.setLiftingMatrix(yl)
+            ag.initialize(pb.T_init[rid])
+            ag.initializeInGlobalFrame(eye)
+            tm.add(ag)
+            agents[rid] = ag
+        tm.exchange_all()
+        teams.append(tm)
+    nbrs = {rid: agents[rid].getNeighbors() for rid in range(8)}
+    plan = ddist.build_plan(nbrs, 8, 2, bool(accel))
+    cache = {}
+
+    def tensor(kind, robot, nbr, aux):
+        key = (kind, robot, nbr, aux)
+        if key not in cache:
+            ptr, nbytes = (agents[robot].outboxDevicePtr if kind == "out" else agents[robot].inboxDevicePtr)(nbr, aux)
+            cache[key] = torch.as_tensor(ddist._DevBuf(ptr, nbytes), device="cuda:0")
+        return cache[key]
+
+    def exchange(senders):
+        for t in plan:
+            if t.src_robot in senders:
+                tensor("in", t.dst_robot, t.src_robot, t.aux).copy_(tensor("out", t.src_robot, t.dst_robot, t.aux))
+                agents[t.dst_robot].markInboxUpdated(t.src_robot, t.aux)
+        torch.cuda.synchronize()
+
+    exchange(range(8))
+    for it in range(20):
+        sel = it % 8
+        for tm in teams:
+            tm.step(sel, 1)
+        exchange([r for r in range(8) if r != sel] if accel else [])
+        for tm in teams:
+            tm.step(sel, 2)
+        exchange([sel])
+        oteam.run(1, stop_on_terminate=False)
+        for rid in range(8):
+            assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, (it, rid)
+            assert agents[rid].iteration_number() == it + 1
