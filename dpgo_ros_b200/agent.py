@@ -205,6 +205,18 @@ class PGOAgent:
         k = self.L.dpgo_b200_get_lc_weights(self.h, _dp(buf), buf.size)
         return buf[:k].copy()
 
+    def sharedLoopClosures(self):
+        """(r1, p1, r2, p2, weight, fixed) arrays of every shared loop closure (publishMeasurementWeights, :721-754)."""
+        k = self.L.dpgo_b200_get_shared_loop_closures(self.h, None, None, None, None, None, None, 0)
+        if k < 0:
+            check(k, "sharedLoopClosures")
+        ids = [np.zeros(k, dtype=np.int32) for _ in range(4)]
+        w = np.zeros(k)
+        fx = np.zeros(k, dtype=np.uint8)
+        self.L.dpgo_b200_get_shared_loop_closures(self.h, _ip(ids[0]), _ip(ids[1]), _ip(ids[2]), _ip(ids[3]), _dp(w),
+                                                  fx.ctypes.data_as(C.POINTER(C.c_ubyte)), k)
+        return ids[0], ids[1], ids[2], ids[3], w, fx
+
     def weightUpdateCount(self) -> int:
         return self.L.dpgo_b200_weight_update_count(self.h)
 
@@ -278,6 +290,44 @@ class Team:
 
     def set_grid(self, num_ctas: int) -> None:
         check(self.L.dpgo_b200_team_set_grid(self.h, num_ctas), "team_set_grid")
+
+    # ---- multi-GPU fabric (include/dpgo_b200.h: "multi-GPU fabric") ---------------------------------
+    def fabric_init(self, world: int, rank: int) -> None:
+        check(self.L.dpgo_b200_team_fabric_init(self.h, world, rank), "team_fabric_init")
+
+    def fabric_window(self, want_handle: bool = True) -> Tuple[int, int, bytes]:
+        """(base pointer, bytes, 64-byte CUDA IPC handle) of this rank's window."""
+        base, nbytes = C.c_void_p(), C.c_size_t()
+        hbuf = C.create_string_buffer(64) if want_handle else None
+        check(self.L.dpgo_b200_team_fabric_window(self.h, C.byref(base), C.byref(nbytes), hbuf), "team_fabric_window")
+        return int(base.value or 0), int(nbytes.value), (hbuf.raw if want_handle else b"")
+
+    def fabric_import(self, peer_rank: int, ipc_handle: Optional[bytes] = None, base: Optional[int] = None) -> None:
+        hb = C.create_string_buffer(ipc_handle, 64) if ipc_handle else None
+        check(self.L.dpgo_b200_team_fabric_import(self.h, peer_rank, hb, C.c_void_p(base) if base else None),
+              "team_fabric_import")
+
+    def fabric_route(self, robot: int, neighbor: int, peer_rank: int, off_reg: int, off_aux: int) -> None:
+        check(self.L.dpgo_b200_team_fabric_route(self.h, robot, neighbor, peer_rank, off_reg, off_aux),
+              "team_fabric_route")
+
+    def fabric_run(self, max_iters: int, stop_on_terminate: bool = True) -> RunResult:
+        out = RunResult()
+        check(self.L.dpgo_b200_team_fabric_run(self.h, max_iters, int(stop_on_terminate), C.byref(out)),
+              "team_fabric_run")
+        return out
+
+    def fabric_set_timeout(self, seconds: float) -> None:
+        check(self.L.dpgo_b200_team_fabric_set_timeout(self.h, float(seconds)), "team_fabric_set_timeout")
+
+    def fabric_close(self) -> None:
+        check(self.L.dpgo_b200_team_fabric_close(self.h), "team_fabric_close")
+
+    def gnc_compute_weights(self) -> None:
+        check(self.L.dpgo_b200_team_gnc_compute_weights(self.h), "team_gnc_compute_weights")
+
+    def gnc_finish_update(self) -> None:
+        check(self.L.dpgo_b200_team_gnc_finish_update(self.h), "team_gnc_finish_update")
 
 
 def make_team(problem, ylift: Optional[np.ndarray] = None, device: int = 0, colocate: bool = True, **params):

@@ -49,7 +49,7 @@ class Status(C.Structure):
 
 class RunResult(C.Structure):
     _fields_ = [("iterations", C.c_int), ("terminated", C.c_int), ("weight_updates", C.c_int),
-                ("device_ms", C.c_float), ("kernel_launches", C.c_int)]
+                ("device_ms", C.c_float), ("kernel_launches", C.c_int), ("stop_reason", C.c_int)]
 
 
 # defaults of launch/PGOAgent.launch:9-50 (the values the node actually runs with)
@@ -78,6 +78,10 @@ SYMBOLS = [
     "dpgo_b200_team_create", "dpgo_b200_team_destroy", "dpgo_b200_team_add_agent",
     "dpgo_b200_team_exchange_all", "dpgo_b200_team_run", "dpgo_b200_team_global_cost", "dpgo_b200_team_set_grid",
     "dpgo_b200_sync_driver_run", "dpgo_b200_team_step",
+    "dpgo_b200_team_fabric_init", "dpgo_b200_team_fabric_window", "dpgo_b200_team_fabric_import",
+    "dpgo_b200_team_fabric_route", "dpgo_b200_team_fabric_run", "dpgo_b200_team_fabric_set_timeout",
+    "dpgo_b200_team_fabric_close", "dpgo_b200_team_gnc_compute_weights", "dpgo_b200_team_gnc_finish_update",
+    "dpgo_b200_get_shared_loop_closures",
 ]
 
 
@@ -141,6 +145,7 @@ def lib():
     L.dpgo_b200_robust_weight.restype = C.c_double
     L.dpgo_b200_robust_weight.argtypes = [vp, C.c_double]
     L.dpgo_b200_get_lc_weights.argtypes = [vp, dp, C.c_int]
+    L.dpgo_b200_get_shared_loop_closures.argtypes = [vp, ip, ip, ip, ip, dp, C.POINTER(C.c_ubyte), C.c_int]
     L.dpgo_b200_eval.argtypes = [vp, dp, dp, dp, dp]
     L.dpgo_b200_hess.argtypes = [vp, dp, dp, dp]
     L.dpgo_b200_precond.argtypes = [vp, dp, dp, dp]
@@ -156,6 +161,15 @@ def lib():
     L.dpgo_b200_team_global_cost.argtypes = [vp, ip]
     L.dpgo_b200_team_set_grid.argtypes = [vp, C.c_int]
     L.dpgo_b200_team_step.argtypes = [vp, C.c_int, C.c_int]
+    L.dpgo_b200_team_fabric_init.argtypes = [vp, C.c_int, C.c_int]
+    L.dpgo_b200_team_fabric_window.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), vp]
+    L.dpgo_b200_team_fabric_import.argtypes = [vp, C.c_int, vp, vp]
+    L.dpgo_b200_team_fabric_route.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]
+    L.dpgo_b200_team_fabric_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(RunResult)]
+    L.dpgo_b200_team_fabric_set_timeout.argtypes = [vp, C.c_double]
+    L.dpgo_b200_team_fabric_close.argtypes = [vp]
+    L.dpgo_b200_team_gnc_compute_weights.argtypes = [vp]
+    L.dpgo_b200_team_gnc_finish_update.argtypes = [vp]
     L.dpgo_b200_sync_driver_run.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, dp, C.POINTER(C.c_longlong), ip]
     _LIB = L
     return L

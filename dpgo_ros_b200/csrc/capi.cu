@@ -300,6 +300,28 @@ int dpgo_b200_get_lc_weights(dpgo_b200_agent_t h, double *out, int cap) {
     return e.code;
   }
 }
+int dpgo_b200_get_shared_loop_closures(dpgo_b200_agent_t h, int *r1, int *p1, int *r2, int *p2, double *weight,
+                                       unsigned char *fixed, int cap) {
+  try {
+    Agent *a = A(h);
+    int k = 0;
+    for (auto &m : a->slc) {
+      if (k < cap) {
+        if (r1) r1[k] = m.r1;
+        if (p1) p1[k] = m.p1;
+        if (r2) r2[k] = m.r2;
+        if (p2) p2[k] = m.p2;
+        if (weight) weight[k] = m.weight;
+        if (fixed) fixed[k] = m.fixed ? 1 : 0;
+      }
+      ++k;
+    }
+    return k;
+  } catch (const Error &e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
 int dpgo_b200_weight_update_count(dpgo_b200_agent_t h) {
   return h && h->a ? h->a->weight_update_count : DPGO_B200_ERR_INVALID;
 }
@@ -453,6 +475,68 @@ double dpgo_b200_team_global_cost(dpgo_b200_team_t h, int *status) {
     if (status) *status = e.code;
     return 0.0;
   }
+}
+int dpgo_b200_team_fabric_init(dpgo_b200_team_t h, int world, int rank) {
+  API_BEGIN
+  TT(h)->fabric_init(world, rank);
+  API_END
+}
+int dpgo_b200_team_fabric_window(dpgo_b200_team_t h, void **base, size_t *bytes, void *ipc_handle_64) {
+  API_BEGIN
+  Team *t = TT(h);
+  if (!t->window) fail(DPGO_B200_ERR_STATE, "fabric_window before fabric_init");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  if (base) *base = t->window;
+  if (bytes) *bytes = t->window_bytes;
+  if (ipc_handle_64) {
+    cuda_check(cudaSetDevice(t->device), "cudaSetDevice");
+    cudaIpcMemHandle_t hd;
+    cuda_check(cudaIpcGetMemHandle(&hd, t->window), "cudaIpcGetMemHandle");
+    std::memcpy(ipc_handle_64, &hd, sizeof(hd));
+  }
+  API_END
+}
+int dpgo_b200_team_fabric_import(dpgo_b200_team_t h, int peer_rank, const void *ipc_handle_64,
+                                 void *same_process_base) {
+  API_BEGIN
+  cudaIpcMemHandle_t hd;
+  if (ipc_handle_64) std::memcpy(&hd, ipc_handle_64, sizeof(hd));
+  TT(h)->fabric_import(peer_rank, ipc_handle_64 ? &hd : nullptr, same_process_base);
+  API_END
+}
+int dpgo_b200_team_fabric_route(dpgo_b200_team_t h, int robot, int neighbor, int peer_rank, size_t off_reg,
+                                size_t off_aux) {
+  API_BEGIN
+  TT(h)->fabric_route(robot, neighbor, peer_rank, off_reg, off_aux);
+  API_END
+}
+int dpgo_b200_team_fabric_run(dpgo_b200_team_t h, int max_iters, int stop_on_terminate, dpgo_b200_run_result *out) {
+  API_BEGIN
+  dpgo_b200_run_result r = TT(h)->fabric_run(max_iters, stop_on_terminate != 0);
+  if (out) *out = r;
+  API_END
+}
+int dpgo_b200_team_fabric_set_timeout(dpgo_b200_team_t h, double seconds) {
+  API_BEGIN
+  if (!(seconds > 0)) fail(DPGO_B200_ERR_INVALID, "fabric timeout must be positive");
+  TT(h)->fab_timeout_s = seconds;
+  TT(h)->team_dirty = true;
+  API_END
+}
+int dpgo_b200_team_fabric_close(dpgo_b200_team_t h) {
+  API_BEGIN
+  TT(h)->fabric_close();
+  API_END
+}
+int dpgo_b200_team_gnc_compute_weights(dpgo_b200_team_t h) {
+  API_BEGIN
+  TT(h)->gnc_compute_weights();
+  API_END
+}
+int dpgo_b200_team_gnc_finish_update(dpgo_b200_team_t h) {
+  API_BEGIN
+  TT(h)->gnc_finish_update();
+  API_END
 }
 int dpgo_b200_team_set_grid(dpgo_b200_team_t h, int num_ctas) {
   API_BEGIN

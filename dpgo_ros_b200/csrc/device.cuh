@@ -17,6 +17,7 @@ constexpr int kMaxRobots = 64;   // robots in the whole problem
 constexpr int kThreads = 256;    // CTA size of every kernel here
 constexpr int kGroupsPerCta = kThreads / 8;
 constexpr int kRed = 4;          // doubles per grid reduction
+constexpr int kMaxRanks = 8;     // GPUs (one process each) that run one problem together
 
 struct AgentStat {
   double relchange, f_init, f_opt, gn_init, gn_opt;
@@ -81,12 +82,38 @@ struct TeamCtl {
   unsigned long long seq;  // completion flag: written last, after a system-scope fence (host polls it)
   unsigned epoch;          // grid_sync epoch reached at kernel exit (carried into the next launch)
   unsigned pad;
+  unsigned long long fab_seq;  // multi-GPU: sequence number of the last fabric barrier this rank arrived at
 };
+constexpr size_t kCtlBytes = 128;   // result block: [TeamCtl (padded) | AgentStat x agents (128 B each) | outboxes]
+constexpr size_t kStatBytes = 128;
+static_assert(sizeof(TeamCtl) <= kCtlBytes, "TeamCtl must fit its slot of the result block");
 
 struct GridSync {
   unsigned long long *counter;  // monotonically increasing arrival counter
   double *slots;                // [2][gridDim.x][kRed] reduction partials
 };
+
+// ---------------------------------------------------------------------------
+// Multi-GPU fabric: one persistent kernel per GPU (one process each), all running the SAME
+// global schedule.  Public poses are published by plain stores into the neighbour's inbox,
+// which for a remote neighbour is peer memory of another GPU (CUDA IPC mapping, NVLink), and
+// the ranks keep in step with flag words in each other's window -- the device-side replacement
+// of the PublicPoses topic and of the iteration gate (src/PGOAgentROS.cpp:662-690, 136-149).
+// Every rank's window starts with   flags[kMaxRanks] | payload[2][kMaxRanks]   (u64 each):
+// flags[s] = number of the last fabric barrier rank s arrived at (monotone), payload[q][s] =
+// the word rank s attached to its arrival at a barrier of parity q.
+// ---------------------------------------------------------------------------
+struct Fabric {
+  int world, rank;  // world <= 1: single-GPU team, no fabric
+  unsigned long long *flags;                     // my window
+  unsigned long long *payload;                   // my window, [2][kMaxRanks]
+  unsigned long long *peer_flags[kMaxRanks];     // peers' windows (peer-mapped); [rank] unused
+  unsigned long long *peer_payload[kMaxRanks];
+  unsigned long long seq0;        // barriers completed before this launch
+  unsigned long long local_mask;  // robots that live on this rank
+  unsigned long long timeout_ns;  // a peer that does not show up for this long aborts the launch
+};
+constexpr size_t kFabricHeaderBytes = 3 * kMaxRanks * sizeof(unsigned long long) + 64;  // 256
 
 struct TeamDev {
   int num_local, num_robots;
@@ -101,6 +128,7 @@ struct TeamDev {
   int prof_iters, prof_cta;
   unsigned long long *done_counter;  // last-block-done counter of the non-cooperative kernels
   double *defer;                     // [num_local][grid][warps][8] parked reporting partials
+  Fabric fab;
 };
 
 // relaxation rank: a compile-time constant in the persistent kernel (RC > 0) so that every pose
@@ -318,7 +346,11 @@ __device__ __forceinline__ void qf_row(double (&x)[4]) {
 struct BarState {
   unsigned long long next;  // meaningful in thread 0 only
   int parity;               // reduction slot parity (uniform)
+  int dead;                 // thread 0 only: the counter was poisoned (a fabric wait timed out somewhere)
 };
+// A CTA that gives up on a peer adds this to the arrival counter: every grid barrier of the launch
+// then falls through, so no CTA can be left spinning on one that already left.
+constexpr unsigned long long kBarPoison = 1ull << 48;
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
   unsigned long long v;
@@ -332,6 +364,7 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsig
 __device__ __forceinline__ void bar_init(const GridSync &gs, BarState &bs) {
   bs.next = 0;
   bs.parity = 0;
+  bs.dead = 0;
   if (threadIdx.x == 0) {
     const unsigned long long start = ld_acquire_u64(gs.counter);
     bs.next = (start / gridDim.x) * gridDim.x + gridDim.x;
@@ -342,9 +375,11 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs, BarState &bs) {
   __syncthreads();
   if (threadIdx.x == 0) {
     red_release_add_u64(gs.counter, 1ull);
-    while (ld_acquire_u64(gs.counter) < bs.next) {
+    unsigned long long v;
+    while ((v = ld_acquire_u64(gs.counter)) < bs.next) {
     }
     bs.next += gridDim.x;
+    if (v >= kBarPoison) bs.dead = 1;
   }
   __syncthreads();
 }
@@ -374,9 +409,11 @@ __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, do
       slots[(size_t)blockIdx.x * kRed + k] = s;
     }
     red_release_add_u64(gs.counter, 1ull);
-    while (ld_acquire_u64(gs.counter) < bs.next) {
+    unsigned long long v;
+    while ((v = ld_acquire_u64(gs.counter)) < bs.next) {
     }
     bs.next += gridDim.x;
+    if (v >= kBarPoison) bs.dead = 1;
   }
   __syncthreads();
   // every warp sums the per-CTA partials itself, in the same order
@@ -387,6 +424,77 @@ __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, do
     vals[k] = wsum32(s);
   }
   bs.parity ^= 1;
+}
+
+// ---------------------------------------------------------------------------
+// fabric barrier (multi-GPU).  arrive: call right after a grid barrier that follows this rank's
+// last stores into peer memory -- thread s of CTA 0 then fences at system scope and writes this
+// rank's flag in peer s's window (release/acquire chain: peer stores of any CTA -> grid barrier
+// -> fence.sys -> flag).  wait: lanes 0..world-1 of every CTA poll their peer's flag in the LOCAL
+// window.  Split arrive / wait lets a rank announce "I am done reading my inbox" early.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct FabState {
+  unsigned long long seq;  // barriers this rank arrived at so far (uniform)
+};
+
+__device__ __forceinline__ void fabric_arrive(const Fabric &F, FabState &fs, unsigned long long payload) {
+  ++fs.seq;
+  if (blockIdx.x == 0 && (int)threadIdx.x < F.world && (int)threadIdx.x != F.rank) {
+    __threadfence_system();
+    st_relaxed_sys_u64(F.peer_payload[threadIdx.x] + (fs.seq & 1) * kMaxRanks + F.rank, payload);
+    st_release_sys_u64(F.peer_flags[threadIdx.x] + F.rank, fs.seq);
+  }
+}
+
+// true: every peer arrived at barrier `upto`; false: timed out / the launch is being abandoned
+__device__ __forceinline__ bool fabric_wait(const Fabric &F, const GridSync &gs, BarState &bs, unsigned long long upto) {
+  int bad = (threadIdx.x == 0) ? bs.dead : 0;
+  if (!bad && (int)threadIdx.x < F.world && (int)threadIdx.x != F.rank) {
+    const unsigned long long *f = F.flags + threadIdx.x;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys_u64(f) < upto) {
+      if ((++spins & 0x3ff) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > F.timeout_ns || ld_acquire_u64(gs.counter) >= kBarPoison) {
+          bad = 1;
+          break;
+        }
+      }
+    }
+  }
+  bad = __syncthreads_or(bad);
+  if (bad && threadIdx.x == 0 && !bs.dead) {
+    red_release_add_u64(gs.counter, kBarPoison);  // release every local CTA that is (or will be) in a grid barrier
+    bs.dead = 1;
+  }
+  return !bad;
+}
+// OR of the words the ranks attached to barrier `seq` (call after fabric_wait(seq) succeeded)
+__device__ __forceinline__ unsigned long long fabric_or_payload(const Fabric &F, unsigned long long seq,
+                                                                unsigned long long mine) {
+  unsigned long long v = mine;
+  for (int s = 0; s < F.world; ++s)
+    if (s != F.rank) v |= ld_acquire_sys_u64(F.payload + (seq & 1) * kMaxRanks + s);
+  return v;
 }
 
 }  // namespace dpgo

@@ -280,6 +280,7 @@ void Agent::build_structure() {
   d_s_slot.upload(h_s_slot);
   d_pub_rowptr.upload(h_pub_rowptr);
   const size_t vec = (size_t)r * 4 * n;
+  if (inbox_ext) fail(DPGO_B200_ERR_STATE, "the pose graph changed after the team's fabric window was laid out");
   d_inbox.alloc((size_t)2 * std::max(1, n_in) * 4 * r);
   free_pinned();
   cuda_check(cudaMallocHost((void **)&h_inbox, d_inbox.n * sizeof(double)), "cudaMallocHost");
@@ -691,6 +692,7 @@ Team::~Team() {
     a->wiring_dirty = true;
     a->own->team_dirty = true;
   }
+  fabric_close();
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
@@ -772,9 +774,17 @@ void Team::prepare() {
         auto &fr = frames_of[b];
         if (fr.empty()) fr = a->my_public_frames(b);
         const int idx = (int)(std::lower_bound(fr.begin(), fr.end(), f) - fr.begin());
-        const size_t o = (size_t)(a->outbox_range.at(b).first + idx) * 4 * r;
-        reg[e] = a->d_outbox_reg() + o;
-        aux[e] = a->d_outbox_aux() + o;
+        auto rt = routes.find({a->id, b});
+        if (rt != routes.end() && peer_base[rt->second.peer]) {
+          // remote neighbour reachable over the fabric: store straight into its inbox on the other GPU
+          unsigned char *pb = peer_base[rt->second.peer];
+          reg[e] = reinterpret_cast<double *>(pb + rt->second.off_reg) + (size_t)idx * 4 * r;
+          aux[e] = reinterpret_cast<double *>(pb + rt->second.off_aux) + (size_t)idx * 4 * r;
+        } else {
+          const size_t o = (size_t)(a->outbox_range.at(b).first + idx) * 4 * r;
+          reg[e] = a->d_outbox_reg() + o;
+          aux[e] = a->d_outbox_aux() + o;
+        }
       }
     }
     if (reg.empty()) {
@@ -828,12 +838,167 @@ void Team::prepare() {
   T.prof_iters = prof_iters;
   T.prof_cta = prof_cta;
   T.done_counter = dBar.p + 2;
+  if (fab_world > 1 && window) {
+    Fabric &Fb = T.fab;
+    Fb.world = fab_world;
+    Fb.rank = fab_rank;
+    Fb.flags = reinterpret_cast<unsigned long long *>(window);
+    Fb.payload = Fb.flags + kMaxRanks;
+    for (int s = 0; s < fab_world; ++s) {
+      unsigned long long *pf = reinterpret_cast<unsigned long long *>(peer_base[s]);
+      Fb.peer_flags[s] = pf;
+      Fb.peer_payload[s] = pf ? pf + kMaxRanks : nullptr;
+    }
+    Fb.local_mask = 0;
+    for (Agent *a : agents) Fb.local_mask |= 1ull << a->id;
+    Fb.timeout_ns = (unsigned long long)(fab_timeout_s * 1e9);
+  }
   team_dirty = false;
+}
+
+// ---- multi-GPU fabric ---------------------------------------------------------
+void Team::fabric_init(int world, int rank) {
+  if (world < 2 || world > kMaxRanks || rank < 0 || rank >= world)
+    fail(DPGO_B200_ERR_INVALID, "fabric_init: need 2 <= world <= 8 and 0 <= rank < world");
+  if (window) fail(DPGO_B200_ERR_STATE, "fabric_init: already initialised");
+  prepare();
+  auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
+  size_t off = kFabricHeaderBytes;
+  std::vector<size_t> offs;
+  for (Agent *a : agents) {
+    offs.push_back(off);
+    off += up(a->d_inbox.n * sizeof(double), 256);
+  }
+  window_bytes = off;
+  cuda_check(cudaMalloc((void **)&window, window_bytes), "cudaMalloc fabric window");
+  cuda_check(cudaMemset(window, 0, window_bytes), "cudaMemset fabric window");
+  cuda_check(cudaStreamSynchronize(stream), "sync before moving the inboxes");
+  for (size_t i = 0; i < agents.size(); ++i) {
+    Agent *a = agents[i];
+    double *dst = reinterpret_cast<double *>(window + offs[i]);
+    cuda_check(cudaMemcpy(dst, a->d_inbox.p, a->d_inbox.n * sizeof(double), cudaMemcpyDeviceToDevice), "move inbox");
+    a->inbox_ext = dst;
+    a->wiring_dirty = true;
+  }
+  // no allocation (cudaFree synchronises the device) may happen once the ranks' kernels wait for each other
+  dGammaTab.alloc((size_t)1 << 16, false);
+  fab_world = world;
+  fab_rank = rank;
+  fab_seq = 0;
+  peer_base[rank] = window;
+  team_dirty = true;
+}
+
+void Team::fabric_import(int peer, const cudaIpcMemHandle_t *handle, void *same_process_base) {
+  if (!window) fail(DPGO_B200_ERR_STATE, "fabric_import before fabric_init");
+  if (peer < 0 || peer >= fab_world || peer == fab_rank) fail(DPGO_B200_ERR_INVALID, "fabric_import: bad peer rank");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  if (same_process_base) {
+    // a team of this process on another device: plain peer access
+    cudaPointerAttributes at{};
+    cuda_check(cudaPointerGetAttributes(&at, same_process_base), "fabric_import: pointer attributes");
+    if (at.device != device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled)
+        cudaGetLastError();
+      else
+        cuda_check(e, "cudaDeviceEnablePeerAccess");
+    }
+    peer_base[peer] = static_cast<unsigned char *>(same_process_base);
+    peer_is_ipc[peer] = false;
+  } else {
+    if (!handle) fail(DPGO_B200_ERR_INVALID, "fabric_import: null handle");
+    void *p = nullptr;
+    cuda_check(cudaIpcOpenMemHandle(&p, *handle, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    peer_base[peer] = static_cast<unsigned char *>(p);
+    peer_is_ipc[peer] = true;
+  }
+  for (Agent *a : agents) a->wiring_dirty = true;
+  team_dirty = true;
+}
+
+void Team::fabric_route(int robot, int nbr, int peer, size_t off_reg, size_t off_aux) {
+  if (!window) fail(DPGO_B200_ERR_STATE, "fabric_route before fabric_init");
+  if (peer < 0 || peer >= fab_world || peer == fab_rank) fail(DPGO_B200_ERR_INVALID, "fabric_route: bad peer rank");
+  Agent *me = nullptr;
+  for (Agent *a : agents)
+    if (a->id == robot) me = a;
+  if (!me) fail(DPGO_B200_ERR_INVALID, "fabric_route: robot is not in this team");
+  if (!me->nbrs.count(nbr)) fail(DPGO_B200_ERR_MISSING, "fabric_route: not a neighbour");
+  routes[{robot, nbr}] = Route{peer, off_reg, off_aux};
+  me->wiring_dirty = true;
+  team_dirty = true;
+}
+
+void Team::fabric_close() {
+  if (!window) return;
+  cudaSetDevice(device);
+  cudaStreamSynchronize(stream);
+  for (int s = 0; s < kMaxRanks; ++s) {
+    if (peer_base[s] && peer_is_ipc[s]) cudaIpcCloseMemHandle(peer_base[s]);
+    peer_base[s] = nullptr;
+    peer_is_ipc[s] = false;
+  }
+  for (Agent *a : agents) {
+    // give the agents their private inboxes back (contents preserved)
+    if (a->inbox_ext && a->d_inbox.p)
+      cudaMemcpy(a->d_inbox.p, a->inbox_ext, a->d_inbox.n * sizeof(double), cudaMemcpyDeviceToDevice);
+    a->inbox_ext = nullptr;
+    a->wiring_dirty = true;
+  }
+  cudaFree(window);
+  window = nullptr;
+  window_bytes = 0;
+  fab_world = 0;
+  routes.clear();
+  std::memset(&T.fab, 0, sizeof(T.fab));
+  team_dirty = true;
+}
+
+// Every rank calls this with the same arguments at the same point of the schedule; the kernels of
+// the ranks meet at the fabric barriers.  Returns when the launch ended on THIS rank -- all ranks
+// leave at the same global iteration (the control decisions are taken from identical data).
+dpgo_b200_run_result Team::fabric_run(int max_iters, bool stop_on_terminate) {
+  dpgo_b200_run_result res{};
+  if (fab_world < 2 || !window) fail(DPGO_B200_ERR_STATE, "fabric_run: fabric_init first");
+  prepare();
+  for (int s = 0; s < fab_world; ++s)
+    if (!peer_base[s]) fail(DPGO_B200_ERR_STATE, "fabric_run: a peer window has not been imported");
+  for (Agent *a : agents) {
+    if (a->state != 2) fail(DPGO_B200_ERR_STATE, "fabric_run: every agent must be initialized in the global frame");
+    for (int b : a->nbrs) {
+      bool local = false;
+      for (Agent *o : agents) local |= (o->id == b);
+      if (!local && !routes.count({a->id, b})) fail(DPGO_B200_ERR_STATE, "fabric_run: a remote neighbour has no route");
+    }
+    if (!a->all_inbox_valid(false) || (a->P.acceleration && !a->all_inbox_valid(true)))
+      fail(DPGO_B200_ERR_MISSING, "fabric_run: neighbour poses missing (exchange_all on every rank, then mark the inboxes)");
+  }
+  RunArgs args{};
+  args.max_iters = std::min(max_iters, 1 << 16);
+  args.force_selected = -2;
+  args.stop_on_terminate = stop_on_terminate ? 1 : 0;
+  args.fabric = 1;
+  T.fab.seq0 = fab_seq;
+  float ms = 0;
+  launch_and_read(args, grid, true, &ms);
+  fab_seq = ctl.fab_seq;
+  res.device_ms = ms;
+  res.kernel_launches = 1;
+  res.iterations = ctl.iters_done;
+  res.stop_reason = ctl.stop_reason;
+  if (ctl.stop_reason == -1) {
+    // a peer never showed up: the barrier counter is poisoned, start clean next time
+    cuda_check(cudaMemset(dBar.p, 0, dBar.n * sizeof(unsigned long long)), "reset barrier");
+    fail(DPGO_B200_ERR_CUDA, "fabric_run: timed out waiting for a peer GPU");
+  }
+  if (ctl.stop_reason == 1) res.terminated = 1;
+  return res;
 }
 
 void Team::layout_result() {
   auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
-  size_t off = up(64 + 128 * agents.size(), 256);
+  size_t off = up(kCtlBytes + kStatBytes * agents.size(), 256);
   std::vector<size_t> offs;
   size_t dev_doubles = 0;
   for (Agent *a : agents) {
@@ -860,8 +1025,8 @@ void Team::layout_result() {
   std::memset(h_result, 0, result_bytes);
   for (size_t i = 0; i < agents.size(); ++i) {
     Agent *a = agents[i];
-    a->d_stat = reinterpret_cast<AgentStat *>(d_result + 64 + 128 * i);
-    a->h_stat = reinterpret_cast<AgentStat *>(h_result + 64 + 128 * i);
+    a->d_stat = reinterpret_cast<AgentStat *>(d_result + kCtlBytes + kStatBytes * i);
+    a->h_stat = reinterpret_cast<AgentStat *>(h_result + kCtlBytes + kStatBytes * i);
     if (device_outbox) {
       a->d_outbox = dOutboxAll.p + offs[i];
       a->h_outbox = nullptr;
@@ -877,7 +1042,7 @@ void Team::layout_result() {
 void Team::flush_inboxes() {
   for (Agent *a : agents)
     if (a->inbox_dirty && a->d_inbox.n) {
-      cuda_check(cudaMemcpyAsync(a->d_inbox.p, a->h_inbox, a->d_inbox.n * sizeof(double), cudaMemcpyHostToDevice,
+      cuda_check(cudaMemcpyAsync(a->inbox_base(), a->h_inbox, a->d_inbox.n * sizeof(double), cudaMemcpyHostToDevice,
                                  stream),
                  "H2D inbox");
       a->inbox_dirty = false;
@@ -1053,6 +1218,7 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
     if (ctl.stop_reason == 1) res.terminated = 1;
     break;
   }
+  res.stop_reason = ctl.stop_reason;
   return res;
 }
 
@@ -1081,6 +1247,11 @@ void Team::exchange_all() {
 // UPDATE_WEIGHT (src/PGOAgentROS.cpp:1211-1233): residual + GNC-TLS weight on the
 // device, ownership rule and Q / G / preconditioner rebuild on the host side.
 void Team::gnc_update_all() {
+  gnc_compute_weights();
+  gnc_finish_update();
+}
+
+void Team::gnc_compute_weights() {
   prepare();
   for (Agent *a : agents) {
     if (a->state != 2) continue;
@@ -1110,6 +1281,9 @@ void Team::gnc_update_all() {
             }
           }
     }
+}
+
+void Team::gnc_finish_update() {
   for (Agent *a : agents) {
     if (a->state != 2) continue;
     if (a->P.cost_type == 5) a->mu *= a->P.gnc_mu_step;

@@ -150,8 +150,10 @@ class Agent {
   // inbox / outbox: [reg | aux] contiguous on the device, mirrored in pinned host memory so the
   // per-robot exchange API (getSharedPoseDict / updateNeighborPoses) costs one async copy per iterate
   DevBuf<double> d_inbox;
-  double *d_inbox_reg() const { return d_inbox.p; }
-  double *d_inbox_aux() const { return d_inbox.p + (size_t)slot_key.size() * 4 * r; }
+  double *inbox_ext = nullptr;  // multi-GPU: the inbox lives in the team's peer-visible window instead
+  double *inbox_base() const { return inbox_ext ? inbox_ext : d_inbox.p; }
+  double *d_inbox_reg() const { return inbox_base(); }
+  double *d_inbox_aux() const { return inbox_base() + (size_t)slot_key.size() * 4 * r; }
   // outbox + AgentStat live in the owning team's result block (one D2H copy per launch)
   double *d_outbox = nullptr, *h_outbox = nullptr;
   AgentStat *d_stat = nullptr, *h_stat = nullptr;
@@ -205,6 +207,28 @@ class Team {
   DevBuf<double> dOutboxAll;
   double last_gamma_use = 0, last_alpha_use = 0;
   void step(int selected_robot, int mode);
+  // ---- multi-GPU fabric (struct Fabric, device.cuh): this team is rank `fab_rank` of `fab_world`
+  // processes, one per GPU, that run the global schedule together in their own persistent kernels
+  struct Route {
+    int peer;            // rank that owns the neighbour
+    size_t off_reg, off_aux;  // byte offsets, in the peer's window, of my contiguous range in its inbox
+  };
+  int fab_world = 0, fab_rank = 0;
+  unsigned char *window = nullptr;  // [flags | payload | inbox of every local agent], cudaMalloc'ed (IPC-exportable)
+  size_t window_bytes = 0;
+  unsigned char *peer_base[kMaxRanks] = {};
+  bool peer_is_ipc[kMaxRanks] = {};
+  unsigned long long fab_seq = 0;
+  double fab_timeout_s = 20.0;
+  std::map<std::pair<int, int>, Route> routes;  // (local robot, remote neighbour)
+  void fabric_init(int world, int rank);
+  void fabric_import(int peer, const cudaIpcMemHandle_t *handle, void *same_process_base);
+  void fabric_route(int robot, int nbr, int peer, size_t off_reg, size_t off_aux);
+  dpgo_b200_run_result fabric_run(int max_iters, bool stop_on_terminate);
+  void fabric_close();
+  // GNC weight update split in two so that the caller can carry weights across ranks in between
+  void gnc_compute_weights();
+  void gnc_finish_update();
   void wait_result(unsigned long long expect);
   TeamCtl *h_ctl() const { return reinterpret_cast<TeamCtl *>(h_result); }
   void layout_result();

@@ -21,6 +21,7 @@ struct RunArgs {
   // single-iteration split used when the public poses cross GPUs between the two halves:
   //   0 full iterate, 1 Nesterov phase only (iteration counter advances), 2 local solve only
   int mode;
+  int fabric;  // 1: this launch is one rank of a multi-GPU run (TeamDev::fab is live)
 };
 
 // non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel

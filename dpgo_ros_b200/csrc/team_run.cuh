@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __shared__ double sm_red[64];
   __shared__ double sm_slab[8 * 16 * 8];
   __shared__ double sm_rel[kMaxLocal];
+  __shared__ unsigned long long sm_mask;
   __shared__ ChunkTable chunks;
   __shared__ __align__(8) uint64_t mbar;
   SmemLayout L;
@@ -361,6 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   const bool accel = P.acceleration != 0;
   const bool use_slab = (P.method == 0) || P.rgd_use_precond;
   const bool schedule = args.force_selected < -1;
+  // multi-GPU: every rank runs this same loop on its own robots; see struct Fabric (device.cuh)
+  const Fabric &F = T.fab;
+  const bool fab = args.fabric && F.world > 1;
+  FabState fs{F.seq0};
+  unsigned long long fab_wait_to = F.seq0;  // barrier to pass before my next store into a peer's inbox
+  bool dead = false;
   int done = 0;
   int stop_reason = 0;
   int pend_ai = -1;        // RGD: agent whose post-step statistics (fOpt, gradNormOpt) are still due
@@ -389,12 +396,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       alpha = ga.y;
       if (args.mode != 2) {
         __syncthreads();  // X / V / Y of my chunk were last written by other threads of this CTA
+        // the selected robot of the previous iteration has finished reading its inbox
+        if (fab && !fabric_wait(F, gs, bs, fab_wait_to)) { dead = true; break; }
         phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha);
         PROF(1)
         grid_barrier(gs, bs);
+        if (fab) {  // every rank's Y (and X) of this iteration has reached its neighbours' inboxes
+          fabric_arrive(F, fs, 0);
+          if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
+        }
         PROF(2)
       }
+    } else if (fab) {
+      // plain RBCD: the X+ published by the previous iteration's robot has arrived (its step ended with a
+      // grid barrier / reduction, so the arrival below is ordered after those stores)
+      fabric_arrive(F, fs, 0);
+      if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
     }
+    bool inbox_released = !(fab && accel);
     if (sel_local >= 0) {
       const AgentDev &A = T.ag[sel_local];
       const bool use_aux = accel && !restart;
@@ -421,6 +440,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         PROF(3)
         grid_barrier(gs, bs);
+        if (!inbox_released) {  // G is assembled: the other ranks may overwrite my inbox (next Nesterov phase)
+          fabric_arrive(F, fs, 0);
+          fab_wait_to = fs.seq;
+          inbox_released = true;
+        }
         PROF(4)
         double prel = 0;
         phase_rgd_step<R>(A, sel_local, P, Xs, accel, restart, gamma, ss, &mbar, L.slab, L.slab_cap, L.zs, sm_slab,
@@ -463,6 +487,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
+    if (!inbox_released) {  // ranks without the selected robot (and RTR, whose solve ends with a reduction)
+      fabric_arrive(F, fs, 0);
+      fab_wait_to = fs.seq;
+    }
     c.iter = iter;
     if (P.robust && args.mode != 2) c.robust_inner_iter++;
     ++done;
@@ -490,6 +518,16 @@ __global__ void __launch_bounds__(kThreads, 1)
                 c.ready_mask &= ~(1ull << rid);
             }
           rel_due = 0;
+        }
+        if (fab) {
+          // every rank is authoritative for the ready bits of its own robots: union over the ranks
+          const unsigned long long mine = c.ready_mask & F.local_mask;
+          fabric_arrive(F, fs, mine);
+          if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
+          if (threadIdx.x == 0) sm_mask = fabric_or_payload(F, fs.seq, mine);
+          __syncthreads();
+          c.ready_mask = sm_mask;
+          fab_wait_to = fs.seq;
         }
         const unsigned long long all = (N >= 64) ? ~0ull : ((1ull << N) - 1ull);
         bool terminate;
@@ -560,7 +598,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (ss.pending) slab_wait(&mbar, ss.parity);  // do not exit with a bulk copy in flight
   grid_barrier(gs, bs);  // every CTA's result-block writes (outboxes, stats) are ordered before the flag
+  if (fab && !dead) {
+    // leave together: on return every publication of every rank has landed in its destination inbox
+    fabric_arrive(F, fs, 0);
+    if (!fabric_wait(F, gs, bs, fs.seq)) dead = true;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c.fab_seq = fs.seq;
+    if (dead) stop_reason = -1;
     c.stop_reason = stop_reason;
     c.iters_done = done;
     c.seq = 0;

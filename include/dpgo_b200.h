@@ -76,6 +76,7 @@ typedef struct {
   int weight_updates;  /* GNC weight updates performed inside this call */
   float device_ms;     /* CUDA-event time of the persistent kernel launches */
   int kernel_launches; /* number of kernels this call launched */
+  int stop_reason;     /* 0 ran max_iters, 1 terminated, 2 GNC weight update due (multi-GPU: the caller does it) */
 } dpgo_b200_run_result;
 
 /* ---- library ------------------------------------------------------------- */
@@ -144,6 +145,10 @@ double dpgo_b200_robust_weight(dpgo_b200_agent_t a, double residual);           
 int dpgo_b200_clear_data_matrices(dpgo_b200_agent_t a);                         /* :1351 */
 /* loop-closure weights in insertion order: private LCs, then shared LCs */
 int dpgo_b200_get_lc_weights(dpgo_b200_agent_t a, double *out, int cap);
+/* mPoseGraph->sharedLoopClosures() as publishMeasurementWeights reads it (:721-754): ids, weight and
+ * fixedWeight of every shared loop closure; returns the total count (arrays may be NULL / shorter) */
+int dpgo_b200_get_shared_loop_closures(dpgo_b200_agent_t a, int *r1, int *p1, int *r2, int *p2, double *weight,
+                                       unsigned char *fixed, int cap);
 int dpgo_b200_weight_update_count(dpgo_b200_agent_t a);                         /* mWeightUpdateCount, :193 */
 
 /* ---- problem-level evaluation on the device (parity hooks for a3/a5/a6) ------- */
@@ -172,6 +177,37 @@ int dpgo_b200_team_step(dpgo_b200_team_t t, int selected_robot, int mode);
 double dpgo_b200_team_global_cost(dpgo_b200_team_t t, int *status);
 /* tuning knob: CTAs of the persistent kernel (0 = one per SM) */
 int dpgo_b200_team_set_grid(dpgo_b200_team_t t, int num_ctas);
+
+/* ---- multi-GPU fabric: one team (process) per GPU, neighbour PublicPoses as raw device stores ----
+ * Replaces the PublicPoses / MatrixMsg topics (msg/PublicPoses.msg:1-8, src/PGOAgentROS.cpp:662-690,
+ * 1255-1284) and the iteration gate (:136-149) for robots that live on different GPUs of one node:
+ * the inboxes of a team's agents sit in one cudaMalloc'ed window that the other ranks map with CUDA
+ * IPC; the persistent kernels publish by storing into the neighbour's inbox over NVLink and keep in
+ * step through flag words in the same windows.  Host-side sequence (every rank):
+ *   fabric_init -> fabric_window (export) -> [all-gather handles + inbox offsets] -> fabric_import
+ *   per peer -> fabric_route per (local robot, remote neighbour) -> team_exchange_all ->
+ *   [host barrier] -> mark_inbox_updated -> fabric_run ...                                          */
+int dpgo_b200_team_fabric_init(dpgo_b200_team_t t, int world, int rank);
+/* base / size of this rank's window and its 64-byte CUDA IPC handle (ipc_handle may be NULL) */
+int dpgo_b200_team_fabric_window(dpgo_b200_team_t t, void **base, size_t *bytes, void *ipc_handle_64);
+/* map a peer's window: by IPC handle (other process) or by pointer (team of this process, tests) */
+int dpgo_b200_team_fabric_import(dpgo_b200_team_t t, int peer_rank, const void *ipc_handle_64,
+                                 void *same_process_base);
+/* poses of local `robot` shared with remote `neighbor` go to byte offsets off_reg / off_aux of the
+ * peer's window (= dpgo_b200_inbox_device_ptr(neighbor's agent, robot, aux) - its window base)      */
+int dpgo_b200_team_fabric_route(dpgo_b200_team_t t, int robot, int neighbor, int peer_rank, size_t off_reg,
+                                size_t off_aux);
+/* up to max_iters (<= 65536) global iterations in ONE persistent launch per rank; called by every
+ * rank at the same point of the schedule.  stop_reason 2: every rank must run the GNC weight update
+ * (gnc_compute_weights -> carry shared-edge weights to the higher-ID owner's rank with
+ * get_lc_weights / set_measurement_weight -> gnc_finish_update) and call fabric_run again.          */
+int dpgo_b200_team_fabric_run(dpgo_b200_team_t t, int max_iters, int stop_on_terminate, dpgo_b200_run_result *out);
+int dpgo_b200_team_fabric_set_timeout(dpgo_b200_team_t t, double seconds);
+int dpgo_b200_team_fabric_close(dpgo_b200_team_t t);
+/* UPDATE_WEIGHT (src/PGOAgentROS.cpp:1211-1233) in two halves: residuals + GNC-TLS weights of the
+ * edges this team owns; then mu / counters / Q, G, preconditioner rebuild / re-publication.         */
+int dpgo_b200_team_gnc_compute_weights(dpgo_b200_team_t t);
+int dpgo_b200_team_gnc_finish_update(dpgo_b200_team_t t);
 
 /* ---- host harness ------------------------------------------------------------------
  * ROS-free replay of PGOAgentROS's synchronous per-iteration call sequence on N
