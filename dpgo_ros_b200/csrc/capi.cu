@@ -144,6 +144,7 @@ int dpgo_b200_iterate(dpgo_b200_agent_t h, int do_opt) {
 }
 int dpgo_b200_get_opt_result(dpgo_b200_agent_t h, dpgo_b200_opt_result *out) {
   API_BEGIN
+  A(h)->finish_opt_stats();
   *out = A(h)->opt;
   API_END
 }
@@ -568,6 +569,13 @@ int dpgo_b200_debug_barrier_bench(int device, int grid, int iters, int mode, flo
   cudaEventElapsedTime(ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  API_END
+}
+int dpgo_b200_debug_host_profile(dpgo_b200_agent_t h, double *out3, int reset) {
+  API_BEGIN
+  Team *t = A(h)->team;
+  for (int i = 0; i < 4; ++i) out3[i] = t->host_prof[i];
+  if (reset) t->host_prof[0] = t->host_prof[1] = t->host_prof[2] = t->host_prof[3] = 0;
   API_END
 }
 int dpgo_b200_debug_team_profile(dpgo_b200_team_t h, int iters, int cta, long long *out /* iters*16 */) {

@@ -45,6 +45,8 @@ struct AgentDev {
   const double *so_val;
   // neighbour public poses (regular and auxiliary), r x 4 per slot
   double *inbox_reg, *inbox_aux;
+  const double *inbox_src;  // pinned host staging block [reg | aux] filled by updateNeighborPoses (device-readable)
+  int inbox_doubles;
   // publication lists, CSR by my pose: destinations of X (reg) and Y (aux)
   const int *pub_rowptr;
   double *const *pub_dst_reg;

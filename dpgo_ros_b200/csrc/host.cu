@@ -5,8 +5,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace dpgo {
@@ -17,6 +19,13 @@ void cuda_check(cudaError_t e, const char *what) {
 }
 
 static inline size_t roundup32(size_t x) { return (x + 31) / 32 * 32; }
+
+// cudaSetDevice takes a driver lock even when nothing changes; cudaGetDevice is a thread-local read
+static inline cudaError_t use_device(int device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return cudaSuccess;
+  return cudaSetDevice(device);
+}
 
 // T~ = [R t; 0 1], Omega = w diag(kappa, kappa, kappa, tau)
 static void edge_blocks(const Meas &m, double *T, double *Om) {
@@ -86,6 +95,7 @@ void Agent::add_measurement(const Meas &m) {
     }
   }
   structure_dirty = values_dirty = precon_dirty = wiring_dirty = true;
+  pub_frames_cache.clear();
   if (team) team->team_dirty = true;
 }
 
@@ -96,13 +106,15 @@ Meas *Agent::find_measurement(int r1, int p1, int r2, int p2) {
   return nullptr;
 }
 
-std::vector<int> Agent::my_public_frames(int nbr) const {
+const std::vector<int> &Agent::my_public_frames(int nbr) const {
+  auto it = pub_frames_cache.find(nbr);
+  if (it != pub_frames_cache.end()) return it->second;
   std::set<int> s;
   for (const auto &m : slc) {
     if (m.r1 == id && m.r2 == nbr) s.insert(m.p1);
     if (m.r2 == id && m.r1 == nbr) s.insert(m.p2);
   }
-  return std::vector<int>(s.begin(), s.end());
+  return pub_frames_cache.emplace(nbr, std::vector<int>(s.begin(), s.end())).first->second;
 }
 
 void Agent::set_lifting_matrix(const double *Y) {
@@ -146,7 +158,7 @@ void Agent::initialize(const double *T) {
 void Agent::initialize_in_global_frame(const double *Tw_rm) {
   if (state == 0) fail(DPGO_B200_ERR_STATE, "initializeInGlobalFrame before initialize");
   if (!have_lift) fail(DPGO_B200_ERR_STATE, "initializeInGlobalFrame: lifting matrix not set");
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   double Tw[12];
   for (int a = 0; a < 3; ++a)
     for (int c = 0; c < 4; ++c) Tw[c * 3 + a] = Tw_rm[a * 4 + c];
@@ -213,6 +225,12 @@ void Agent::build_structure() {
     slot_key.push_back(k);
   }
   const int n_in = (int)slot_key.size();
+  nbr_slots.clear();
+  for (int sidx = 0; sidx < n_in; ++sidx) {
+    NbrSlots &ns = nbr_slots[slot_key[sidx].first];
+    if (ns.frames.empty()) ns.first = sidx;
+    ns.frames.push_back(slot_key[sidx].second);
+  }
   inbox_valid_reg.assign(n_in, 0);
   inbox_valid_aux.assign(n_in, 0);
   // Q structure by output pose
@@ -478,7 +496,7 @@ void Agent::build_preconditioner() {
 }
 
 void Agent::ensure_device() {
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   if (structure_dirty) build_structure();
   if (values_dirty) build_values();
   if (precon_dirty) build_preconditioner();
@@ -493,6 +511,8 @@ AgentDev Agent::dev_view() const {
   A.qe_col = d_qe_col.p; A.qe_val = d_qe_val.p; A.qo_rowptr = d_qo_rowptr.p; A.qo_col = d_qo_col.p; A.qo_val = d_qo_val.p;
   A.se_slot = d_se_slot.p; A.se_val = d_se_val.p; A.so_rowptr = d_so_rowptr.p; A.so_slot = d_so_slot.p; A.so_val = d_so_val.p;
   A.inbox_reg = d_inbox_reg(); A.inbox_aux = d_inbox_aux();
+  A.inbox_src = h_inbox;  // pinned + UVA: the same pointer is valid on the device
+  A.inbox_doubles = (int)d_inbox.n;
   A.pub_rowptr = d_pub_rowptr.p; A.pub_dst_reg = d_pub_dst_reg.p; A.pub_dst_aux = d_pub_dst_aux.p;
   A.Pinv = dPinv.p;
   A.G = dG.p; A.Rg = dRg.p; A.RgT = dRgT.p; A.Z = dZ.p; A.eta = dEta.p; A.dlt0 = dDlt0.p; A.dlt1 = dDlt1.p;
@@ -510,7 +530,7 @@ bool Agent::all_inbox_valid(bool aux) const {
 
 // ---- iterate (standalone path: a team of one, neighbours fed through the inbox)
 bool Agent::iterate(bool do_opt) {
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   Team *tm = team;
   if (state != 2) {
     iter++;
@@ -518,7 +538,7 @@ bool Agent::iterate(bool do_opt) {
     if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
     return false;
   }
-  tm->prepare();
+  tm->prepare(false);
   const bool accel = P.acceleration != 0;
   const bool restart = accel && ((iter + 2) % P.restart_interval == 0);
   bool can_opt = do_opt;
@@ -537,9 +557,9 @@ bool Agent::iterate(bool do_opt) {
 int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, int cap) {
   if (state != 2) fail(DPGO_B200_ERR_STATE, "getSharedPoseDictWithNeighbor: agent not initialized");
   if (aux && !P.acceleration) fail(DPGO_B200_ERR_STATE, "auxiliary poses need acceleration");
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
-  team->prepare();
-  const std::vector<int> fr = my_public_frames(nbr);
+  cuda_check(use_device(device), "cudaSetDevice");
+  team->prepare(false);
+  const std::vector<int> &fr = my_public_frames(nbr);
   const int cnt = (int)fr.size();
   if (cnt > cap) fail(DPGO_B200_ERR_INVALID, "getSharedPoseDictWithNeighbor: buffer too small");
   if (cnt == 0) return 0;
@@ -566,12 +586,21 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
 }
 
 void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const double *poses, int count) {
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   if (structure_dirty) build_structure();
   // stage in pinned host memory; the next launch uploads the inbox with one async copy
   double *inbox = h_inbox + (aux ? (size_t)slot_key.size() * 4 * r : 0);
   auto &valid = aux ? inbox_valid_aux : inbox_valid_reg;
   const size_t pb = (size_t)4 * r * sizeof(double);
+  // the usual message holds exactly the poses this agent needs from `nbr`, in frame order: one copy
+  auto ns = nbr_slots.find(nbr);
+  if (ns != nbr_slots.end() && (int)ns->second.frames.size() == count && count > 0 &&
+      std::memcmp(ns->second.frames.data(), frames, sizeof(int) * count) == 0) {
+    std::memcpy(inbox + (size_t)ns->second.first * 4 * r, poses, pb * count);
+    std::memset(valid.data() + ns->second.first, 1, count);
+    inbox_dirty = true;
+    return;
+  }
   for (int k = 0; k < count; ++k) {
     auto it = slot_of.find({nbr, frames[k]});
     if (it == slot_of.end()) continue;  // a pose this agent does not need
@@ -579,6 +608,30 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
     valid[it->second] = 1;
     inbox_dirty = true;
   }
+}
+
+// mLocalOptResult.fOpt / gradNormOpt (src/PGOAgentROS.cpp:169-172) when the launch skipped them: one
+// gradient pass at X+ against the G of the solve (still cached: G is rebuilt by the next solve only)
+void Agent::finish_opt_stats() {
+  if (!stats_pending) return;
+  cuda_check(use_device(device), "cudaSetDevice");
+  team->prepare(false);
+  const int grid = team->grid;
+  if (d_stat_partials.n != (size_t)grid * 2) d_stat_partials.alloc((size_t)grid * 2);
+  cuda_check(launch_post_stats(team->T.ag[local_index], dX2.p, d_stat_partials.p, grid, team->stream), "k_post_stats");
+  std::vector<double> part((size_t)grid * 2);
+  cuda_check(cudaMemcpyAsync(part.data(), d_stat_partials.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                             team->stream),
+             "D2H partials");
+  cuda_check(cudaStreamSynchronize(team->stream), "k_post_stats");
+  double f = 0, g2 = 0;
+  for (int b = 0; b < grid; ++b) {
+    f += part[(size_t)b * 2];
+    g2 += part[(size_t)b * 2 + 1];
+  }
+  opt.f_opt = f;
+  opt.gradnorm_opt = std::sqrt(g2);
+  stats_pending = false;
 }
 
 dpgo_b200_status Agent::get_status() const {
@@ -629,7 +682,7 @@ void Agent::update_measurement_weights() {
 
 bool Agent::compute_residual(const Meas &m, double *res) {
   if (state != 2) return false;
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   team->prepare();
   // single-measurement residual through the same kernel as the weight update
   DevBuf<int> src, dst;
@@ -673,7 +726,7 @@ bool Agent::compute_residual(const Meas &m, double *res) {
 // Team
 // ============================================================================
 Team::Team(int device_) : device(device_) {
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   cuda_check(cudaEventCreate(&ev0), "eventCreate");
   cuda_check(cudaEventCreate(&ev1), "eventCreate");
   cuda_check(cudaStreamCreate(&stream), "streamCreate");  // blocking stream: ordered against legacy-stream setup work
@@ -739,8 +792,8 @@ void Team::remove(Agent *a) {
   }
 }
 
-void Team::prepare() {
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+void Team::prepare(bool need_inbox) {
+  cuda_check(use_device(device), "cudaSetDevice");
   if (agents.empty()) fail(DPGO_B200_ERR_STATE, "team has no agents");
   bool rewire = team_dirty;
   for (Agent *a : agents) {
@@ -748,7 +801,7 @@ void Team::prepare() {
     a->ensure_device();
     if (a->wiring_dirty) rewire = true;
   }
-  flush_inboxes();
+  if (need_inbox) flush_inboxes();
   if (!rewire) return;
   layout_result();
   const int r = agents[0]->r;
@@ -892,7 +945,7 @@ void Team::fabric_init(int world, int rank) {
 void Team::fabric_import(int peer, const cudaIpcMemHandle_t *handle, void *same_process_base) {
   if (!window) fail(DPGO_B200_ERR_STATE, "fabric_import before fabric_init");
   if (peer < 0 || peer >= fab_world || peer == fab_rank) fail(DPGO_B200_ERR_INVALID, "fabric_import: bad peer rank");
-  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  cuda_check(use_device(device), "cudaSetDevice");
   if (same_process_base) {
     // a team of this process on another device: plain peer access
     cudaPointerAttributes at{};
@@ -1113,6 +1166,7 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
   ctl.gamma = gamma_state;
   args.ctl_in = ctl;
   const TeamDev &Tl = T;
+  const auto hp0 = std::chrono::steady_clock::now();
   if (timed) cuda_check(cudaEventRecord(ev0, stream), "eventRecord");
   if ((args.force_selected == -1 || args.mode == 1) && args.max_iters == 1 && args.mode != 2)
     cuda_check(launch_nesterov_only(Tl, args, use_grid, stream), "launch k_nesterov_only");
@@ -1124,8 +1178,13 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
     cuda_check(cudaEventSynchronize(ev1), "k_team_run");
     if (ms) cudaEventElapsedTime(ms, ev0, ev1);
   }
+  const auto hp1 = std::chrono::steady_clock::now();
   wait_result(args.seq);
+  const auto hp2 = std::chrono::steady_clock::now();
   read_back();
+  host_prof[0] += std::chrono::duration<double>(hp1 - hp0).count();  // launch call
+  host_prof[1] += std::chrono::duration<double>(hp2 - hp1).count();  // launch returned -> result visible
+  host_prof[2] += 1.0;
   if (P.acceleration && ctl.iters_done > 0 && args.mode != 2) gamma_state = h_gamma_state[ctl.iters_done - 1];
   ctl.gamma = gamma_state;
 }
@@ -1146,11 +1205,30 @@ void Team::wait_result(unsigned long long expect) {
 }
 
 void Team::run_forced(int sel_local) {
-  prepare();
+  prepare(false);
   RunArgs args{};
   args.max_iters = 1;
   args.force_selected = sel_local;
-  launch_and_read(args, sel_local < 0 ? small_grid : grid, false, nullptr);
+  // poses staged by updateNeighborPoses since the last solve: the solve kernel pulls them from the pinned host
+  // block itself (one coalesced PCIe read hidden behind its first phase) instead of a cudaMemcpyAsync per call
+  if (sel_local >= 0)
+    for (size_t i = 0; i < agents.size(); ++i)
+      if (agents[i]->inbox_dirty && agents[i]->d_inbox.n && agents[i]->h_inbox) {
+        args.pull_mask |= 1u << i;
+        agents[i]->inbox_dirty = false;
+      }
+  // iterate(true) of a stand-alone agent returns as soon as X+ is published; fOpt / gradNormOpt of
+  // mLocalOptResult cost a second gradient pass and are evaluated when somebody reads them
+  args.skip_stats = 1;
+  static const bool time_it = getenv("DPGO_B200_TIME_LAUNCHES") != nullptr;  // diagnostics
+  float ms = 0;
+  launch_and_read(args, sel_local < 0 ? small_grid : grid, time_it, &ms);
+  host_prof[3] += ms * 1e-3;
+  if (sel_local >= 0 && agents[sel_local]->P.method == 1) {
+    Agent *a = agents[sel_local];
+    a->stats_pending = true;
+    a->opt.f_opt = a->opt.gradnorm_opt = std::nan("");
+  }
 }
 
 // One global iteration for the LOCAL agents of a team that holds only part of the robots

@@ -71,7 +71,7 @@ class Agent {
   void add_measurement(const Meas &m);
   Meas *find_measurement(int r1, int p1, int r2, int p2);
   std::vector<int> neighbors() const { return std::vector<int>(nbrs.begin(), nbrs.end()); }
-  std::vector<int> my_public_frames(int nbr) const;
+  const std::vector<int> &my_public_frames(int nbr) const;  // sorted; cached until the pose graph changes
 
   // ---- lifecycle
   void set_lifting_matrix(const double *Y);
@@ -115,6 +115,13 @@ class Agent {
   std::vector<Meas> odom, plc, slc;
   std::set<std::pair<std::pair<int, int>, std::pair<int, int>>> have;
   std::set<int> nbrs;
+  mutable std::map<int, std::vector<int>> pub_frames_cache;
+  // per neighbour: the contiguous inbox slot range that holds its poses and their (sorted) frame ids
+  struct NbrSlots {
+    int first = 0;
+    std::vector<int> frames;
+  };
+  std::map<int, NbrSlots> nbr_slots;
 
   // state machine
   int state = 0, instance = 0, iter = 0;
@@ -152,6 +159,9 @@ class Agent {
   DevBuf<double> d_inbox;
   double *inbox_ext = nullptr;  // multi-GPU: the inbox lives in the team's peer-visible window instead
   double *inbox_base() const { return inbox_ext ? inbox_ext : d_inbox.p; }
+  bool stats_pending = false;  // fOpt / gradNormOpt of the last iterate(true) not evaluated yet
+  void finish_opt_stats();
+  DevBuf<double> d_stat_partials;
   double *d_inbox_reg() const { return inbox_base(); }
   double *d_inbox_aux() const { return inbox_base() + (size_t)slot_key.size() * 4 * r; }
   // outbox + AgentStat live in the owning team's result block (one D2H copy per launch)
@@ -184,7 +194,9 @@ class Team {
   ~Team();
   void add(Agent *a);
   void remove(Agent *a);
-  void prepare();  // ensure every agent's device data + wiring + TeamDev are current
+  // ensure every agent's device data + wiring + TeamDev are current; need_inbox: the next launch reads the
+  // neighbour poses, so staged host inboxes are uploaded (iterate(false) does not pay for that copy)
+  void prepare(bool need_inbox = true);
   void exchange_all();
   dpgo_b200_run_result run(int max_iters, bool stop_on_terminate);
   // one iteration with a forced selection (standalone iterate path); returns kernel ms
@@ -249,6 +261,7 @@ class Team {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool team_dirty = true;
   int launches = 0;
+  double host_prof[4] = {0, 0, 0, 0};  // diagnostics: seconds in the launch call, seconds until the result, launches
   DevBuf<long long> dProf;
   int prof_iters = 0, prof_cta = 0;
 };

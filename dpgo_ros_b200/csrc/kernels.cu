@@ -93,6 +93,33 @@ __global__ void __launch_bounds__(kThreads) k_eval(const __grid_constant__ Agent
   }
 }
 
+// deferred mLocalOptResult.fOpt / gradNormOpt of a stand-alone iterate(true): gradient pass at X+ with the G of
+// the solve (build_g = false), nothing written but the partial sums
+__global__ void __launch_bounds__(kThreads) k_post_stats(const __grid_constant__ AgentDev A, const double *X,
+                                                         double *partials /* [grid][2] */) {
+  __shared__ double stage[kGroupsPerCta * kStageStride];
+  __shared__ double sm[2 * (kThreads / 32)];
+  double pf = 0, pg2 = 0;
+  phase_grad<0>(A, X, nullptr, false, nullptr, nullptr, nullptr, nullptr, stage, pf, pg2);
+  pf = wsum32(pf);
+  pg2 = wsum32(pg2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sm[warp * 2] = pf;
+    sm[warp * 2 + 1] = pg2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      a += sm[w * 2];
+      b += sm[w * 2 + 1];
+    }
+    partials[blockIdx.x * 2] = a;
+    partials[blockIdx.x * 2 + 1] = b;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) k_hess(const __grid_constant__ AgentDev A, const double *X,
                                                    const double *V, double *out) {
   __shared__ double stage[kGroupsPerCta * kStageStride];
@@ -228,18 +255,22 @@ void count_launch() { ++g_launches; }
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - 11 * 1024;  // leave room for the static arrays
 
-template <int R>
+template <int R, int M>
 cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream);
+template <int R>
+static cudaError_t launch_run_m(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
+  return T.p.method == 1 ? launch_run_t<R, 1>(T, args, grid, stream) : launch_run_t<R, 0>(T, args, grid, stream);
+}
 
 cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
   if (grid > kMaxGrid) return cudaErrorInvalidValue;
   switch (T.ag[0].r) {
-    case 3: return launch_run_t<3>(T, args, grid, stream);
-    case 4: return launch_run_t<4>(T, args, grid, stream);
-    case 5: return launch_run_t<5>(T, args, grid, stream);
-    case 6: return launch_run_t<6>(T, args, grid, stream);
-    case 7: return launch_run_t<7>(T, args, grid, stream);
-    case 8: return launch_run_t<8>(T, args, grid, stream);
+    case 3: return launch_run_m<3>(T, args, grid, stream);
+    case 4: return launch_run_m<4>(T, args, grid, stream);
+    case 5: return launch_run_m<5>(T, args, grid, stream);
+    case 6: return launch_run_m<6>(T, args, grid, stream);
+    case 7: return launch_run_m<7>(T, args, grid, stream);
+    case 8: return launch_run_m<8>(T, args, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -266,6 +297,11 @@ cudaError_t launch_eval(const AgentDev &A, const double *X, const double *inbox,
                         double *partials, int grid, cudaStream_t s) {
   ++g_launches;
   k_eval<<<grid, kThreads, 0, s>>>(A, X, inbox, egrad, rgrad, partials);
+  return cudaGetLastError();
+}
+cudaError_t launch_post_stats(const AgentDev &A, const double *X, double *partials, int grid, cudaStream_t s) {
+  ++g_launches;
+  k_post_stats<<<grid, kThreads, 0, s>>>(A, X, partials);
   return cudaGetLastError();
 }
 cudaError_t launch_hess(const AgentDev &A, const double *X, const double *V, double *out, int grid, cudaStream_t s) {

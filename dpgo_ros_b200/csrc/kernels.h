@@ -22,6 +22,8 @@ struct RunArgs {
   //   0 full iterate, 1 Nesterov phase only (iteration counter advances), 2 local solve only
   int mode;
   int fabric;  // 1: this launch is one rank of a multi-GPU run (TeamDev::fab is live)
+  unsigned pull_mask;  // local agents whose staged host inbox (AgentDev::inbox_src) is copied in by the kernel
+  int skip_stats;  // 1: leave fOpt / gradNormOpt of the last step to Agent::finish_opt_stats (AgentStat::optimized = 2)
 };
 
 // non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel
@@ -41,6 +43,8 @@ cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cud
 cudaError_t launch_nesterov_only(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream);
 cudaError_t launch_eval(const AgentDev &A, const double *X, const double *inbox, double *egrad, double *rgrad,
                         double *partials, int grid, cudaStream_t s);
+// f and |rgrad|^2 at X against the cached G: per-CTA partials [grid][2]
+cudaError_t launch_post_stats(const AgentDev &A, const double *X, double *partials, int grid, cudaStream_t s);
 cudaError_t launch_hess(const AgentDev &A, const double *X, const double *V, double *out, int grid, cudaStream_t s);
 cudaError_t launch_transpose_rows(const double *V, double *VT, int r, int n4, cudaStream_t s);
 cudaError_t launch_precond(const AgentDev &A, const double *X, const double *V, const double *VT, double *out,

@@ -314,20 +314,60 @@ __device__ __forceinline__ void defer_store(const TeamDev &T, int ai, int q, dou
   partial = wsum32(partial);
   if ((threadIdx.x & 31) == 0) defer_slot(T, ai)[q] = partial;
 }
-// total of quantity q of agent ai over the whole grid (warp-collective, same order everywhere)
+// total of quantity q of agent ai over the whole grid (warp-collective, same order everywhere).  The loads of
+// eight entries are issued together: the loop is a chain of L2 round trips otherwise (~37 per lane at 148 CTAs)
 __device__ __forceinline__ double defer_total(const TeamDev &T, int ai, int q) {
   const int lane = threadIdx.x & 31;
   const int entries = (int)gridDim.x * (kThreads / 32);
   const double *base = T.defer + (size_t)ai * entries * kDeferQ + q;
   double s = 0;
-  for (int e = lane; e < entries; e += 32) s += __ldcg(base + (size_t)e * kDeferQ);
+  for (int e0 = lane; e0 < entries; e0 += 32 * 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + 32 * u;
+      v[u] = (e < entries) ? __ldcg(base + (size_t)e * kDeferQ) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
   return wsum32(s);
+}
+// all five reporting sums of agent ai at once (warp-collective): an entry is one 64-byte row
+__device__ __forceinline__ void defer_total5(const TeamDev &T, int ai, double (&t)[5]) {
+  const int lane = threadIdx.x & 31;
+  const int entries = (int)gridDim.x * (kThreads / 32);
+  const double *base = T.defer + (size_t)ai * entries * kDeferQ;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) t[q] = 0;
+  for (int e0 = lane; e0 < entries; e0 += 32 * 4) {
+    double2 a[4], b[4];
+    double c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + 32 * u;
+      const bool ok = e < entries;
+      const double *row = base + (size_t)(ok ? e : 0) * kDeferQ;
+      a[u] = ok ? __ldcg(reinterpret_cast<const double2 *>(row)) : make_double2(0, 0);
+      b[u] = ok ? __ldcg(reinterpret_cast<const double2 *>(row) + 1) : make_double2(0, 0);
+      c[u] = ok ? __ldcg(row + 4) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      t[0] += a[u].x; t[1] += a[u].y; t[2] += b[u].x; t[3] += b[u].y; t[4] += c[u];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) t[q] = wsum32(t[q]);
 }
 
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-template <int R>
+// M: local solver, fixed at compile time (0 RTR, 1 RGD) so that the RGD kernel -- the bench workload and the
+// stand-alone iterate() path -- does not carry the RTR-tCG code (instruction-cache footprint on a cold launch,
+// register pressure)
+template <int R, int M>
 __global__ void __launch_bounds__(kThreads, 1)
     k_team_run(const __grid_constant__ TeamDev T, const __grid_constant__ RunArgs args) {
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
@@ -360,8 +400,20 @@ __global__ void __launch_bounds__(kThreads, 1)
   bar_init(gs, bs);
   const int N = T.num_robots;
   const bool accel = P.acceleration != 0;
-  const bool use_slab = (P.method == 0) || P.rgd_use_precond;
+  const bool use_slab = (M == 0) || P.rgd_use_precond;
   const bool schedule = args.force_selected < -1;
+  if (args.pull_mask) {
+    // updateNeighborPoses staged the neighbours' poses in pinned host memory: fetch them with 16-byte loads
+    // spread over the whole grid (one PCIe round trip, overlapped with the Nesterov phase that follows)
+    for (int ai = 0; ai < T.num_local; ++ai)
+      if (args.pull_mask & (1u << ai)) {
+        const double2 *src = reinterpret_cast<const double2 *>(T.ag[ai].inbox_src);
+        double2 *dst = reinterpret_cast<double2 *>(T.ag[ai].inbox_reg);
+        const int cnt = T.ag[ai].inbox_doubles / 2;
+        for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) dst[i] = src[i];
+      }
+    if (!accel || args.mode == 2) grid_barrier(gs, bs);  // otherwise the barrier after the Nesterov phase orders it
+  }
   // multi-GPU: every rank runs this same loop on its own robots; see struct Fabric (device.cuh)
   const Fabric &F = T.fab;
   const bool fab = args.fabric && F.world > 1;
@@ -420,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const double *Xs = use_aux ? A.Y : A.X;
       const double *inbox = use_aux ? A.inbox_aux : A.inbox_reg;
       if (use_slab) slab_prefetch(A, sel_local, ss, &mbar, L.slab, L.slab_cap);  // no-op when already in flight
-      if (P.method == 1) {
+      if constexpr (M == 1) {
         // ---- RGD (a2): gradient (+ the previous step's deferred statistics), preconditioned step
         // the two gradient passes are independent: warps 0-3 take the step's gradient, warps 4-7 the
         // deferred statistics of the previous step (both fit: <= 4 groups of 16 per CTA are busy)
@@ -500,12 +552,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (rel_due) {
           // total the parked relative changes of every agent that stepped since the last turn
           grid_barrier(gs, bs);
-          if ((threadIdx.x >> 5) == 0) {
-            for (int ai = 0; ai < T.num_local; ++ai)
-              if (rel_due & (1u << ai)) {
-                const double t = defer_total(T, ai, 4);
-                if (threadIdx.x == 0) sm_rel[ai] = t;
-              }
+          {
+            const int ai = threadIdx.x >> 5;  // one warp per local agent (kMaxLocal == warps per CTA)
+            if (ai < T.num_local && (rel_due & (1u << ai))) {
+              const double t = defer_total(T, ai, 4);
+              if ((threadIdx.x & 31) == 0) sm_rel[ai] = t;
+            }
           }
           __syncthreads();
           for (int ai = 0; ai < T.num_local; ++ai)
@@ -550,6 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   // ---- epilogue: everything that was deferred becomes observable now
   grid_barrier(gs, bs);
+  if (args.skip_stats) pend_ai = -1;  // fOpt / gradNormOpt are evaluated on demand by the host (finish_opt_stats)
   if (pend_ai >= 0) {
     // statistics of the last RGD step (mLocalOptResult.fOpt / gradNormOpt, src/PGOAgentROS.cpp:169-172)
     const AgentDev &B = T.ag[pend_ai];
@@ -559,13 +612,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     defer_store(T, pend_ai, 3, qg2);
     grid_barrier(gs, bs);
   }
-  if (touched && blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
-    for (int ai = 0; ai < T.num_local; ++ai)
-      if (touched & (1u << ai)) {
+  if (touched && blockIdx.x == 0) {
+    const int ai = threadIdx.x >> 5;  // one warp per local agent
+    if (ai < T.num_local && (touched & (1u << ai))) {
         double t[5];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) t[q] = defer_total(T, ai, q);
-        if (threadIdx.x == 0) {
+        defer_total5(T, ai, t);
+        if ((threadIdx.x & 31) == 0) {
           AgentStat *st = T.ag[ai].stat;
           const double relchange = sqrt(t[4] / T.ag[ai].n);
           st->f_init = t[0]; st->gn_init = sqrt(t[1]); st->f_opt = t[2]; st->gn_opt = sqrt(t[3]);
@@ -578,12 +630,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   // the ready bits of agents that stepped after the last leader turn (uniform: every thread needs c)
   if (rel_due) {
-    if ((threadIdx.x >> 5) == 0) {
-      for (int ai = 0; ai < T.num_local; ++ai)
-        if (rel_due & (1u << ai)) {
-          const double t = defer_total(T, ai, 4);
-          if (threadIdx.x == 0) sm_rel[ai] = t;
-        }
+    {
+      const int ai = threadIdx.x >> 5;
+      if (ai < T.num_local && (rel_due & (1u << ai))) {
+        const double t = defer_total(T, ai, 4);
+        if ((threadIdx.x & 31) == 0) sm_rel[ai] = t;
+      }
     }
     __syncthreads();
     for (int ai = 0; ai < T.num_local; ++ai)
@@ -626,7 +678,7 @@ static void smem_plan(int max_n, int grid, bool want_slab, size_t &slab_cap, siz
   total = slab_cap + fixed;
 }
 
-template <int R>
+template <int R, int M>
 cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream) {
   int max_n = 1;
   for (int i = 0; i < T.num_local; ++i) max_n = std::max(max_n, T.ag[i].n);
@@ -634,15 +686,18 @@ cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t 
   size_t slab_cap, smem;
   smem_plan(max_n, grid, want_slab, slab_cap, smem);
   args.slab_cap = slab_cap;
-  static std::atomic<size_t> configured{0};
-  if (smem > configured.load()) {
-    cudaError_t err = cudaFuncSetAttribute(k_team_run<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<size_t> configured[64];  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem > configured[dev].load()) {
+    cudaError_t err = cudaFuncSetAttribute(k_team_run<R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    configured.store(smem);
+    configured[dev].store(smem);
   }
   void *params[] = {(void *)&T, (void *)&args};
   count_launch();
-  return cudaLaunchCooperativeKernel((void *)k_team_run<R>, dim3(grid), dim3(kThreads), params, smem, stream);
+  return cudaLaunchCooperativeKernel((void *)k_team_run<R, M>, dim3(grid), dim3(kThreads), params, smem, stream);
 }
 
 }  // namespace dpgo

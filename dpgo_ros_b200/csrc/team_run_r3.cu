@@ -1,6 +1,6 @@
-// k_team_run<3>: the persistent RBCD kernel for relaxation rank r = 3
+// k_team_run<3, 1>: the persistent RBCD kernel for relaxation rank r = 3, RGD local solver
 #include "team_run.cuh"
 
 namespace dpgo {
-template cudaError_t launch_run_t<3>(const TeamDev &, RunArgs, int, cudaStream_t);
+template cudaError_t launch_run_t<3, 1>(const TeamDev &, RunArgs, int, cudaStream_t);
 }  // namespace dpgo

@@ -1,0 +1,6 @@
+// k_team_run<3, 0>: the persistent RBCD kernel for relaxation rank r = 3, RTR-tCG local solver
+#include "team_run.cuh"
+
+namespace dpgo {
+template cudaError_t launch_run_t<3, 0>(const TeamDev &, RunArgs, int, cudaStream_t);
+}  // namespace dpgo

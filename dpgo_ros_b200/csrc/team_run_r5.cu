@@ -1,6 +1,6 @@
-// k_team_run<5>: the persistent RBCD kernel for relaxation rank r = 5
+// k_team_run<5, 1>: the persistent RBCD kernel for relaxation rank r = 5, RGD local solver
 #include "team_run.cuh"
 
 namespace dpgo {
-template cudaError_t launch_run_t<5>(const TeamDev &, RunArgs, int, cudaStream_t);
+template cudaError_t launch_run_t<5, 1>(const TeamDev &, RunArgs, int, cudaStream_t);
 }  // namespace dpgo

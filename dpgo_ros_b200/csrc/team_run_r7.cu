@@ -1,6 +1,6 @@
-// k_team_run<7>: the persistent RBCD kernel for relaxation rank r = 7
+// k_team_run<7, 1>: the persistent RBCD kernel for relaxation rank r = 7, RGD local solver
 #include "team_run.cuh"
 
 namespace dpgo {
-template cudaError_t launch_run_t<7>(const TeamDev &, RunArgs, int, cudaStream_t);
+template cudaError_t launch_run_t<7, 1>(const TeamDev &, RunArgs, int, cudaStream_t);
 }  // namespace dpgo
