@@ -180,6 +180,7 @@ int dpgo_b200_get_x(dpgo_b200_agent_t h, int which, double *out) {
   Agent *a = A(h);
   if (a->state != 2) fail(DPGO_B200_ERR_STATE, "getX: agent not initialized");
   cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+  a->materialize_lookahead();
   const DevBuf<double> &b = which == 0 ? a->dX : (which == 1 ? a->dY : a->dV);
   cuda_check(cudaMemcpy(out, b.p, sizeof(double) * a->r * 4 * a->n, cudaMemcpyDeviceToHost), "D2H X");
   API_END
@@ -189,6 +190,8 @@ int dpgo_b200_set_x(dpgo_b200_agent_t h, const double *X) {
   Agent *a = A(h);
   if (a->state != 2) fail(DPGO_B200_ERR_STATE, "setX: agent not initialized");
   cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+  a->materialize_lookahead();
+  a->drop_lookahead();
   const size_t bytes = sizeof(double) * a->r * 4 * a->n;
   cuda_check(cudaMemcpy(a->dX.p, X, bytes, cudaMemcpyHostToDevice), "H2D X");
   if (a->P.acceleration) {

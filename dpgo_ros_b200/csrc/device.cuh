@@ -17,6 +17,7 @@ constexpr int kMaxRobots = 64;   // robots in the whole problem
 constexpr int kThreads = 256;    // CTA size of every kernel here
 constexpr int kGroupsPerCta = kThreads / 8;
 constexpr int kRed = 4;          // doubles per grid reduction
+constexpr int kLaMax = 8;        // speculated iterate(false) steps per launch (stand-alone path)
 constexpr int kMaxRanks = 8;     // GPUs (one process each) that run one problem together
 
 struct AgentStat {
@@ -45,6 +46,11 @@ struct AgentDev {
   const double *so_val;
   // neighbour public poses (regular and auxiliary), r x 4 per slot
   double *inbox_reg, *inbox_aux;
+  // lookahead of the stand-alone path (phase_lookahead): speculated states [kLaMax][r x 4n], their public poses
+  // in mapped host memory [kLaMax][la_stride], and the base of the regular outbox the publication lists point into
+  double *LX, *la_out;
+  const double *outbox_base;
+  int la_stride;
   const double *inbox_src;  // pinned host staging block [reg | aux] filled by updateNeighborPoses (device-readable)
   int inbox_doubles;
   // publication lists, CSR by my pose: destinations of X (reg) and Y (aux)
@@ -85,6 +91,7 @@ struct TeamCtl {
   unsigned epoch;          // grid_sync epoch reached at kernel exit (carried into the next launch)
   unsigned pad;
   unsigned long long fab_seq;  // multi-GPU: sequence number of the last fabric barrier this rank arrived at
+  unsigned long long la_seq;   // stand-alone path: the lookahead written by launch `la_seq` is complete
 };
 constexpr size_t kCtlBytes = 128;   // result block: [TeamCtl (padded) | AgentStat x agents (128 B each) | outboxes]
 constexpr size_t kStatBytes = 128;

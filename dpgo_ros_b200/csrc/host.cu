@@ -94,6 +94,8 @@ void Agent::add_measurement(const Meas &m) {
       nbrs.insert(m.r1);
     }
   }
+  if (la_used > 0 && !structure_dirty) materialize_lookahead();
+  drop_lookahead();
   structure_dirty = values_dirty = precon_dirty = wiring_dirty = true;
   pub_frames_cache.clear();
   if (team) team->team_dirty = true;
@@ -178,6 +180,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
         X[((size_t)i * 4 + c) * r + a] = s;
       }
   }
+  drop_lookahead();
   dX.upload(X);
   dXinit.upload(X);
   dY.upload(X);
@@ -191,6 +194,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
 }
 
 void Agent::reset() {
+  drop_lookahead();
   instance++;
   iter = 0;
   state = 0;
@@ -309,6 +313,7 @@ void Agent::build_structure() {
     b->alloc(vec);
   dS.alloc((size_t)6 * n);
   dS2.alloc((size_t)6 * n);
+  if (P.acceleration) dLX.alloc((size_t)kLaMax * vec);
   if (dX.n != vec) {  // not initialised yet: allocate so the views are valid
     dX.alloc(vec);
     dY.alloc(vec);
@@ -511,6 +516,10 @@ AgentDev Agent::dev_view() const {
   A.qe_col = d_qe_col.p; A.qe_val = d_qe_val.p; A.qo_rowptr = d_qo_rowptr.p; A.qo_col = d_qo_col.p; A.qo_val = d_qo_val.p;
   A.se_slot = d_se_slot.p; A.se_val = d_se_val.p; A.so_rowptr = d_so_rowptr.p; A.so_slot = d_so_slot.p; A.so_val = d_so_val.p;
   A.inbox_reg = d_inbox_reg(); A.inbox_aux = d_inbox_aux();
+  A.LX = dLX.p;
+  A.la_out = d_la_out;
+  A.outbox_base = d_outbox;
+  A.la_stride = la_stride;
   A.inbox_src = h_inbox;  // pinned + UVA: the same pointer is valid on the device
   A.inbox_doubles = (int)d_inbox.n;
   A.pub_rowptr = d_pub_rowptr.p; A.pub_dst_reg = d_pub_dst_reg.p; A.pub_dst_aux = d_pub_dst_aux.p;
@@ -538,8 +547,28 @@ bool Agent::iterate(bool do_opt) {
     if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
     return false;
   }
-  tm->prepare(false);
+  tm->prepare(false, true);
   const bool accel = P.acceleration != 0;
+  if (!do_opt && la_used < la_valid && lookahead_usable()) {
+    // this iterate(false) was computed ahead of time by the last launch (phase_lookahead): no GPU round trip
+    if (la_used == 0) {
+      volatile TeamCtl *c = reinterpret_cast<volatile TeamCtl *>(tm->h_result);
+      while (c->la_seq != la_launch) {
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (la_restart[la_used]) la_vsrc = la_used;
+    tm->gamma_state = la_gamma[la_used];
+    ++la_used;
+    ++iter;
+    tm->ctl.iter = iter;
+    tm->ctl.gamma = tm->gamma_state;
+    if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
+    status.iteration_number = iter;
+    team_status[id] = get_status();
+    publish_requested = true;
+    return false;
+  }
   const bool restart = accel && ((iter + 2) % P.restart_interval == 0);
   bool can_opt = do_opt;
   if (do_opt && !all_inbox_valid(accel && !restart)) can_opt = false;  // data matrices cannot be built
@@ -558,7 +587,7 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
   if (state != 2) fail(DPGO_B200_ERR_STATE, "getSharedPoseDictWithNeighbor: agent not initialized");
   if (aux && !P.acceleration) fail(DPGO_B200_ERR_STATE, "auxiliary poses need acceleration");
   cuda_check(use_device(device), "cudaSetDevice");
-  team->prepare(false);
+  team->prepare(false, true);
   const std::vector<int> &fr = my_public_frames(nbr);
   const int cnt = (int)fr.size();
   if (cnt > cap) fail(DPGO_B200_ERR_INVALID, "getSharedPoseDictWithNeighbor: buffer too small");
@@ -568,7 +597,11 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
   for (Agent *o : team->agents)
     if (o->id == nbr) colocated = true;
   const size_t pb = (size_t)4 * r * sizeof(double);
-  if (!colocated) {
+  if (!colocated && la_used > 0) {
+    // poses of a speculated iterate(false): X = Y there, one copy serves the regular and the auxiliary dictionary
+    const auto rg = outbox_range.at(nbr);
+    std::memcpy(poses, h_la_out + (size_t)(la_used - 1) * la_stride + (size_t)rg.first * 4 * r, pb * cnt);
+  } else if (!colocated) {
     if (outbox_stale || !outbox_mirror_valid) team->exchange_all();
     const auto rg = outbox_range.at(nbr);
     const size_t o = (aux ? (size_t)std::max(1, outbox_total) * 4 * r : 0) + (size_t)rg.first * 4 * r;
@@ -610,12 +643,28 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
   }
 }
 
+bool Agent::lookahead_usable() const {
+  return P.acceleration && state == 2 && team == own.get() && h_la_out != nullptr && !team->window;
+}
+
+void Agent::materialize_lookahead() {
+  if (la_used == 0) return;
+  cuda_check(use_device(device), "cudaSetDevice");
+  RunArgs args{};
+  args.max_iters = 1;
+  args.force_selected = -1;
+  args.commit_only = 1;
+  team->launch_and_read(args, team->small_grid, false, nullptr);  // commits la_used steps (fills la_commit itself)
+  drop_lookahead();
+  outbox_stale = true;
+}
+
 // mLocalOptResult.fOpt / gradNormOpt (src/PGOAgentROS.cpp:169-172) when the launch skipped them: one
 // gradient pass at X+ against the G of the solve (still cached: G is rebuilt by the next solve only)
 void Agent::finish_opt_stats() {
   if (!stats_pending) return;
   cuda_check(use_device(device), "cudaSetDevice");
-  team->prepare(false);
+  team->prepare(false, true);  // needs X+ (X2) and G only
   const int grid = team->grid;
   if (d_stat_partials.n != (size_t)grid * 2) d_stat_partials.alloc((size_t)grid * 2);
   cuda_check(launch_post_stats(team->T.ag[local_index], dX2.p, d_stat_partials.p, grid, team->stream), "k_post_stats");
@@ -757,6 +806,8 @@ void Team::add(Agent *a) {
   if (a->device != device) fail(DPGO_B200_ERR_INVALID, "agent lives on another device");
   if (!agents.empty() && (agents[0]->r != a->r || agents[0]->P.num_robots != a->P.num_robots))
     fail(DPGO_B200_ERR_INVALID, "agents of one team must share r and num_robots");
+  if (a->la_used > 0) a->materialize_lookahead();
+  a->drop_lookahead();
   if (a->team && a->team != this && a->team != a->own.get()) a->team->remove(a);
   if (agents.empty() && a->own && a->own.get() != this) {
     const unsigned ep = ctl.epoch;
@@ -792,9 +843,12 @@ void Team::remove(Agent *a) {
   }
 }
 
-void Team::prepare(bool need_inbox) {
+void Team::prepare(bool need_inbox, bool keep_lookahead) {
   cuda_check(use_device(device), "cudaSetDevice");
   if (agents.empty()) fail(DPGO_B200_ERR_STATE, "team has no agents");
+  if (!keep_lookahead)
+    for (Agent *a : agents)
+      if (a->la_used > 0) a->materialize_lookahead();  // whoever comes next reads X / Y / V directly
   bool rewire = team_dirty;
   for (Agent *a : agents) {
     if (a->structure_dirty || a->values_dirty || a->precon_dirty) rewire = true;
@@ -1064,6 +1118,13 @@ void Team::layout_result() {
     }
   }
   if (device_outbox) dOutboxAll.alloc(std::max<size_t>(dev_doubles, 32));
+  // a stand-alone accelerated agent also gets kLaMax lookahead outboxes (regular half only: X = Y there)
+  size_t la_off = 0;
+  const bool la_team = agents.size() == 1 && agents[0]->own.get() == this && agents[0]->P.acceleration && !device_outbox;
+  if (la_team) {
+    la_off = off;
+    off += up((size_t)kLaMax * (agents[0]->outbox_doubles() / 2) * sizeof(double), 256);
+  }
   if (off != result_bytes) {
     cuda_check(cudaDeviceSynchronize(), "sync before result realloc");
     if (h_result) cudaFreeHost(h_result);
@@ -1089,6 +1150,14 @@ void Team::layout_result() {
     }
     a->outbox_stale = true;
     a->outbox_mirror_valid = false;
+    a->drop_lookahead();
+    a->d_la_out = a->h_la_out = nullptr;
+    a->la_stride = 0;
+    if (la_team) {
+      a->d_la_out = reinterpret_cast<double *>(d_result + la_off);
+      a->h_la_out = reinterpret_cast<double *>(h_result + la_off);
+      a->la_stride = (int)(a->outbox_doubles() / 2);
+    }
   }
 }
 
@@ -1139,8 +1208,22 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
   const dpgo_b200_params &P = agents[0]->P;
   const int N = P.num_robots;
   args.gamma_tab = nullptr;
-  if (P.acceleration) {
-    const int K = args.max_iters;
+  // stand-alone lookahead: commit what the host consumed, speculate the next N-1 iterate(false) steps
+  Agent *la = (agents.size() == 1 && agents[0]->lookahead_usable() && args.max_iters == 1 && args.mode == 0 &&
+               args.force_selected >= -1)
+                  ? agents[0]
+                  : nullptr;
+  int la_depth = 0;
+  if (la) {
+    args.la_commit = la->la_used;
+    args.la_vsrc = la->la_vsrc;
+    if (!args.commit_only && !P.cost_type) la_depth = std::min(kLaMax, std::max(0, N - 1));
+    args.la_depth = la_depth;
+  }
+  if (P.acceleration && args.commit_only) {
+    // nothing advances
+  } else if (P.acceleration) {
+    const int K = args.max_iters + la_depth;
     h_gamma_tab.resize(K);
     h_gamma_state.resize(K);
     double g = gamma_state;
@@ -1153,9 +1236,13 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
     if (args.mode == 2) {  // second half of a split iteration: the sequences were advanced by the first half
       args.gamma0 = last_gamma_use;
       args.alpha0 = last_alpha_use;
-    } else if (K == 1) {
+    } else if (args.max_iters == 1) {
       args.gamma0 = last_gamma_use = h_gamma_tab[0].x;
       args.alpha0 = last_alpha_use = h_gamma_tab[0].y;
+      for (int j = 0; j < la_depth; ++j) {
+        const bool rst = (ctl.iter + (j + 1) + 2) % P.restart_interval == 0;
+        args.la_tab[j] = make_double2(h_gamma_tab[1 + j].y, rst ? 1.0 : 0.0);
+      }
     } else {
       dGammaTab.alloc(std::max<size_t>(dGammaTab.n, (size_t)K), false);
       cuda_check(cudaMemcpyAsync(dGammaTab.p, h_gamma_tab.data(), sizeof(double2) * K, cudaMemcpyHostToDevice, stream),
@@ -1187,6 +1274,17 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
   host_prof[2] += 1.0;
   if (P.acceleration && ctl.iters_done > 0 && args.mode != 2) gamma_state = h_gamma_state[ctl.iters_done - 1];
   ctl.gamma = gamma_state;
+  if (la) {
+    la->drop_lookahead();
+    if (la_depth > 0 && ctl.iters_done == 1) {
+      la->la_valid = la_depth;
+      la->la_launch = args.seq;
+      for (int j = 0; j < la_depth; ++j) {
+        la->la_gamma[j] = h_gamma_state[1 + j];
+        la->la_restart[j] = args.la_tab[j].y != 0.0;
+      }
+    }
+  }
 }
 
 // completion: poll the sequence number the kernel publishes (after a system-scope fence) in the
@@ -1205,7 +1303,7 @@ void Team::wait_result(unsigned long long expect) {
 }
 
 void Team::run_forced(int sel_local) {
-  prepare(false);
+  prepare(false, true);  // consumed lookahead steps are committed by this very launch
   RunArgs args{};
   args.max_iters = 1;
   args.force_selected = sel_local;

@@ -159,6 +159,18 @@ class Agent {
   DevBuf<double> d_inbox;
   double *inbox_ext = nullptr;  // multi-GPU: the inbox lives in the team's peer-visible window instead
   double *inbox_base() const { return inbox_ext ? inbox_ext : d_inbox.p; }
+  // ---- lookahead of the stand-alone accelerated path (phases.cuh, phase_lookahead)
+  DevBuf<double> dLX;                 // [kLaMax][r x 4n] speculated states
+  double *d_la_out = nullptr, *h_la_out = nullptr;  // [kLaMax][la_stride] public poses, in the team's mapped result block
+  int la_stride = 0;
+  int la_valid = 0, la_used = 0;      // speculated steps available / consumed by iterate(false) without a launch
+  int la_vsrc = -1;                   // consumed restart step (V = X there)
+  unsigned long long la_launch = 0;   // launch whose tail wrote the lookahead (TeamCtl::la_seq)
+  double la_gamma[kLaMax];            // Nesterov gamma after each speculated step
+  unsigned char la_restart[kLaMax];
+  bool lookahead_usable() const;      // stand-alone, accelerated, initialised
+  void materialize_lookahead();       // write the consumed speculated state back to X / Y / V (one tiny launch)
+  void drop_lookahead() { la_valid = la_used = 0; la_vsrc = -1; }
   bool stats_pending = false;  // fOpt / gradNormOpt of the last iterate(true) not evaluated yet
   void finish_opt_stats();
   DevBuf<double> d_stat_partials;
@@ -196,7 +208,7 @@ class Team {
   void remove(Agent *a);
   // ensure every agent's device data + wiring + TeamDev are current; need_inbox: the next launch reads the
   // neighbour poses, so staged host inboxes are uploaded (iterate(false) does not pay for that copy)
-  void prepare(bool need_inbox = true);
+  void prepare(bool need_inbox = true, bool keep_lookahead = false);
   void exchange_all();
   dpgo_b200_run_result run(int max_iters, bool stop_on_terminate);
   // one iteration with a forced selection (standalone iterate path); returns kernel ms

@@ -23,10 +23,18 @@ void count_launch();
 __global__ void __launch_bounds__(kThreads) k_nesterov_only(const __grid_constant__ TeamDev T,
                                                             const __grid_constant__ RunArgs args) {
   TeamCtl c = args.ctl_in;
-  const int iter = c.iter + 1;
+  const int iter = args.commit_only ? c.iter : c.iter + 1;
   const bool accel = T.p.acceleration != 0;
   const bool restart = accel && ((iter + 1) % T.p.restart_interval == 0);
-  if (accel) phase_nesterov<0>(T, args.force_selected, restart, args.alpha0);
+  LaCommit lc{nullptr, nullptr};
+  if (args.la_commit > 0) {
+    const size_t vec = (size_t)4 * T.ag[0].r * T.ag[0].n;
+    lc.X = T.ag[0].LX + (size_t)(args.la_commit - 1) * vec;
+    lc.V = args.la_vsrc >= 0 ? T.ag[0].LX + (size_t)args.la_vsrc * vec : nullptr;
+  }
+  if (accel) phase_nesterov<0>(T, args.force_selected, restart, args.alpha0, lc, args.commit_only != 0);
+  // same pose -> thread-group mapping as phase_nesterov, so every pose's new X / V come from this very thread
+  if (accel && args.la_depth > 0) phase_lookahead<0>(T.ag[0], args.la_depth, args.la_tab);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
@@ -34,9 +42,10 @@ __global__ void __launch_bounds__(kThreads) k_nesterov_only(const __grid_constan
     if (prev == gridDim.x - 1) {  // last block: everyone's outbox writes are visible system-wide
       *T.done_counter = 0ull;
       c.iter = iter;
-      if (T.p.robust) c.robust_inner_iter++;
+      if (T.p.robust && !args.commit_only) c.robust_inner_iter++;
       c.stop_reason = 0;
-      c.iters_done = 1;
+      c.iters_done = args.commit_only ? 0 : 1;
+      c.la_seq = args.seq;
       c.seq = 0;
       *T.ctl = c;
       __threadfence_system();

@@ -23,6 +23,12 @@ struct RunArgs {
   int mode;
   int fabric;  // 1: this launch is one rank of a multi-GPU run (TeamDev::fab is live)
   unsigned pull_mask;  // local agents whose staged host inbox (AgentDev::inbox_src) is copied in by the kernel
+  // stand-alone lookahead (phases.cuh, phase_lookahead)
+  int la_commit;       // speculated steps the host consumed since the last launch (state = LX[la_commit - 1])
+  int la_vsrc;         // consumed step whose X became V (restart iteration), or -1
+  int la_depth;        // steps to speculate at the end of this launch
+  int commit_only;     // k_nesterov_only: write the consumed state back to X / Y / V and do nothing else
+  double2 la_tab[kLaMax];  // (alpha, restart != 0) of the speculated steps
   int skip_stats;  // 1: leave fOpt / gradNormOpt of the last step to Agent::finish_opt_stats (AgentStat::optimized = 2)
 };
 

@@ -82,10 +82,18 @@ __device__ __forceinline__ int gshfl(int v, int src) { return __shfl_sync(0xffff
 // Publishes Y (aux) and, for non-selected agents, X (reg) into the neighbours'
 // inboxes (a9: getAuxSharedPoseDictWithNeighbor :666 / updateAuxNeighborPoses :1278).
 // ---------------------------------------------------------------------------
+// Speculated iterate(false) steps of a stand-alone agent that the host has consumed without a launch (see
+// phase_lookahead): the agent's state is then X = Y = Xsrc, V = Vsrc instead of what A.X / A.V / A.Y hold, and
+// the first kernel that runs afterwards commits it while it loads the poses anyway.
+struct LaCommit {
+  const double *X, *V;  // null: nothing to commit
+};
+
 // per-pose body (group-collective)
 template <int RC>
 __device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, bool valid, int a, int sel_local,
-                                              bool restart, double alpha) {
+                                              bool restart, double alpha, LaCommit lc = LaCommit{nullptr, nullptr},
+                                              bool commit_only = false) {
   const AgentDev &A = T.ag[ai];
   const int r = rdim<RC>(A);
   const bool act = valid && a < r;
@@ -96,7 +104,16 @@ __device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, b
     pe0 = A.pub_rowptr[j];
     pe1 = A.pub_rowptr[j + 1];
   }
-  ld4(A.X + off, r, a, act, x);
+  ld4((lc.X ? lc.X : A.X) + off, r, a, act, x);
+  if (lc.X) {
+    ld4((lc.V ? lc.V : A.V) + off, r, a, act, v);
+    if (valid) {
+      st4(A.X + off, r, a, act, x);
+      st4(A.Y + off, r, a, act, x);
+      if (lc.V) st4(A.V + off, r, a, act, v);
+    }
+    if (commit_only) return;
+  }
   if (restart) {
     if (ai != sel_local && valid) {
       st4(A.V + off, r, a, act, x);
@@ -106,7 +123,7 @@ __device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, b
     }
     return;
   }
-  ld4(A.V + off, r, a, act, v);
+  if (!lc.X) ld4(A.V + off, r, a, act, v);
 #pragma unroll
   for (int c = 0; c < 4; ++c) m[c] = (1.0 - alpha) * x[c] + alpha * v[c];
   if (!valid) {  // keep idle groups on the fast path of sym3_invsqrt
@@ -127,7 +144,8 @@ __device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, b
 
 // pose -> group by PoseIter (stand-alone kernels)
 template <int RC>
-__device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, bool restart, double alpha) {
+__device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, bool restart, double alpha,
+                                               LaCommit lc = LaCommit{nullptr, nullptr}, bool commit_only = false) {
   PoseIter it;
   const int total = T.pose_prefix[T.num_local];
   int item;
@@ -137,8 +155,61 @@ __device__ __forceinline__ void phase_nesterov(const TeamDev &T, int sel_local, 
     if (valid) {
       while (item >= T.pose_prefix[ai + 1]) ++ai;
     }
-    nesterov_pose<RC>(T, ai, valid ? item - T.pose_prefix[ai] : 0, valid, it.a, sel_local, restart, alpha);
+    nesterov_pose<RC>(T, ai, valid ? item - T.pose_prefix[ai] : 0, valid, it.a, sel_local, restart, alpha, lc,
+                      commit_only);
   }
+}
+
+// ---------------------------------------------------------------------------
+// Lookahead for the stand-alone (per-robot API) path.  iterate(false) of an accelerated agent
+// (src/PGOAgentROS.cpp:1185) depends on nothing but the agent's own X and V:
+//     Y = proj((1-alpha) X + alpha V), X = Y     (restart iterations: V = Y = X)
+// and in the synchronous schedule an agent answers N-1 of them between two solves.  A launch costs ~10 us
+// before its result is visible to the host, the arithmetic ~1 us, so the kernel that ends a solve (or an
+// iterate(false) that had to launch) also SPECULATES the next `depth` iterate(false) steps, pose by pose with
+// no grid sync: the states go to A.LX[j], the public poses to lookahead outbox j in mapped host memory.
+// The host then serves iterate(false) + getSharedPoseDict for those steps without touching the GPU and the
+// next launch commits the consumed state (LaCommit).
+// ---------------------------------------------------------------------------
+template <int RC, class Iter>
+__device__ __forceinline__ void lookahead_pose(const AgentDev &A, int j, bool valid, int a, int depth,
+                                               const double2 *tab) {
+  const int r = rdim<RC>(A);
+  const bool act = valid && a < r;
+  const size_t off = (size_t)j * 4 * r, vec = (size_t)4 * r * A.n;
+  double x[4], v[4];
+  int pe0 = 0, pe1 = 0;
+  if (valid) {
+    pe0 = A.pub_rowptr[j];
+    pe1 = A.pub_rowptr[j + 1];
+  }
+  ld4(A.X + off, r, a, act, x);
+  ld4(A.V + off, r, a, act, v);
+  for (int s = 0; s < depth; ++s) {
+    const double alpha = tab[s].x;
+    if (tab[s].y != 0.0) {  // restart iteration: V = Y = X
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = x[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x[c] = (1.0 - alpha) * x[c] + alpha * v[c];
+      if (!valid) {
+        x[0] = (a == 0); x[1] = (a == 1); x[2] = (a == 2);
+      }
+      stiefel_project_row(x);
+    }
+    if (valid) {
+      st4(A.LX + s * vec + off, r, a, act, x);
+      for (int e = pe0; e < pe1; ++e)
+        st4(A.la_out + (size_t)s * A.la_stride + (A.pub_dst_reg[e] - A.outbox_base), r, a, act, x);
+    }
+  }
+}
+template <int RC>
+__device__ __forceinline__ void phase_lookahead(const AgentDev &A, int depth, const double2 *tab) {
+  PoseIter it;
+  int j;
+  while (it.next(A.n, j)) lookahead_pose<RC, PoseIter>(A, j < A.n ? j : 0, j < A.n, it.a, depth, tab);
 }
 
 // Per-CTA pose ownership used by the persistent kernel: CTA b owns the balanced chunk
@@ -150,7 +221,8 @@ struct ChunkTable {
 };
 template <int RC>
 __device__ __forceinline__ void phase_nesterov_chunk(const TeamDev &T, const ChunkTable &ct, int sel_local,
-                                                     bool restart, double alpha) {
+                                                     bool restart, double alpha,
+                                                     LaCommit lc = LaCommit{nullptr, nullptr}) {
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   const int total = ct.prefix[T.num_local];
   for (int base = 0; base < total; base += kGroupsPerCta) {
@@ -160,7 +232,7 @@ __device__ __forceinline__ void phase_nesterov_chunk(const TeamDev &T, const Chu
     if (valid) {
       while (item >= ct.prefix[ai + 1]) ++ai;
     }
-    nesterov_pose<RC>(T, ai, valid ? ct.p0[ai] + item - ct.prefix[ai] : 0, valid, a, sel_local, restart, alpha);
+    nesterov_pose<RC>(T, ai, valid ? ct.p0[ai] + item - ct.prefix[ai] : 0, valid, a, sel_local, restart, alpha, lc);
   }
 }
 

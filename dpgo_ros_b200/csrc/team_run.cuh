@@ -450,7 +450,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncthreads();  // X / V / Y of my chunk were last written by other threads of this CTA
         // the selected robot of the previous iteration has finished reading its inbox
         if (fab && !fabric_wait(F, gs, bs, fab_wait_to)) { dead = true; break; }
-        phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha);
+        LaCommit lc{nullptr, nullptr};
+        if (step == 0 && args.la_commit > 0) {
+          const size_t vec = (size_t)4 * R * T.ag[0].n;
+          lc.X = T.ag[0].LX + (size_t)(args.la_commit - 1) * vec;
+          lc.V = args.la_vsrc >= 0 ? T.ag[0].LX + (size_t)args.la_vsrc * vec : nullptr;
+        }
+        phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha, lc);
         PROF(1)
         grid_barrier(gs, bs);
         if (fab) {  // every rank's Y (and X) of this iteration has reached its neighbours' inboxes
@@ -664,6 +670,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     *T.ctl = c;
     __threadfence_system();
     reinterpret_cast<volatile TeamCtl *>(T.ctl)->seq = args.seq;
+  }
+  if (args.la_depth > 0 && !dead) {
+    // the host already has this launch's result; speculate the agent's next iterate(false) steps behind it
+    phase_lookahead<R>(T.ag[0], args.la_depth, args.la_tab);
+    grid_barrier(gs, bs);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      reinterpret_cast<volatile TeamCtl *>(T.ctl)->la_seq = args.seq;
+    }
   }
 }
 

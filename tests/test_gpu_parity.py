@@ -202,11 +202,13 @@ def test_standalone_agents_with_host_exchange(small_problem):
         assert abs(st.relative_change - oteam.status(sel).relative_change) < 1e-9
 
 
-@pytest.mark.parametrize("accel", [0, 1])
-def test_native_sync_driver_matches_oracle(sphere8_problem, accel):
-    """dpgo_b200_sync_driver_run: per-robot C ABI + host buffers + one thread per robot."""
+@pytest.mark.parametrize("accel,restart", [(0, 50), (1, 50), (1, 5), (1, 7)])
+def test_native_sync_driver_matches_oracle(sphere8_problem, accel, restart):
+    """dpgo_b200_sync_driver_run: per-robot C ABI + host buffers + one thread per robot.  With acceleration the
+    iterate(false) calls are served from the lookahead the previous launch speculated (restart intervals 5 and 7
+    put restart iterations inside the speculated chains)."""
     kw = dict(r=5, method=1, rgd_stepsize=0.2 if accel else 0.05, rgd_use_preconditioner=1, acceleration=accel,
-              restart_interval=50, rel_change_tol=0.1, max_num_iters=1000)
+              restart_interval=restart, rel_change_tol=0.1, max_num_iters=1000)
     oteam = orc.OracleTeam(sphere8_problem, **kw)
     _, agents = gpu.make_team(sphere8_problem, colocate=False, **kw)
     gpu.exchange_host(agents, accel=bool(accel))
@@ -214,8 +216,15 @@ def test_native_sync_driver_matches_oracle(sphere8_problem, accel):
     oteam.run(60, stop_on_terminate=False)
     for rid in range(8):
         assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, rid
+        if accel:
+            assert rel(agents[rid].getX(2), oteam.get_x(rid, 2)) < 1e-9, rid   # V
         assert agents[rid].iteration_number() == 60
     assert sec > 0
+    # keep going after the state was read back (lookahead materialised / dropped): still on the oracle's path
+    sec, term = gpu.sync_driver_run(agents, 21, bool(accel))
+    oteam.run(21, stop_on_terminate=False)
+    for rid in range(8):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, rid
 
 
 def test_iterate_without_neighbor_poses_is_refused(small_problem):
