@@ -16,7 +16,7 @@ for grid in (148, 64, 16, 1):
 pb = datasets.load_g2o_problem("sphere2500", 8)
 kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=50, rel_change_tol=0.0, max_num_iters=10**9)
 team, agents = gpu.make_team(pb, **kw)
-team.run(20, stop_on_terminate=False)
+team.run(3000, stop_on_terminate=False)
 names = ["start", "nesterov", "barrier", "grad", "reduce", "rgdstep", "reduce", "grad2", "reduce"]
 for cta in (0, 73, 147):
     iters = 12
@@ -24,6 +24,7 @@ for cta in (0, 73, 147):
     rc = L.dpgo_b200_debug_team_profile(team.h, iters, cta, buf)
     dbg = np.array(buf[iters * 16:])
     print('   grad marks 0..9 (cycles from mark 0):', [int(x - dbg[0]) for x in dbg[:10]])
+    print('   warp-1 nesterov marks 24..27 (from dense mark 19):', [int(dbg[k] - dbg[19]) for k in (24, 25, 26, 27)])
     print('   dense marks 20,16,17,18,19,21,22,23 (from 20):', [int(dbg[k] - dbg[20]) for k in (20, 16, 17, 18, 19, 21, 22, 23)])
     a = np.array(buf[:iters * 16]).reshape(iters, 16)
     d = np.diff(a[:, :9], axis=1)
