@@ -38,6 +38,39 @@ import numpy as np  # noqa: E402
 CONFIG2 = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=50,
                rel_change_tol=0.0, max_num_iters=10 ** 9)  # tolerance 0: the bench never stops early
 WORKLOAD = "sphere2500.g2o / 8 agents / r=5 / RGD(step 0.2, precond) + Nesterov(restart 50) / RoundRobin"
+# the reference's asynchronous demo (launch/asapp_demo.launch:2-10: sphere2500, RGD 0.2 + preconditioner, no
+# acceleration) as its equal-rate / unit-delay schedule: every robot steps every tick (secondary figure, not `value`)
+ASYNC_CONFIG = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=0, rel_change_tol=0.0,
+                    max_num_iters=10 ** 9)
+
+
+def async_cpu_reference(ticks=300, threads=None):
+    from dpgo_ros_b200 import datasets
+    from oracle import binding as orc
+    threads = threads or min(8, os.cpu_count() or 1)
+    pb = datasets.load_g2o_problem("sphere2500", 8)
+    team = orc.OracleTeam(pb, **ASYNC_CONFIG)
+    team.run_parallel(20, threads=threads)
+    res = team.run_parallel(ticks, threads=threads)
+    return res.iterations / res.wall_seconds
+
+
+def async_mode_single_gpu(pb, device, ticks=2000):
+    """Secondary figure: the asynchronous mode (all 8 robots step every tick) on one GPU."""
+    from dpgo_ros_b200 import agent as gpu
+    team, agents = gpu.make_team(pb, device=device, **ASYNC_CONFIG)
+    team.set_schedule(1)
+    team.run(200, stop_on_terminate=False)
+    res = team.run(ticks, stop_on_terminate=False)
+    cost = team.global_cost()
+    team.close()
+    for a in agents:
+        a.close()
+    tps = ticks / (res.device_ms * 1e-3)
+    return {"workload": "sphere2500.g2o / 8 agents / RGD(step 0.2, precond), no acceleration / every robot steps "
+                        "every tick (asynchronous mode, equal-rate unit-delay schedule)",
+            "ticks_per_s": tps, "robot_updates_per_s": tps * pb.num_robots, "us_per_tick": 1e6 / tps,
+            "final_cost_2f": cost}
 
 
 def load_peaks():
@@ -243,6 +276,8 @@ def main():
         traffic = json.load(open(tpath))["traffic_bytes_per_step"] * args.steps
     achieved = step_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
     cpu = cpu_reference(args.cpu_steps, 50)
+    async_mode = async_mode_single_gpu(pb, local_rank)
+    async_mode["cpu_ticks_per_s"] = async_cpu_reference()
     line = {
         "metric": "rbcd_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -267,6 +302,7 @@ def main():
         "cpu_baseline": {"value": cpu["value"], "unit": "iters/s", "cores": cpu["threads"], "kind": "port",
                          "sample": f"{cpu['steps']} steps of the same workload on the oracle, one OS thread per "
                                    f"agent ({cpu['threads']} threads, {cpu['cores']} host cores)"},
+        "async_mode": async_mode,
     }
     print(json.dumps(line))
     return 0

@@ -288,6 +288,10 @@ class Team:
         """One global iteration for the local agents of a partial team (multi-GPU); see dpgo_b200_team_step."""
         check(self.L.dpgo_b200_team_step(self.h, selected_robot, mode), "team_step")
 
+    def set_schedule(self, schedule: int) -> None:
+        """0: synchronous RoundRobin token; 1: parallel ticks (the asynchronous mode, see dpgo_b200_team_set_schedule)."""
+        check(self.L.dpgo_b200_team_set_schedule(self.h, schedule), "team_set_schedule")
+
     def set_grid(self, num_ctas: int) -> None:
         check(self.L.dpgo_b200_team_set_grid(self.h, num_ctas), "team_set_grid")
 

@@ -81,7 +81,7 @@ SYMBOLS = [
     "dpgo_b200_team_fabric_init", "dpgo_b200_team_fabric_window", "dpgo_b200_team_fabric_import",
     "dpgo_b200_team_fabric_route", "dpgo_b200_team_fabric_run", "dpgo_b200_team_fabric_set_timeout",
     "dpgo_b200_team_fabric_close", "dpgo_b200_team_gnc_compute_weights", "dpgo_b200_team_gnc_finish_update",
-    "dpgo_b200_get_shared_loop_closures",
+    "dpgo_b200_get_shared_loop_closures", "dpgo_b200_team_set_schedule",
 ]
 
 
@@ -160,6 +160,7 @@ def lib():
     L.dpgo_b200_team_global_cost.restype = C.c_double
     L.dpgo_b200_team_global_cost.argtypes = [vp, ip]
     L.dpgo_b200_team_set_grid.argtypes = [vp, C.c_int]
+    L.dpgo_b200_team_set_schedule.argtypes = [vp, C.c_int]
     L.dpgo_b200_team_step.argtypes = [vp, C.c_int, C.c_int]
     L.dpgo_b200_team_fabric_init.argtypes = [vp, C.c_int, C.c_int]
     L.dpgo_b200_team_fabric_window.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), vp]

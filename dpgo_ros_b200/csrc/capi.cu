@@ -542,6 +542,12 @@ int dpgo_b200_team_gnc_finish_update(dpgo_b200_team_t h) {
   TT(h)->gnc_finish_update();
   API_END
 }
+int dpgo_b200_team_set_schedule(dpgo_b200_team_t h, int schedule) {
+  API_BEGIN
+  if (schedule != 0 && schedule != 1) fail(DPGO_B200_ERR_INVALID, "schedule must be 0 (RoundRobin) or 1 (parallel)");
+  TT(h)->schedule = schedule;
+  API_END
+}
 int dpgo_b200_team_set_grid(dpgo_b200_team_t h, int num_ctas) {
   API_BEGIN
   Team *t = TT(h);

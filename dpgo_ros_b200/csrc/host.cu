@@ -1086,6 +1086,7 @@ dpgo_b200_run_result Team::fabric_run(int max_iters, bool stop_on_terminate) {
   args.force_selected = -2;
   args.stop_on_terminate = stop_on_terminate ? 1 : 0;
   args.fabric = 1;
+  args.parallel = parallel_schedule_checked();
   T.fab.seq0 = fab_seq;
   float ms = 0;
   launch_and_read(args, grid, true, &ms);
@@ -1362,6 +1363,16 @@ void Team::step(int selected_robot, int mode) {
   launch_and_read(args, small ? small_grid : grid, false, nullptr);
 }
 
+int Team::parallel_schedule_checked() const {
+  if (schedule == 0) return 0;
+  const dpgo_b200_params &P = agents[0]->P;
+  if (P.method != 1 || P.acceleration || P.cost_type != 0)
+    fail(DPGO_B200_ERR_INVALID,
+         "the parallel (asynchronous-mode) schedule runs RGD without acceleration on the L2 cost "
+         "(src/PGOAgentROSNode.cpp:80-93)");
+  return 1;
+}
+
 dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
   dpgo_b200_run_result res{};
   prepare();
@@ -1380,6 +1391,7 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
     args.max_iters = std::min(remaining, 1 << 16);
     args.force_selected = -2;
     args.stop_on_terminate = stop_on_terminate ? 1 : 0;
+    args.parallel = parallel_schedule_checked();
     float ms = 0;
     launch_and_read(args, grid, true, &ms);
     res.device_ms += ms;

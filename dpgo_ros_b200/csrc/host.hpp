@@ -211,6 +211,8 @@ class Team {
   void prepare(bool need_inbox = true, bool keep_lookahead = false);
   void exchange_all();
   dpgo_b200_run_result run(int max_iters, bool stop_on_terminate);
+  int parallel_schedule_checked() const;
+  int schedule = 0;  // 0: synchronous RoundRobin token (:464-472); 1: parallel ticks (asynchronous mode, :119-127)
   // one iteration with a forced selection (standalone iterate path); returns kernel ms
   void run_forced(int sel_local);
   void gnc_update_all();

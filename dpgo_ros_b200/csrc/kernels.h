@@ -29,6 +29,7 @@ struct RunArgs {
   int la_depth;        // steps to speculate at the end of this launch
   int commit_only;     // k_nesterov_only: write the consumed state back to X / Y / V and do nothing else
   double2 la_tab[kLaMax];  // (alpha, restart != 0) of the speculated steps
+  int parallel;        // 1: asynchronous mode as the equal-rate / unit-delay schedule (every robot steps every tick)
   int skip_stats;  // 1: leave fOpt / gradNormOpt of the last step to Agent::finish_opt_stats (AgentStat::optimized = 2)
 };
 

@@ -428,9 +428,49 @@ __global__ void __launch_bounds__(kThreads, 1)
 #define PROF(k)                                                                                       \
   if (T.prof && step < T.prof_iters && threadIdx.x == 0 && (int)blockIdx.x == T.prof_cta)             \
     T.prof[step * 16 + (k)] = clock64();
+  unsigned pend_all = 0;  // parallel schedule: agents whose fOpt / gradNormOpt are evaluated at exit
   for (int step = 0; step < args.max_iters; ++step) {
     const int iter = (args.mode == 2) ? c.iter : c.iter + 1;
     PROF(0)
+    if constexpr (M == 1) {
+      if (args.parallel) {
+        // ---- asynchronous mode as its equal-rate / unit-delay schedule (oracle: Team::runParallel; wrapper:
+        // runOnceAsynchronous, src/PGOAgentROS.cpp:119-127): every robot takes an RGD step against the neighbour
+        // poses of the previous tick.  One agent per GPU makes the ticks of all robots truly concurrent.
+        for (int ai = 0; ai < T.num_local; ++ai) {
+          const AgentDev &A = T.ag[ai];
+          double pf = 0, pg2 = 0;
+          phase_grad<R>(A, A.X, A.inbox_reg, true, nullptr, A.Rg, A.RgT, nullptr, L.stage, pf, pg2);
+          defer_store(T, ai, 0, pf);
+          defer_store(T, ai, 1, pg2);
+        }
+        grid_barrier(gs, bs);
+        if (fab) {  // every rank has assembled its G: the inboxes may be overwritten
+          fabric_arrive(F, fs, 0);
+          if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
+        }
+        for (int ai = 0; ai < T.num_local; ++ai) {
+          const AgentDev &A = T.ag[ai];
+          if (use_slab) slab_prefetch(A, ai, ss, &mbar, L.slab, L.slab_cap);
+          double prel = 0;
+          phase_rgd_step<R>(A, ai, P, A.X, false, false, 0.0, ss, &mbar, L.slab, L.slab_cap, L.zs, sm_slab, A.X2, prel);
+          defer_store(T, ai, 4, prel);
+          __syncthreads();  // the slab buffer and zs are reused by the next agent
+        }
+        grid_barrier(gs, bs);
+        if (fab) {  // every rank's X+ has reached its neighbours' inboxes
+          fabric_arrive(F, fs, 0);
+          if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
+        }
+        const unsigned everyone = (T.num_local >= 32) ? ~0u : ((1u << T.num_local) - 1u);
+        touched |= everyone;
+        rel_due |= everyone;
+        pend_all = everyone;
+        c.iter = iter;
+        ++done;
+        continue;
+      }
+    }
     int sel_robot, sel_local;
     if (!schedule) {
       sel_local = args.force_selected;
@@ -609,6 +649,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   // ---- epilogue: everything that was deferred becomes observable now
   grid_barrier(gs, bs);
   if (args.skip_stats) pend_ai = -1;  // fOpt / gradNormOpt are evaluated on demand by the host (finish_opt_stats)
+  if (pend_all) {
+    for (int ai = 0; ai < T.num_local; ++ai) {
+      const AgentDev &B = T.ag[ai];
+      double qf = 0, qg2 = 0;
+      phase_grad<R>(B, B.X2, nullptr, false, nullptr, nullptr, nullptr, nullptr, L.stage, qf, qg2);
+      defer_store(T, ai, 2, qf);
+      defer_store(T, ai, 3, qg2);
+    }
+    grid_barrier(gs, bs);
+  }
   if (pend_ai >= 0) {
     // statistics of the last RGD step (mLocalOptResult.fOpt / gradNormOpt, src/PGOAgentROS.cpp:169-172)
     const AgentDev &B = T.ag[pend_ai];

@@ -435,14 +435,40 @@ def load_tunnels_problem() -> Problem:
     return Problem(name="tunnels/8", num_robots=8, meas=meas, n=n, T_init=T_init)
 
 
-def make_synthetic_problem(num_poses: int, num_edges: int, num_robots: int, seed: int = 0,
-                           lc_window: int = 2000, kappa: float = 200.0, tau: float = 100.0) -> Problem:
-    """Seeded synthetic SE(3) graph of SURVEY §8d config 5 (generator committed here).
+def _snake_lattice(num_poses: int):
+    """Lattice coordinates of a 3-D boustrophedon path: consecutive poses are always lattice neighbours."""
+    side = int(np.ceil(num_poses ** (1.0 / 3.0)))
+    nx = ny = side
+    nz = int(np.ceil(num_poses / (nx * ny)))
+    idx = np.arange(nx * ny * nz)
+    z = idx // (nx * ny)
+    rem = idx % (nx * ny)
+    yy = rem // nx
+    y = np.where(z % 2 == 0, yy, ny - 1 - yy)          # alternate the row order per layer
+    row = z * ny + yy                                  # global row counter along the path
+    xx = rem % nx
+    x = np.where(row % 2 == 0, xx, nx - 1 - xx)        # alternate the direction per row
+    coords = np.stack([x, y, z], axis=1)[:num_poses]
+    lut = -np.ones((nx, ny, nz), dtype=np.int64)
+    lut[coords[:, 0], coords[:, 1], coords[:, 2]] = np.arange(num_poses)
+    return coords, lut, (nx, ny, nz)
 
-    Random-walk trajectory (step U[0.5,1.5] along the body x-axis, rotation
-    exp(N(0, 0.2^2 I))), `num_poses-1` odometry edges, the rest loop closures:
-    90 % with |i-j| <= lc_window, 10 % uniform, no duplicates; measurement noise
-    rotation exp(N(0, 0.05^2 I)), translation N(0, 0.1^2 I).
+
+def make_synthetic_problem(num_poses: int, num_edges: int, num_robots: int, seed: int = 0,
+                           kappa: float = 200.0, tau: float = 100.0, init: str = "near_truth") -> Problem:
+    """Seeded synthetic SE(3) graph for BASELINE config 5 (100k poses / 1M edges / 8 agents at full size).
+
+    The trajectory snakes through a unit 3-D lattice (like the grid3D / torus3D benchmark graphs): pose i sits
+    on lattice site i of a boustrophedon path, its orientation follows a random walk exp(N(0, 0.2^2 I)) per
+    step.  Edges: the `num_poses - 1` odometry edges plus loop closures drawn without replacement (seeded) from
+    all non-consecutive pose pairs whose sites are within the 26-neighbourhood (relative translations <= sqrt 3,
+    so the graph is as well conditioned as the real benchmarks).  Noise: rotation exp(N(0, 0.05^2 I)),
+    translation N(0, 0.1^2 I); constant kappa / tau.  Contiguous split over `num_robots` (the dataset
+    publisher's rule, src/PGODatasetPublisherNode.cpp:84-103).
+
+    init: "near_truth" perturbs the ground truth by exp(N(0, 0.05^2 I)) / N(0, 0.1^2 I) and stands in for the
+    Chordal initialisation of the async demo (launch/asapp_demo.launch:10; initialisation is SURVEY 8f rank 1,
+    outside the hot path); "odometry" chains the odometry edges from pose 0.
     """
     rng = np.random.default_rng(seed)
 
@@ -458,42 +484,33 @@ def make_synthetic_problem(num_poses: int, num_edges: int, num_robots: int, seed
         c = np.cos(th)[..., None]
         return np.eye(3) + s * K + (1 - c) * (K @ K)
 
+    coords, lut, dims = _snake_lattice(num_poses)
+    tgt = coords.astype(np.float64)
     dR = expm_so3(rng.normal(0, 0.2, size=(num_poses - 1, 3)))
-    step = rng.uniform(0.5, 1.5, size=num_poses - 1)
     Rgt = np.empty((num_poses, 3, 3))
-    tgt = np.empty((num_poses, 3))
     Rgt[0] = np.eye(3)
-    tgt[0] = 0
     for i in range(num_poses - 1):
-        tgt[i + 1] = tgt[i] + Rgt[i] @ np.array([step[i], 0.0, 0.0])
         Rgt[i + 1] = Rgt[i] @ dR[i]
+    # candidate loop closures: half of the 26-neighbourhood (each unordered pair once), minus the odometry pairs
+    cs, cd = [], []
+    offs = [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1) if (dz, dy, dx) > (0, 0, 0)]
+    for dx, dy, dz in offs:
+        q = coords + np.array([dx, dy, dz])
+        ok = ((q >= 0) & (q < np.array(dims))).all(axis=1)
+        a = np.nonzero(ok)[0]
+        b = lut[q[a, 0], q[a, 1], q[a, 2]]
+        keep = (b >= 0) & (np.abs(b - a) > 1)
+        a, b = a[keep], b[keep]
+        cs.append(np.minimum(a, b))
+        cd.append(np.maximum(a, b))
+    cs, cd = np.concatenate(cs), np.concatenate(cd)
     n_lc = num_edges - (num_poses - 1)
-    src = np.arange(num_poses - 1, dtype=np.int64)
-    dst = src + 1
-    have = set()
-    lc_s, lc_d = [], []
-    while len(lc_s) < n_lc:
-        need = n_lc - len(lc_s)
-        i = rng.integers(0, num_poses, size=need * 2)
-        local = rng.random(need * 2) < 0.9
-        off = rng.integers(2, max(3, lc_window + 1), size=need * 2)
-        j_local = i + off
-        j_unif = rng.integers(0, num_poses, size=need * 2)
-        j = np.where(local, j_local, j_unif)
-        for a, b in zip(i.tolist(), j.tolist()):
-            if b >= num_poses or a == b or abs(a - b) == 1:
-                continue
-            if a > b:
-                a, b = b, a
-            if (a, b) in have:
-                continue
-            have.add((a, b))
-            lc_s.append(a)
-            lc_d.append(b)
-            if len(lc_s) >= n_lc:
-                break
-    src = np.concatenate([src, np.array(lc_s, dtype=np.int64)])
-    dst = np.concatenate([dst, np.array(lc_d, dtype=np.int64)])
+    if n_lc > len(cs):
+        raise ValueError(f"only {len(cs)} lattice loop closures available for {num_poses} poses, asked for {n_lc}")
+    pick = rng.choice(len(cs), size=n_lc, replace=False)
+    pick.sort()
+    src = np.concatenate([np.arange(num_poses - 1, dtype=np.int64), cs[pick]])
+    dst = np.concatenate([np.arange(1, num_poses, dtype=np.int64), cd[pick]])
     m = src.shape[0]
     Rn = expm_so3(rng.normal(0, 0.05, size=(m, 3)))
     tn = rng.normal(0, 0.1, size=(m, 3))
@@ -502,7 +519,13 @@ def make_synthetic_problem(num_poses: int, num_edges: int, num_robots: int, seed
     meas = Measurements(r1=np.zeros(m, np.int32), p1=src.astype(np.int32), r2=np.zeros(m, np.int32),
                         p2=dst.astype(np.int32), R=Rrel, t=trel, kappa=np.full(m, kappa), tau=np.full(m, tau),
                         weight=np.ones(m), fixed=np.zeros(m, np.uint8))
-    Rg, tg = _global_odometry_init(meas, num_poses)
+    if init == "near_truth":
+        Rg = Rgt @ expm_so3(rng.normal(0, 0.05, size=(num_poses, 3)))
+        tg = tgt + rng.normal(0, 0.1, size=(num_poses, 3))
+    elif init == "odometry":
+        Rg, tg = _global_odometry_init(meas, num_poses)
+    else:
+        raise ValueError(init)
     part, start = partition_contiguous(meas, num_poses, num_robots)
     n = [int(start[r + 1] - start[r]) for r in range(num_robots)]
     T_init = []

@@ -175,6 +175,12 @@ int dpgo_b200_team_run(dpgo_b200_team_t t, int max_iters, int stop_on_terminate,
  *         iteration were delivered (the gate of src/PGOAgentROS.cpp:136-149).               */
 int dpgo_b200_team_step(dpgo_b200_team_t t, int selected_robot, int mode);
 double dpgo_b200_team_global_cost(dpgo_b200_team_t t, int *status);
+/* schedule of team_run / team_fabric_run.  0 (default): the synchronous protocol -- one UPDATE token, RoundRobin
+ * (src/PGOAgentROS.cpp:443-479, 1161-1189).  1: the asynchronous mode (asynchronous=true selects RGD and lets
+ * every robot optimise on its own clock, src/PGOAgentROSNode.cpp:80-93, src/PGOAgentROS.cpp:119-127) as its
+ * deterministic equal-rate / unit-delay schedule: in every iteration ALL robots take an RGD step against the
+ * neighbour poses of the previous iteration, then all publish; no acceleration, no termination test.        */
+int dpgo_b200_team_set_schedule(dpgo_b200_team_t t, int schedule);
 /* tuning knob: CTAs of the persistent kernel (0 = one per SM) */
 int dpgo_b200_team_set_grid(dpgo_b200_team_t t, int num_ctas);
 

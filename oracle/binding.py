@@ -97,6 +97,7 @@ def lib():
     L.orc_initialize_in_global_frame.argtypes = [C.c_void_p, C.c_int, dp]
     L.orc_exchange_all.argtypes = [C.c_void_p]
     L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
+    L.orc_run_parallel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
     L.orc_agent_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_get_x.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
     L.orc_get_opt_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrcOptResult)]
@@ -203,6 +204,12 @@ class OracleTeam:
     def run(self, max_iters: int, threads: int = 1, stop_on_terminate: bool = True) -> OrcRunResult:
         out = OrcRunResult()
         _chk(self.L.orc_run(self.h, max_iters, threads, int(stop_on_terminate), C.byref(out)), "run")
+        return out
+
+    def run_parallel(self, ticks: int, threads: int = 1) -> OrcRunResult:
+        """The asynchronous mode as its equal-rate / unit-delay schedule (Team::runParallel)."""
+        out = OrcRunResult()
+        _chk(self.L.orc_run_parallel(self.h, ticks, threads, C.byref(out)), "run_parallel")
         return out
 
     def iterate(self, rid: int, do_opt: bool):

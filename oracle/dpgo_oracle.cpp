@@ -1212,6 +1212,26 @@ TeamRunResult Team::run(int maxIters, int numThreads, bool stopOnTerminate) {
   return res;
 }
 
+TeamRunResult Team::runParallel(int ticks, int numThreads) {
+  TeamRunResult res;
+  const int N = size();
+  if (params_.acceleration) throw std::runtime_error("the asynchronous schedule runs without acceleration");
+  SpinPool pool(std::max(1, std::min(numThreads, N)));
+  auto t0 = std::chrono::high_resolution_clock::now();
+  for (int it = 0; it < ticks; ++it) {
+    pool.parallelFor(N, [&](int a) { agents_[a]->iterate(true); });
+    for (int a = 0; a < N; ++a) deliver(a);
+    for (int a = 0; a < N; ++a) {
+      const Status s = agents_[a]->getStatus();
+      for (int b = 0; b < N; ++b)
+        if (b != a) agents_[b]->setNeighborStatus(s);
+    }
+    res.iterations++;
+  }
+  res.wallSeconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  return res;
+}
+
 double Team::globalCost() const {
   double cost = 0;
   const int r = params_.r;

@@ -330,6 +330,11 @@ class Team {
   void exchangeAll();
   // run up to maxIters more global iterations (or until termination)
   TeamRunResult run(int maxIters, int numThreads, bool stopOnTerminate);
+  // The asynchronous mode (ASAPP: runOnceAsynchronous, src/PGOAgentROS.cpp:119-127; every robot optimises on its
+  // own clock against the latest neighbour poses it has received, no acceleration, no termination test --
+  // SURVEY 3.3) restated as its deterministic equal-rate / unit-delay schedule: in every tick ALL robots run
+  // iterate(true) against the neighbour poses published in the previous tick, then all publish.
+  TeamRunResult runParallel(int ticks, int numThreads);
   int nextSelected() const { return selected_; }
   // total cost 2 f over the whole team graph at the current X (each edge once)
   double globalCost() const;

@@ -163,6 +163,15 @@ int orc_run(void *t, int max_iters, int threads, int stop_on_terminate, orc_run_
   ORC_CATCH
 }
 
+int orc_run_parallel(void *t, int ticks, int threads, orc_run_result *out) {
+  ORC_TRY TeamRunResult r = ((Team *)t)->runParallel(ticks, threads);
+  out->iterations = r.iterations;
+  out->terminated = r.terminated;
+  out->weight_updates = r.weightUpdates;
+  out->wall_seconds = r.wallSeconds;
+  ORC_CATCH
+}
+
 int orc_agent_iterate(void *t, int agent, int do_opt) {
   ORC_TRY((Team *)t)->agent(agent).iterate(do_opt != 0);
   ORC_CATCH

@@ -1,0 +1,78 @@
+"""The asynchronous mode as its equal-rate / unit-delay ("parallel") schedule: every robot takes an RGD step per tick
+against the neighbour poses of the previous tick (dpgo_b200_team_set_schedule(1); oracle: Team::runParallel).
+BASELINE config 5 at a size the oracle finishes in seconds, plus the same schedule over the multi-GPU fabric."""
+import numpy as np
+import pytest
+
+from dpgo_ros_b200 import agent as gpu
+from dpgo_ros_b200 import datasets
+from oracle import binding as orc
+
+pytestmark = pytest.mark.gpu
+
+ASYNC = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=0, rel_change_tol=0.0,
+             max_num_iters=10 ** 9)   # launch/asapp_demo.launch:7-8
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def synth8():
+    return datasets.make_synthetic_problem(2000, 20000, 8, seed=0)
+
+
+def test_parallel_schedule_matches_oracle(synth8):
+    oteam = orc.OracleTeam(synth8, **ASYNC)
+    team, agents = gpu.make_team(synth8, **ASYNC)
+    team.set_schedule(1)
+    c0 = team.global_cost()
+    res = team.run(40, stop_on_terminate=False)
+    oteam.run_parallel(40, threads=8)
+    assert res.iterations == 40 and res.kernel_launches == 1
+    for rid in range(8):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, rid
+        o, g = oteam.opt_result(rid), agents[rid].localOptResult()
+        assert abs(g.f_init - o.f_init) <= 1e-9 * abs(o.f_init)
+        assert abs(g.f_opt - o.f_opt) <= 1e-9 * abs(o.f_opt)
+        assert abs(g.relative_change - o.relative_change) <= 1e-9
+    c1 = team.global_cost()
+    assert abs(c1 - oteam.global_cost()) <= 1e-9 * c1
+    assert c1 < 0.3 * c0   # 380053 -> ~108400 (the optimum is ~108373)
+
+
+def test_parallel_schedule_on_sphere2500(sphere8_problem):
+    kw = dict(ASYNC, rgd_stepsize=0.1)
+    oteam = orc.OracleTeam(sphere8_problem, **kw)
+    team, agents = gpu.make_team(sphere8_problem, **kw)
+    team.set_schedule(1)
+    team.run(25, stop_on_terminate=False)
+    oteam.run_parallel(25, threads=8)
+    for rid in range(8):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, rid
+
+
+def test_parallel_schedule_rejects_acceleration(synth8):
+    from dpgo_ros_b200.capi import DpgoError
+    team, agents = gpu.make_team(synth8, **dict(ASYNC, acceleration=1, restart_interval=50))
+    team.set_schedule(1)
+    with pytest.raises(DpgoError):
+        team.run(2, stop_on_terminate=False)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_parallel_schedule_over_fabric(synth8, world):
+    """Every rank steps its robots concurrently; two fabric barriers per tick.  Bit-identical to one team."""
+    from dpgo_ros_b200 import dist as ddist
+    team, agents = gpu.make_team(synth8, **ASYNC)
+    team.set_grid(24)
+    team.set_schedule(1)
+    team.run(30, stop_on_terminate=False)
+    ref = {a.id: a.getX() for a in agents}
+    fab = ddist.LocalFabric(synth8, world, grid=24, schedule=1, **ASYNC)
+    done, term, wu, ms = fab.run(30, stop_on_terminate=False)
+    assert done == 30
+    for rid, a in fab.all_agents().items():
+        assert rel(a.getX(), ref[rid]) == 0.0, rid
+    fab.close()
