@@ -151,14 +151,14 @@ __global__ void __launch_bounds__(kThreads) k_precond(const __grid_constant__ Ag
                                                       size_t slab_cap) {
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
   __shared__ double sm_slab[8 * 16 * 8];
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[1];
   double *slab = reinterpret_cast<double *>(dyn_smem_raw);
   double *zs = reinterpret_cast<double *>(dyn_smem_raw + slab_cap);
-  if (threadIdx.x == 0) mbar_init(&mbar);
+  if (threadIdx.x == 0) mbar_init(&mbar[0]);
   __syncthreads();
   SlabState ss{-1, 0u, 0};
   double p = 0;
-  phase_precond<R>(A, 0, X, V, VT, out, nullptr, ss, &mbar, slab, slab_cap, zs, sm_slab, p);
+  phase_precond<R>(A, 0, X, V, VT, out, nullptr, ss, mbar, slab, slab_cap, zs, sm_slab, p);
 }
 
 __global__ void __launch_bounds__(kThreads) k_manifold_op(int op, int r, int n, const double *Ain, const double *Bin,
@@ -268,6 +268,7 @@ template <int R, int M>
 cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream);
 template <int R>
 static cudaError_t launch_run_m(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
+  if (T.p.method == 1 && args.parallel) return launch_run_t<R, 2>(T, args, grid, stream);
   return T.p.method == 1 ? launch_run_t<R, 1>(T, args, grid, stream) : launch_run_t<R, 0>(T, args, grid, stream);
 }
 

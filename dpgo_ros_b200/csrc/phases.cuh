@@ -469,7 +469,9 @@ struct DensePassCols {
 
 // acc over one pass of <= DensePassCols/4 poses whose columns start at `cols`
 // (shared memory or global, column stride ld); result to zs[pose][c][8].
-template <int R>
+// STREAM: evict-first loads for columns streamed from global memory (measured slower than plain loads on the
+// config-5 agent -- 3.3 vs 3.7 TB/s -- so nobody instantiates it with true)
+template <int R, bool STREAM = false>
 __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const double *VT, int r, int n4, int npass,
                                            double *zs, double *red /* [8 warps][16 cols][8] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -497,7 +499,7 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
       if (q < n4) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const double pv = (c < ncols) ? cols[(size_t)c * ld + q] : 0.0;
+          const double pv = (c < ncols) ? (STREAM ? __ldcs(cols + (size_t)c * ld + q) : cols[(size_t)c * ld + q]) : 0.0;
 #pragma unroll
           for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[i][a], pv, acc[a][c]);
         }
@@ -583,7 +585,11 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
   const size_t ldp = agent_ldp(A);
   const int pps = slab_poses(A, np, slab_cap_bytes);
   if (pps <= 0) {
-    // slab larger than shared memory: stream the columns from global memory
+    // slab larger than shared memory (BASELINE config 5: n = 12 500 poses, 136 MB of columns per CTA): stream the
+    // columns from global memory, 36 independent loads per thread in flight.  This is the HBM-bound regime --
+    // Pinv is read exactly once per application.  (Two shared-memory ring variants, fed by per-column TMA bulk
+    // copies and by 16-byte cp.async, measured 1.6 and 2.3 TB/s against 3.7 TB/s for this loop: the ring's
+    // per-tile barriers cost more than the registers it frees.)
     constexpr int NPP = DensePassCols<R>::value / 4;
     for (int sub = 0; sub < np; sub += NPP)
       dense_pass<R>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(NPP, np - sub), zs + sub * 32, red);

@@ -364,7 +364,7 @@ __device__ __forceinline__ void defer_total5(const TeamDev &T, int ai, double (&
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-// M: local solver, fixed at compile time (0 RTR, 1 RGD) so that the RGD kernel -- the bench workload and the
+// M: local solver / schedule, fixed at compile time (0 RTR, 1 RGD, 2 RGD under the parallel schedule) so that the RGD kernel -- the bench workload and the
 // stand-alone iterate() path -- does not carry the RTR-tCG code (instruction-cache footprint on a cold launch,
 // register pressure)
 template <int R, int M>
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __shared__ double sm_rel[kMaxLocal];
   __shared__ unsigned long long sm_mask;
   __shared__ ChunkTable chunks;
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[1];
   SmemLayout L;
   L.slab = reinterpret_cast<double *>(dyn_smem_raw);
   L.slab_cap = args.slab_cap;
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const GridSync &gs = T.gs;
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) g_dbg = T.prof ? T.prof + 4096 : nullptr;
-    mbar_init(&mbar);
+    mbar_init(&mbar[0]);
     chunks.prefix[0] = 0;
     for (int i = 0; i < T.num_local; ++i) {
       cta_pose_chunk(T.ag[i].n, chunks.p0[i], chunks.np[i]);
@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int N = T.num_robots;
   const bool accel = P.acceleration != 0;
   const bool use_slab = (M == 0) || P.rgd_use_precond;
+  if (M == 2 && !args.parallel) return;  // (never launched that way)
   const bool schedule = args.force_selected < -1;
   if (args.pull_mask) {
     // updateNeighborPoses staged the neighbours' poses in pinned host memory: fetch them with 16-byte loads
@@ -432,8 +433,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   for (int step = 0; step < args.max_iters; ++step) {
     const int iter = (args.mode == 2) ? c.iter : c.iter + 1;
     PROF(0)
-    if constexpr (M == 1) {
-      if (args.parallel) {
+    if constexpr (M == 2) {
+      {
         // ---- asynchronous mode as its equal-rate / unit-delay schedule (oracle: Team::runParallel; wrapper:
         // runOnceAsynchronous, src/PGOAgentROS.cpp:119-127): every robot takes an RGD step against the neighbour
         // poses of the previous tick.  One agent per GPU makes the ticks of all robots truly concurrent.
@@ -451,9 +452,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int ai = 0; ai < T.num_local; ++ai) {
           const AgentDev &A = T.ag[ai];
-          if (use_slab) slab_prefetch(A, ai, ss, &mbar, L.slab, L.slab_cap);
+          if (use_slab) slab_prefetch(A, ai, ss, mbar, L.slab, L.slab_cap);
           double prel = 0;
-          phase_rgd_step<R>(A, ai, P, A.X, false, false, 0.0, ss, &mbar, L.slab, L.slab_cap, L.zs, sm_slab, A.X2, prel);
+          phase_rgd_step<R>(A, ai, P, A.X, false, false, 0.0, ss, mbar, L.slab, L.slab_cap, L.zs, sm_slab, A.X2,
+                                 prel);
           defer_store(T, ai, 4, prel);
           __syncthreads();  // the slab buffer and zs are reused by the next agent
         }
@@ -517,8 +519,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool use_aux = accel && !restart;
       const double *Xs = use_aux ? A.Y : A.X;
       const double *inbox = use_aux ? A.inbox_aux : A.inbox_reg;
-      if (use_slab) slab_prefetch(A, sel_local, ss, &mbar, L.slab, L.slab_cap);  // no-op when already in flight
-      if constexpr (M == 1) {
+      if (use_slab) slab_prefetch(A, sel_local, ss, mbar, L.slab, L.slab_cap);  // no-op when already in flight
+      if constexpr (M == 2) {
+        // parallel schedule: handled at the top of the loop
+      } else if constexpr (M == 1) {
         // ---- RGD (a2): gradient (+ the previous step's deferred statistics), preconditioned step
         // the two gradient passes are independent: warps 0-3 take the step's gradient, warps 4-7 the
         // deferred statistics of the previous step (both fit: <= 4 groups of 16 per CTA are busy)
@@ -545,13 +549,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         PROF(4)
         double prel = 0;
-        phase_rgd_step<R>(A, sel_local, P, Xs, accel, restart, gamma, ss, &mbar, L.slab, L.slab_cap, L.zs, sm_slab,
-                          A.X2, prel);
+        phase_rgd_step<R>(A, sel_local, P, Xs, accel, restart, gamma, ss, mbar, L.slab, L.slab_cap, L.zs,
+                               sm_slab, A.X2, prel);
         defer_store(T, sel_local, 4, prel);
         // the next agent's slab is fetched while the following phases run
         if (use_slab && schedule) {
           const int nxt = T.local_of_robot[(sel_robot + 1) % N];
-          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, &mbar, L.slab, L.slab_cap);
+          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, mbar, L.slab, L.slab_cap);
         }
         PROF(5)
         pend_ai = sel_local;
@@ -561,12 +565,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         PROF(6)
       } else {
         // ---- RTR (a2)
-        const RtrOut ro = rtr_solve<R>(A, sel_local, P, gs, bs, Xs, inbox, ss, &mbar, L, sm_slab, sm_red);
+        const RtrOut ro = rtr_solve<R>(A, sel_local, P, gs, bs, Xs, inbox, ss, mbar, L, sm_slab, sm_red);
         double v[1] = {0};
         phase_commit<R>(A, ro.x, accel, restart, gamma, v[0]);
         if (schedule) {
           const int nxt = T.local_of_robot[(sel_robot + 1) % N];
-          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, &mbar, L.slab, L.slab_cap);
+          if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, mbar, L.slab, L.slab_cap);
         }
         grid_reduce<1>(gs, bs, v, sm_red);
         const double relchange = sqrt(v[0] / A.n);
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           c.ready_mask &= ~(1ull << rid);
       }
   }
-  if (ss.pending) slab_wait(&mbar, ss.parity);  // do not exit with a bulk copy in flight
+  if (ss.pending) slab_wait(mbar, ss.parity);  // do not exit with a bulk copy in flight
   grid_barrier(gs, bs);  // every CTA's result-block writes (outboxes, stats) are ordered before the flag
   if (fab && !dead) {
     // leave together: on return every publication of every rank has landed in its destination inbox

@@ -76,3 +76,24 @@ def test_parallel_schedule_over_fabric(synth8, world):
     for rid, a in fab.all_agents().items():
         assert rel(a.getX(), ref[rid]) == 0.0, rid
     fab.close()
+
+
+def test_streaming_preconditioner_matches_oracle():
+    """Agents whose preconditioner slab does not fit shared memory (n = 2000 here, 12 500 in config 5) stream it
+    through the TMA ring (dense_stream): same (Q + lambda I)^-1 application as the oracle's sparse solve."""
+    pb = datasets.make_synthetic_problem(4000, 30000, 2, seed=1)
+    kw = dict(ASYNC)
+    oteam = orc.OracleTeam(pb, **kw)
+    team, agents = gpu.make_team(pb, **kw)
+    rng = np.random.default_rng(0)
+    for rid in range(2):
+        X = agents[rid].getX()
+        V = np.asfortranarray(rng.standard_normal(X.shape))
+        got = agents[rid].precond(X, V)
+        want = oteam.precond(rid, X, V)
+        assert rel(got, want) < 1e-8, rid
+    team.set_schedule(1)
+    team.run(6, stop_on_terminate=False)
+    oteam.run_parallel(6, threads=2)
+    for rid in range(2):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-8, rid
