@@ -222,3 +222,39 @@ def test_tunnels_counts():
     same = meas.r1 == meas.r2
     odo = same & (meas.p1 + 1 == meas.p2)
     assert int(odo.sum()) == 1247 and int((same & ~odo).sum()) == 96 and int((~same).sum()) == 3548
+
+
+def test_parallel_schedule_is_all_robots_from_the_previous_tick(small_problem):
+    """Team::runParallel (the asynchronous mode as its equal-rate / unit-delay schedule): one tick == every robot's
+    iterate(true) against the poses published in the previous tick, then everybody publishes."""
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=0, rel_change_tol=0.0)
+    a = orc.OracleTeam(small_problem, **kw)
+    b = orc.OracleTeam(small_problem, **kw)
+    for _ in range(5):
+        a.run_parallel(1, threads=2)
+        for rid in range(2):
+            b.iterate(rid, True)     # no exchange in between: both see the other's previous iterate
+        b.exchange_all()
+    for rid in range(2):
+        assert np.array_equal(a.get_x(rid), b.get_x(rid))
+    with pytest.raises(Exception):
+        orc.OracleTeam(small_problem, **dict(kw, acceleration=1)).run_parallel(1)
+
+
+def test_synthetic_lattice_problem_is_well_posed():
+    """BASELINE config 5 generator at a small size: edge count, partition, and the asapp RGD settings converge."""
+    from dpgo_ros_b200 import datasets
+    pb = datasets.make_synthetic_problem(1000, 8000, 4, seed=3)
+    assert len(pb.meas) == 8000 and sum(pb.n) == 1000
+    m = pb.meas
+    same = (m.r1 == m.r2)
+    odo = same & (m.p2 == m.p1 + 1)
+    assert odo.sum() == 1000 - 4          # one odometry edge per consecutive pair inside a robot
+    assert np.all(np.linalg.norm(m.t, axis=1) < 2.5)   # lattice neighbours: short lever arms
+    pb2 = datasets.make_synthetic_problem(1000, 8000, 4, seed=3)
+    assert np.array_equal(pb.meas.R, pb2.meas.R) and np.array_equal(pb.T_init[2], pb2.T_init[2])   # seeded
+    t = orc.OracleTeam(pb, r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=0,
+                       rel_change_tol=0.0)
+    c0 = t.global_cost()
+    t.run_parallel(30, threads=4)
+    assert t.global_cost() < 0.5 * c0
