@@ -81,7 +81,8 @@ SYMBOLS = [
     "dpgo_b200_team_fabric_init", "dpgo_b200_team_fabric_window", "dpgo_b200_team_fabric_import",
     "dpgo_b200_team_fabric_route", "dpgo_b200_team_fabric_run", "dpgo_b200_team_fabric_set_timeout",
     "dpgo_b200_team_fabric_close", "dpgo_b200_team_gnc_compute_weights", "dpgo_b200_team_gnc_finish_update",
-    "dpgo_b200_get_shared_loop_closures", "dpgo_b200_team_set_schedule",
+    "dpgo_b200_get_shared_loop_closures", "dpgo_b200_team_set_schedule", "dpgo_b200_get_opt_result_lazy",
+    "dpgo_b200_get_pose",
 ]
 
 
@@ -133,6 +134,8 @@ def lib():
     L.dpgo_b200_get_status.argtypes = [vp, C.POINTER(Status)]
     L.dpgo_b200_set_neighbor_status.argtypes = [vp, C.POINTER(Status)]
     L.dpgo_b200_get_x.argtypes = [vp, C.c_int, dp]
+    L.dpgo_b200_get_pose.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.dpgo_b200_get_opt_result_lazy.argtypes = [vp, C.POINTER(OptResult)]
     L.dpgo_b200_set_x.argtypes = [vp, dp]
     L.dpgo_b200_num_shared_poses.argtypes = [vp, C.c_int]
     L.dpgo_b200_get_shared_pose_dict.argtypes = [vp, C.c_int, C.c_int, ip, dp, C.c_int, ip]

@@ -148,6 +148,11 @@ int dpgo_b200_get_opt_result(dpgo_b200_agent_t h, dpgo_b200_opt_result *out) {
   *out = A(h)->opt;
   API_END
 }
+int dpgo_b200_get_opt_result_lazy(dpgo_b200_agent_t h, dpgo_b200_opt_result *out) {
+  API_BEGIN
+  *out = A(h)->opt;
+  API_END
+}
 int dpgo_b200_get_status(dpgo_b200_agent_t h, dpgo_b200_status *out) {
   API_BEGIN
   *out = A(h)->get_status();
@@ -183,6 +188,17 @@ int dpgo_b200_get_x(dpgo_b200_agent_t h, int which, double *out) {
   a->materialize_lookahead();
   const DevBuf<double> &b = which == 0 ? a->dX : (which == 1 ? a->dY : a->dV);
   cuda_check(cudaMemcpy(out, b.p, sizeof(double) * a->r * 4 * a->n, cudaMemcpyDeviceToHost), "D2H X");
+  API_END
+}
+int dpgo_b200_get_pose(dpgo_b200_agent_t h, int which, int index, double *out) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "getSharedPose: agent not initialized");
+  if (index < 0 || index >= a->n || which < 0 || which > 2) fail(DPGO_B200_ERR_INVALID, "getSharedPose: index out of range");
+  cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+  a->materialize_lookahead();
+  const DevBuf<double> &b = which == 0 ? a->dX : (which == 1 ? a->dY : a->dV);
+  cuda_check(cudaMemcpy(out, b.p + (size_t)index * 4 * a->r, sizeof(double) * 4 * a->r, cudaMemcpyDeviceToHost), "D2H pose");
   API_END
 }
 int dpgo_b200_set_x(dpgo_b200_agent_t h, const double *X) {

@@ -110,6 +110,9 @@ int dpgo_b200_initialize_in_global_frame(dpgo_b200_agent_t a, const double *T_wo
 /* ---- the hot call: iterate(bool), :160 (true) and :1185 (false) -------------- */
 int dpgo_b200_iterate(dpgo_b200_agent_t a, int do_optimization);
 int dpgo_b200_get_opt_result(dpgo_b200_agent_t a, dpgo_b200_opt_result *out);   /* :169-172 */
+/* same, but f_opt / gradnorm_opt of a stand-alone RGD iterate stay NaN when they have not been
+ * evaluated yet (they cost a second gradient pass; the wrapper only prints them when verbose) */
+int dpgo_b200_get_opt_result_lazy(dpgo_b200_agent_t a, dpgo_b200_opt_result *out);
 int dpgo_b200_get_status(dpgo_b200_agent_t a, dpgo_b200_status *out);           /* getStatus, :616 */
 int dpgo_b200_set_neighbor_status(dpgo_b200_agent_t a, const dpgo_b200_status *s);  /* :965 */
 int dpgo_b200_should_terminate(dpgo_b200_agent_t a);                            /* :208  (1/0, <0 error) */
@@ -118,6 +121,8 @@ int dpgo_b200_should_update_measurement_weights(dpgo_b200_agent_t a);           
 /* which: 0 X, 1 Y (auxiliary), 2 V -- getX of the north star; host buffer r x 4n */
 int dpgo_b200_get_x(dpgo_b200_agent_t a, int which, double *out);
 int dpgo_b200_set_x(dpgo_b200_agent_t a, const double *X);
+/* one pose (r x 4, column-major) of X / Y / V: getSharedPose, src/PGOAgentROS.cpp:424 */
+int dpgo_b200_get_pose(dpgo_b200_agent_t a, int which, int index, double *out);
 
 /* ---- public-pose exchange with HOST buffers (a9) ----------------------------
  * getSharedPoseDictWithNeighbor / getAuxSharedPoseDictWithNeighbor (:666-668)
