@@ -264,12 +264,30 @@ void count_launch() { ++g_launches; }
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - 11 * 1024;  // leave room for the static arrays
 
-template <int R, int M>
+template <int R, int M, bool BIG>
 cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream);
+// a team with an agent whose per-pose slab (4 columns of Pinv) exceeds the shared-memory budget takes the
+// streaming kernels
+static bool needs_streaming(const TeamDev &T, int grid) {
+  if (T.p.method != 1 || !T.p.rgd_use_precond) return false;
+  int max_n = 1;
+  for (int i = 0; i < T.num_local; ++i) max_n = std::max(max_n, T.ag[i].n);
+  // same budget as smem_plan (team_run.cuh): what is left for the slab after the staging tiles and zs
+  const size_t chunk = (size_t)std::max(1, (max_n + grid - 1) / grid);
+  const size_t fixed = (size_t)kGroupsPerCta * kStageStride * sizeof(double) + chunk * 32 * sizeof(double);
+  const size_t slab_cap = fixed + 16 * 1024 < kMaxDynSmem ? ((kMaxDynSmem - fixed) / 128) * 128 : 0;
+  for (int i = 0; i < T.num_local; ++i) {
+    const size_t ldp = ((size_t)4 * T.ag[i].n + 31) / 32 * 32;
+    if (4 * ldp * sizeof(double) > slab_cap) return true;  // not even one pose's columns fit
+  }
+  return false;
+}
 template <int R>
 static cudaError_t launch_run_m(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
-  if (T.p.method == 1 && args.parallel) return launch_run_t<R, 2>(T, args, grid, stream);
-  return T.p.method == 1 ? launch_run_t<R, 1>(T, args, grid, stream) : launch_run_t<R, 0>(T, args, grid, stream);
+  if (T.p.method != 1) return launch_run_t<R, 0, false>(T, args, grid, stream);
+  if (needs_streaming(T, grid))
+    return args.parallel ? launch_run_t<R, 2, true>(T, args, grid, stream) : launch_run_t<R, 1, true>(T, args, grid, stream);
+  return args.parallel ? launch_run_t<R, 2, false>(T, args, grid, stream) : launch_run_t<R, 1, false>(T, args, grid, stream);
 }
 
 cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {

@@ -469,8 +469,7 @@ struct DensePassCols {
 
 // acc over one pass of <= DensePassCols/4 poses whose columns start at `cols`
 // (shared memory or global, column stride ld); result to zs[pose][c][8].
-// STREAM: evict-first loads for columns streamed from global memory (measured slower than plain loads on the
-// config-5 agent -- 3.3 vs 3.7 TB/s -- so nobody instantiates it with true)
+// STREAM: `cols` is global memory read once (agents whose slab does not fit shared memory)
 template <int R, bool STREAM = false>
 __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const double *VT, int r, int n4, int npass,
                                            double *zs, double *red /* [8 warps][16 cols][8] */) {
@@ -493,15 +492,33 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
 #pragma unroll
       for (int a = 0; a < R; ++a) vr[i][a] = (a < r && q < n4) ? VT[(size_t)a * n4 + q] : 0.0;
     }
+    if constexpr (STREAM) {
+      // columns streamed from HBM: request the whole chunk (QC x NC independent loads per thread) before the first
+      // multiply -- the bytes in flight per SM are what bounds this pass
+      double pv[QC][NC];
 #pragma unroll
-    for (int i = 0; i < QC; ++i) {
-      const int q = q0 + kThreads * i;
-      if (q < n4) {
+      for (int i = 0; i < QC; ++i) {
+        const int q = q0 + kThreads * i;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const double pv = (c < ncols) ? (STREAM ? __ldcs(cols + (size_t)c * ld + q) : cols[(size_t)c * ld + q]) : 0.0;
+        for (int c = 0; c < NC; ++c) pv[i][c] = (q < n4 && c < ncols) ? cols[(size_t)c * ld + q] : 0.0;
+      }
 #pragma unroll
-          for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[i][a], pv, acc[a][c]);
+      for (int i = 0; i < QC; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[i][a], pv[i][c], acc[a][c]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < QC; ++i) {
+        const int q = q0 + kThreads * i;
+        if (q < n4) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const double pv = (c < ncols) ? cols[(size_t)c * ld + q] : 0.0;
+#pragma unroll
+            for (int a = 0; a < R; ++a) acc[a][c] = fma(vr[i][a], pv, acc[a][c]);
+          }
         }
       }
     }
@@ -577,7 +594,9 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
 }
 
 // Z slab of this CTA's chunk [p0, p0+np) into zs[pose_local][c][8].
-template <int R>
+// BIG: instantiated for teams with an agent whose slab does not fit shared memory; only those kernels carry the
+// register-hungry streaming pass (it costs the small-agent kernels 4 us per iteration in spills otherwise)
+template <int R, bool BIG = false>
 __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const double *VT, int p0, int np,
                                            SlabState &ss, uint64_t *mbar, double *slab, size_t slab_cap_bytes,
                                            double *zs, double *red) {
@@ -586,13 +605,15 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
   const int pps = slab_poses(A, np, slab_cap_bytes);
   if (pps <= 0) {
     // slab larger than shared memory (BASELINE config 5: n = 12 500 poses, 136 MB of columns per CTA): stream the
-    // columns from global memory, 36 independent loads per thread in flight.  This is the HBM-bound regime --
-    // Pinv is read exactly once per application.  (Two shared-memory ring variants, fed by per-column TMA bulk
-    // copies and by 16-byte cp.async, measured 1.6 and 2.3 TB/s against 3.7 TB/s for this loop: the ring's
-    // per-tile barriers cost more than the registers it frees.)
+    // columns from global memory.  This is the HBM-bound regime -- Pinv is read exactly once per application.
+    // With all 36 loads of a chunk requested before the first multiply (dense_pass<R, true>) the pass runs at
+    // 4.6 TB/s; left to the compiler's schedule it reached 3.3 - 3.7 TB/s (2.0 in the parallel-schedule kernel).
+    // (Two shared-memory ring variants, fed by per-column TMA bulk copies and by 16-byte cp.async, measured 1.6
+    // and 2.3 TB/s: the ring's per-tile barriers cost more than the registers it frees.)
     constexpr int NPP = DensePassCols<R>::value / 4;
     for (int sub = 0; sub < np; sub += NPP)
-      dense_pass<R>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(NPP, np - sub), zs + sub * 32, red);
+      dense_pass<R, BIG>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(NPP, np - sub), zs + sub * 32,
+                         red);
     __syncthreads();
     return;
   }
@@ -686,7 +707,7 @@ __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid
 //   X+ = Retr_Xs( -eta * Proj_Xs( P^-1 rgrad ) ), fused with finish_pose.
 // With the preconditioner the CTA first computes its dense slab.
 // ---------------------------------------------------------------------------
-template <int R>
+template <int R, bool BIG = false>
 __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const SolverParams &P, const double *Xs,
                                                bool accel, bool restart, double gamma, SlabState &ss,
                                                uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
@@ -706,7 +727,7 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
     }
     DBG(20);
     // poses of this CTA's chunk are processed by group k (same ownership as phase_nesterov_chunk)
-    dense_slab<R>(A, ai, A.RgT, p0, np, ss, mbar, slab, slab_cap, zs, red);
+    dense_slab<R, BIG>(A, ai, A.RgT, p0, np, ss, mbar, slab, slab_cap, zs, red);
     DBG(19);
     for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
       const int k = k0 + lg;

@@ -367,7 +367,8 @@ __device__ __forceinline__ void defer_total5(const TeamDev &T, int ai, double (&
 // M: local solver / schedule, fixed at compile time (0 RTR, 1 RGD, 2 RGD under the parallel schedule) so that the RGD kernel -- the bench workload and the
 // stand-alone iterate() path -- does not carry the RTR-tCG code (instruction-cache footprint on a cold launch,
 // register pressure)
-template <int R, int M>
+// BIG: some agent's preconditioner slab does not fit shared memory (streaming dense pass; RGD kernels only)
+template <int R, int M, bool BIG = false>
 __global__ void __launch_bounds__(kThreads, 1)
     k_team_run(const __grid_constant__ TeamDev T, const __grid_constant__ RunArgs args) {
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const AgentDev &A = T.ag[ai];
           if (use_slab) slab_prefetch(A, ai, ss, mbar, L.slab, L.slab_cap);
           double prel = 0;
-          phase_rgd_step<R>(A, ai, P, A.X, false, false, 0.0, ss, mbar, L.slab, L.slab_cap, L.zs, sm_slab, A.X2,
+          phase_rgd_step<R, BIG>(A, ai, P, A.X, false, false, 0.0, ss, mbar, L.slab, L.slab_cap, L.zs, sm_slab, A.X2,
                                  prel);
           defer_store(T, ai, 4, prel);
           __syncthreads();  // the slab buffer and zs are reused by the next agent
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         PROF(4)
         double prel = 0;
-        phase_rgd_step<R>(A, sel_local, P, Xs, accel, restart, gamma, ss, mbar, L.slab, L.slab_cap, L.zs,
+        phase_rgd_step<R, BIG>(A, sel_local, P, Xs, accel, restart, gamma, ss, mbar, L.slab, L.slab_cap, L.zs,
                                sm_slab, A.X2, prel);
         defer_store(T, sel_local, 4, prel);
         // the next agent's slab is fetched while the following phases run
@@ -747,7 +748,7 @@ static void smem_plan(int max_n, int grid, bool want_slab, size_t &slab_cap, siz
   total = slab_cap + fixed;
 }
 
-template <int R, int M>
+template <int R, int M, bool BIG>
 cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream) {
   int max_n = 1;
   for (int i = 0; i < T.num_local; ++i) max_n = std::max(max_n, T.ag[i].n);
@@ -760,13 +761,13 @@ cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t 
   cudaGetDevice(&dev);
   dev &= 63;
   if (smem > configured[dev].load()) {
-    cudaError_t err = cudaFuncSetAttribute(k_team_run<R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(k_team_run<R, M, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     configured[dev].store(smem);
   }
   void *params[] = {(void *)&T, (void *)&args};
   count_launch();
-  return cudaLaunchCooperativeKernel((void *)k_team_run<R, M>, dim3(grid), dim3(kThreads), params, smem, stream);
+  return cudaLaunchCooperativeKernel((void *)k_team_run<R, M, BIG>, dim3(grid), dim3(kThreads), params, smem, stream);
 }
 
 }  // namespace dpgo

@@ -3,5 +3,5 @@
 #include "team_run.cuh"
 
 namespace dpgo {
-template cudaError_t launch_run_t<6, 2>(const TeamDev &, RunArgs, int, cudaStream_t);
+template cudaError_t launch_run_t<6, 2, false>(const TeamDev &, RunArgs, int, cudaStream_t);
 }  // namespace dpgo

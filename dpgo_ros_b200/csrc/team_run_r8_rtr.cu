@@ -2,5 +2,5 @@
 #include "team_run.cuh"
 
 namespace dpgo {
-template cudaError_t launch_run_t<8, 0>(const TeamDev &, RunArgs, int, cudaStream_t);
+template cudaError_t launch_run_t<8, 0, false>(const TeamDev &, RunArgs, int, cudaStream_t);
 }  // namespace dpgo
