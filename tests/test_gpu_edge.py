@@ -1,0 +1,89 @@
+"""Edge cases of the hot path through the C ABI: every supported relaxation rank, a robot without neighbours,
+ragged teams (robots of very different sizes, one with a single shared edge), unsupported configurations."""
+import numpy as np
+import pytest
+
+from dpgo_ros_b200 import agent as gpu
+from dpgo_ros_b200 import datasets
+from dpgo_ros_b200.capi import DpgoError
+from oracle import binding as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("r", [3, 4, 6, 7, 8])
+@pytest.mark.parametrize("method", [0, 1])
+def test_every_relaxation_rank(r, method):
+    """r = 3 ... 8 each has its own kernel instantiation (RGD and RTR); r = 5 is covered everywhere else."""
+    pb = datasets.load_g2o_problem("tinyGrid3D", 2) if r == 3 else datasets.make_synthetic_problem(240, 1200, 3, seed=r)
+    kw = (dict(method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=9)
+          if method == 1 else dict(method=0, gradnorm_tol=1e-3, acceleration=0))
+    kw.update(r=r, rel_change_tol=0.0, max_num_iters=10 ** 6)
+    oteam = orc.OracleTeam(pb, **kw)
+    team, agents = gpu.make_team(pb, **kw)
+    iters = 12 if method == 1 else 6
+    res = team.run(iters, stop_on_terminate=False)
+    oteam.run(iters, stop_on_terminate=False)
+    assert res.iterations == iters
+    for rid in range(pb.num_robots):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < (1e-9 if method == 1 else 1e-6), (r, rid)
+
+
+def test_single_robot_has_no_exchange():
+    """One robot owns the whole graph: no neighbours, no inbox, no publication lists."""
+    pb = datasets.load_g2o_problem("smallGrid3D", 1)
+    kw = dict(r=5, method=0, gradnorm_tol=1e-2, acceleration=0, rel_change_tol=1e-3, max_num_iters=200)
+    oteam = orc.OracleTeam(pb, **kw)
+    team, agents = gpu.make_team(pb, **kw)
+    assert agents[0].getNeighbors() == []
+    res = team.run(200, stop_on_terminate=True)
+    ores = oteam.run(200, stop_on_terminate=True)
+    assert res.iterations == ores.iterations and res.terminated
+    assert abs(team.global_cost() - oteam.global_cost()) < 1e-6 * oteam.global_cost()
+    assert abs(team.global_cost() - 1025.398) < 1e-2        # SE-Sync's optimum for smallGrid3D
+
+
+def test_ragged_team():
+    """Robots of 9 ... 600 poses in one team (the chunk tables, slab sizes and grids differ per robot)."""
+    pb = datasets.make_synthetic_problem(1000, 6000, 5, seed=11)
+    # re-partition unevenly: robot sizes 9, 41, 150, 200, 600
+    meas = pb.meas
+    start = np.array([0, 9, 50, 200, 400, 1000])
+    gid = np.concatenate([[0], np.cumsum(pb.n)])
+    g1 = gid[meas.r1] + meas.p1
+    g2 = gid[meas.r2] + meas.p2
+    rob = lambda g: np.searchsorted(start, g, side="right") - 1
+    m2 = meas.take(np.arange(len(meas)))
+    m2.r1, m2.r2 = rob(g1).astype(np.int32), rob(g2).astype(np.int32)
+    m2.p1, m2.p2 = (g1 - start[m2.r1]).astype(np.int32), (g2 - start[m2.r2]).astype(np.int32)
+    m2.fixed = ((m2.r1 == m2.r2) & (m2.p1 + 1 == m2.p2)).astype(np.uint8)
+    Tall = np.concatenate(pb.T_init)
+    pb2 = datasets.Problem(name="ragged", num_robots=5, meas=m2, n=[int(start[i + 1] - start[i]) for i in range(5)],
+                           T_init=[Tall[start[i]:start[i + 1]] for i in range(5)])
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=20,
+              rel_change_tol=0.0, max_num_iters=10 ** 6)
+    oteam = orc.OracleTeam(pb2, **kw)
+    team, agents = gpu.make_team(pb2, **kw)
+    team.run(35, stop_on_terminate=False)
+    oteam.run(35, stop_on_terminate=False)
+    for rid in range(5):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-9, rid
+    assert team.global_cost() < 0.6 * orc.OracleTeam(pb2, **kw).global_cost()
+
+
+def test_unsupported_configurations_are_refused():
+    pb = datasets.load_g2o_problem("tinyGrid3D", 2)
+    for bad in (dict(r=9), dict(r=2), dict(cost_type=2), dict(d=2)):
+        with pytest.raises(DpgoError):
+            gpu.make_team(pb, **dict(dict(r=5), **bad))
+    # a team must hold one problem: same r, same robot count
+    _, a5 = gpu.make_team(pb, colocate=False, r=5)
+    _, a6 = gpu.make_team(pb, colocate=False, r=6)
+    team = gpu.Team(0)
+    team.add(a5[0])
+    with pytest.raises(DpgoError):
+        team.add(a6[1])
