@@ -55,6 +55,47 @@ def async_cpu_reference(ticks=300, threads=None):
     return res.iterations / res.wall_seconds
 
 
+def hbm_regime_single_rank(device, iters=6):
+    """Secondary figure: one rank of BASELINE config 5 at the named size (synthetic 100k poses / 1M edges / 8 agents,
+    robot 0: 12 500 poses) -- one iterate(true) streams the 20 GB dense preconditioner once, the regime in which the
+    HBM roofline is the physical bound.  Same measurement as tools/bench_config5.py."""
+    import time as _t
+    from dpgo_ros_b200 import agent as gpu, datasets
+    pb = datasets.make_synthetic_problem(100000, 1000000, 8, seed=0)
+    P = gpu.make_params(num_robots=8, **ASYNC_CONFIG)
+    yl = datasets.fixed_lifting_matrix(P.r)
+    eye = np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1)
+    ag = gpu.PGOAgent(0, P, device)
+    m = pb.robot_measurements(0)
+    ag.addMeasurements(m)
+    ag.setLiftingMatrix(yl)
+    ag.initialize(pb.T_init[0])
+    ag.initializeInGlobalFrame(eye)
+    need = {}
+    for e in np.nonzero(m.r1 != m.r2)[0]:
+        o, f = (int(m.r2[e]), int(m.p2[e])) if int(m.r1[e]) == 0 else (int(m.r1[e]), int(m.p1[e]))
+        need.setdefault(o, set()).add(f)
+    for o, frames in need.items():
+        fr = np.array(sorted(frames), dtype=np.int32)
+        ag.updateNeighborPoses(o, fr, np.ascontiguousarray(np.einsum("ak,nkc->nca", yl, pb.T_init[o][fr])), False)
+    ag.iterate(True)   # builds Q and the 50 016^2 dense inverse
+    ts = []
+    for _ in range(iters):
+        t0 = _t.perf_counter()
+        ag.iterate(True)
+        ts.append(_t.perf_counter() - t0)
+    ag.close()
+    n = pb.n[0]
+    npad = (4 * n + 31) // 32 * 32
+    nbytes = npad * npad * 8 + 2 * n * P.r * 4 * 8 + len(m) * 128 + 2 * n * P.r * 4 * 8
+    ms = float(np.median(ts)) * 1e3
+    peak, _ = load_peaks()
+    return {"workload": "config 5 at the named size, one of its 8 ranks: robot 0 of the synthetic 100k-pose / 1M-edge graph "
+                        f"(n={n}, {len(m)} edges), RGD 0.2 + dense preconditioner, per-robot C ABI iterate(true)",
+            "ms_per_iterate": ms, "algorithmic_bytes": nbytes, "achieved_GBps": nbytes / (ms * 1e-3) / 1e9,
+            "peak_GBps": peak, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+
+
 def async_mode_single_gpu(pb, device, ticks=2000):
     """Secondary figure: the asynchronous mode (all 8 robots step every tick) on one GPU."""
     from dpgo_ros_b200 import agent as gpu
@@ -278,6 +319,10 @@ def main():
     cpu = cpu_reference(args.cpu_steps, 50)
     async_mode = async_mode_single_gpu(pb, local_rank)
     async_mode["cpu_ticks_per_s"] = async_cpu_reference()
+    try:
+        hbm_regime = hbm_regime_single_rank(local_rank)
+    except Exception as e:  # noqa: BLE001  (secondary figure: never fail the bench line over it)
+        hbm_regime = {"error": str(e)[:200]}
     line = {
         "metric": "rbcd_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -303,6 +348,7 @@ def main():
                          "sample": f"{cpu['steps']} steps of the same workload on the oracle, one OS thread per "
                                    f"agent ({cpu['threads']} threads, {cpu['cores']} host cores)"},
         "async_mode": async_mode,
+        "hbm_bound_regime": hbm_regime,
     }
     print(json.dumps(line))
     return 0
