@@ -82,7 +82,7 @@ SYMBOLS = [
     "dpgo_b200_team_fabric_route", "dpgo_b200_team_fabric_run", "dpgo_b200_team_fabric_set_timeout",
     "dpgo_b200_team_fabric_close", "dpgo_b200_team_gnc_compute_weights", "dpgo_b200_team_gnc_finish_update",
     "dpgo_b200_get_shared_loop_closures", "dpgo_b200_team_set_schedule", "dpgo_b200_get_opt_result_lazy",
-    "dpgo_b200_get_pose",
+    "dpgo_b200_get_pose", "dpgo_b200_sync_driver_shm_bytes", "dpgo_b200_sync_driver_run_shm",
 ]
 
 
@@ -174,6 +174,10 @@ def lib():
     L.dpgo_b200_team_fabric_close.argtypes = [vp]
     L.dpgo_b200_team_gnc_compute_weights.argtypes = [vp]
     L.dpgo_b200_team_gnc_finish_update.argtypes = [vp]
+    L.dpgo_b200_sync_driver_shm_bytes.restype = C.c_size_t
+    L.dpgo_b200_sync_driver_shm_bytes.argtypes = [C.c_int, C.c_int]
+    L.dpgo_b200_sync_driver_run_shm.argtypes = [C.POINTER(vp), ip, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, dp, ip]
     L.dpgo_b200_sync_driver_run.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, dp, C.POINTER(C.c_longlong), ip]
     _LIB = L
     return L

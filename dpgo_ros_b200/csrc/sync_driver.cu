@@ -43,6 +43,164 @@ struct Msg {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// The same replay with the robots spread over several PROCESSES of one node (one per GPU): the mailboxes, the
+// barrier and the status board live in a POSIX shared-memory segment, standing in for the TCPROS transport between
+// the per-robot processes of the reference deployment (launch/dpgo_demo.launch:21-123).  Every process calls
+// dpgo_b200_sync_driver_run_shm with its own robots; the protocol (and the arithmetic) is the one above.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kShmMaxRobots = 64;
+constexpr int kShmPoseDoubles = 4 * 8;  // r <= 8
+
+struct ShmHeader {
+  std::atomic<int> count;
+  std::atomic<unsigned> gen;
+  std::atomic<int> err, term;
+  int cap;  // poses per mailbox
+  dpgo_b200_status status[kShmMaxRobots];
+};
+struct ShmView {
+  ShmHeader *h;
+  unsigned char *boxes;
+  size_t box_bytes;
+  int N;
+  // mailbox a -> b: [int count | int frames[cap] | double reg[cap * 32] | double aux[cap * 32]]
+  unsigned char *box(int a, int b) const { return boxes + ((size_t)a * N + b) * box_bytes; }
+  int *count(int a, int b) const { return reinterpret_cast<int *>(box(a, b)); }
+  int *frames(int a, int b) const { return reinterpret_cast<int *>(box(a, b)) + 2; }
+  double *reg(int a, int b) const { return reinterpret_cast<double *>(box(a, b) + 8 + ((size_t)h->cap * 4 + 7) / 8 * 8); }
+  double *aux(int a, int b) const { return reg(a, b) + (size_t)h->cap * kShmPoseDoubles; }
+};
+size_t shm_box_bytes(int cap) { return 8 + ((size_t)cap * 4 + 7) / 8 * 8 + (size_t)2 * cap * kShmPoseDoubles * sizeof(double); }
+
+void shm_barrier(ShmHeader *h, int n) {
+  const unsigned g = h->gen.load(std::memory_order_acquire);
+  if (h->count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+    h->count.store(0, std::memory_order_relaxed);
+    h->gen.fetch_add(1, std::memory_order_release);
+  } else {
+    while (h->gen.load(std::memory_order_acquire) == g) {
+    }
+  }
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" size_t dpgo_b200_sync_driver_shm_bytes(int num_robots, int max_shared_poses) {
+  return sizeof(ShmHeader) + (size_t)num_robots * num_robots * shm_box_bytes(max_shared_poses);
+}
+
+extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const int *robot_ids, int num_local,
+                                             int num_robots, void *shm, int max_shared_poses, int steps,
+                                             int accelerated, int start_iter, double *seconds, int *terminated_at) {
+  if (!agents || !robot_ids || !shm || num_local < 1 || num_robots < num_local || num_robots > kShmMaxRobots || steps < 0)
+    return DPGO_B200_ERR_INVALID;
+  const int N = num_robots;
+  ShmView V;
+  V.h = static_cast<ShmHeader *>(shm);
+  V.boxes = static_cast<unsigned char *>(shm) + sizeof(ShmHeader);
+  V.box_bytes = shm_box_bytes(max_shared_poses);
+  V.N = N;
+  V.h->cap = max_shared_poses;  // (every rank writes the same value)
+  std::vector<std::vector<int>> nbrs(num_local);
+  for (int i = 0; i < num_local; ++i) {
+    const int k = dpgo_b200_num_neighbors(agents[i]);
+    nbrs[i].resize(k > 0 ? k : 0);
+    if (k > 0 && dpgo_b200_get_neighbors(agents[i], nbrs[i].data(), k) != 0) return DPGO_B200_ERR_INVALID;
+    for (int b : nbrs[i])
+      if (dpgo_b200_num_shared_poses(agents[i], b) > max_shared_poses) return DPGO_B200_ERR_INVALID;
+  }
+  ShmHeader *H = V.h;
+  auto fail = [&](int rc) { H->err.store(rc); };
+  auto pack = [&](int i) {  // publishPublicPoses of local robot i
+    const int a = robot_ids[i];
+    for (int b : nbrs[i]) {
+      int cnt = 0;
+      int rc = dpgo_b200_get_shared_pose_dict(agents[i], b, 0, V.frames(a, b), V.reg(a, b), max_shared_poses, &cnt);
+      if (rc) fail(rc);
+      *V.count(a, b) = cnt;
+      if (accelerated) {
+        rc = dpgo_b200_get_shared_pose_dict(agents[i], b, 1, V.frames(a, b), V.aux(a, b), max_shared_poses, &cnt);
+        if (rc) fail(rc);
+      }
+    }
+  };
+  auto deliver = [&](int i, int sel, bool except) {  // publicPosesCallback of local robot i
+    const int b = robot_ids[i];
+    for (int a : nbrs[i]) {
+      if (except ? (a == sel) : (a != sel)) continue;
+      const int cnt = *V.count(a, b);
+      int rc = dpgo_b200_update_neighbor_poses(agents[i], a, 0, V.frames(a, b), V.reg(a, b), cnt);
+      if (rc) fail(rc);
+      if (accelerated) {
+        rc = dpgo_b200_update_neighbor_poses(agents[i], a, 1, V.frames(a, b), V.aux(a, b), cnt);
+        if (rc) fail(rc);
+      }
+    }
+  };
+  int my_term = -1;
+  if (steps == 0) {
+    // INITIALIZE (:1099-1101): everybody publishes once, everybody hears everybody
+    std::vector<std::thread> th0;
+    auto once = [&](int i) {
+      pack(i);
+      shm_barrier(H, N);
+      deliver(i, -1, /*except=*/true);
+      shm_barrier(H, N);
+    };
+    for (int i = 1; i < num_local; ++i) th0.emplace_back(once, i);
+    once(0);
+    for (auto &t : th0) t.join();
+    if (seconds) *seconds = 0;
+    if (terminated_at) *terminated_at = -1;
+    return H->err.load();
+  }
+  auto worker = [&](int i) {
+    const int a = robot_ids[i];
+    for (int s = 0; s < steps; ++s) {
+      const int sel = (start_iter + s) % N;
+      if (accelerated) {
+        if (a != sel) {
+          if (dpgo_b200_iterate(agents[i], 0)) fail(-1);
+          pack(i);
+        }
+        shm_barrier(H, N);
+        deliver(i, sel, /*except=*/true);
+        shm_barrier(H, N);
+      } else if (a != sel) {
+        if (dpgo_b200_iterate(agents[i], 0)) fail(-1);
+      }
+      if (a == sel) {
+        if (dpgo_b200_iterate(agents[i], 1)) fail(-1);
+        pack(i);
+      }
+      dpgo_b200_get_status(agents[i], &H->status[a]);  // publishStatus
+      shm_barrier(H, N);
+      deliver(i, sel, /*except=*/false);
+      if (a == 0) {
+        for (int b = 1; b < N; ++b) dpgo_b200_set_neighbor_status(agents[i], &H->status[b]);
+        if (sel == 0 && H->term.load() < 0 && dpgo_b200_should_terminate(agents[i]) == 1) H->term.store(s + 1);
+      }
+      shm_barrier(H, N);
+      if (H->err.load()) return;
+    }
+  };
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  std::vector<std::thread> th;
+  for (int i = 1; i < num_local; ++i) th.emplace_back(worker, i);
+  worker(0);
+  for (auto &t : th) t.join();
+  const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  my_term = H->term.load();
+  if (seconds) *seconds = dt;
+  if (terminated_at) *terminated_at = my_term;
+  return H->err.load();
+}
+#pragma GCC visibility pop
+
 #pragma GCC visibility push(default)
 extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int steps, int accelerated,
                                          double *seconds, long long *payload_bytes, int *terminated_at) {

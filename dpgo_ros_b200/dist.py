@@ -486,6 +486,83 @@ class HostRankTeam:
             a.close()
 
 
+class ShmHostTeam:
+    """The e2e arm at N GPUs, native: the robots of this rank are STAND-ALONE agents driven through the per-robot C ABI
+    with HOST buffers by dpgo_b200_sync_driver_run_shm (one OS thread per robot, wrapper call order); the public poses
+    of robots in other processes travel through a POSIX shared-memory segment -- the one-process-per-robot deployment
+    of the reference (launch/dpgo_demo.launch:21-123) with TCPROS swapped for shared memory."""
+
+    def __init__(self, problem, rank: int, world: int, device: int, tag: str, **params):
+        import ctypes as C
+        import struct
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        from . import agent as gpu
+        from . import capi
+        self.C, self.L = C, capi.lib()
+        self.rank, self.world, self.N = rank, world, problem.num_robots
+        params = dict(params)
+        self.accel = bool(params.get("acceleration", 0))
+        self.local = robots_of_rank(self.N, world, rank)
+        _, allagents = gpu.make_team(problem, device=device, colocate=False, **params)
+        self.agents = [a for a in allagents if a.id in self.local]
+        for a in allagents:
+            if a.id not in self.local:
+                a.close()
+        mine = max([self.L.dpgo_b200_num_shared_poses(a.h, nb) for a in self.agents for nb in a.getNeighbors()] + [1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        self.cap = int(max(gathered))
+        nbytes = int(self.L.dpgo_b200_sync_driver_shm_bytes(self.N, self.cap))
+        name = f"dpgo_b200_{tag}"
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+            self.shm.buf[:nbytes] = bytes(nbytes)
+            struct.pack_into("i", self.shm.buf, 12, -1)   # ShmHeader::term
+        dist.barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name, create=False)
+            try:  # only the creator unlinks; keep this process's resource tracker from trying (and warning) at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
+        self._keep = C.c_char.from_buffer(self.shm.buf)
+        self.ptr = C.addressof(self._keep)
+        self.iter = 0
+        self.run(0)   # initial publication of every robot
+
+    def run(self, steps: int):
+        """`steps` global iterations (0: the INITIALIZE exchange).  Returns seconds of this rank's driver."""
+        C = self.C
+        arr = (C.c_void_p * len(self.agents))(*[a.h for a in self.agents])
+        ids = (C.c_int * len(self.agents))(*[a.id for a in self.agents])
+        sec, term = C.c_double(), C.c_int()
+        check_rc = self.L.dpgo_b200_sync_driver_run_shm(arr, ids, len(self.agents), self.N, C.c_void_p(self.ptr), self.cap,
+                                                        steps, int(self.accel), self.iter, C.byref(sec), C.byref(term))
+        if check_rc != 0:
+            raise RuntimeError(f"sync_driver_run_shm failed with {check_rc}")
+        self.iter += steps
+        return sec.value
+
+    def payload_bytes_per_step(self) -> int:
+        total = 0
+        for a in self.agents:
+            for nb in a.getNeighbors():
+                total += self.L.dpgo_b200_num_shared_poses(a.h, nb) * a.r * 4 * 8 * (2 if self.accel else 1)
+        return total
+
+    def close(self):
+        import torch.distributed as dist
+        for a in self.agents:
+            a.close()
+        del self._keep
+        dist.barrier()
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()
+
+
 def bench_multi_gpu(args, config: dict, workload: str) -> int:
     """`bench.py --gpus N` under torchrun: 8/N robots per GPU.  `value`: the fabric -- one persistent launch per
     rank runs all K steps, public poses stored into the neighbours' inboxes over NVLink; device time, max over
@@ -540,22 +617,20 @@ def bench_multi_gpu(args, config: dict, workload: str) -> int:
     dist.barrier()
     nccl_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / nccl_steps], device=dev, dtype=torch.float64)
     dist.all_reduce(nccl_ms, op=dist.ReduceOp.MAX)
-    # e2e: per-robot C ABI, host buffers, gloo between the processes
-    gloo = dist.new_group(backend="gloo")
-    e2e_steps = min(args.steps, 400)
-    ht = HostRankTeam(pb, rank, world, local_rank, gloo, **config)
-    for it in range(8):
-        ht.step(it)
-    dist.barrier(group=gloo)
-    ht.bytes = 0
-    t0 = time.perf_counter()
-    for it in range(8, 8 + e2e_steps):
-        ht.step(it)
-    dist.barrier(group=gloo)
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], device=dev, dtype=torch.float64)
+    # e2e: per-robot C ABI with host buffers, driven natively (one OS thread per robot); poses between the processes
+    # through shared memory
+    e2e_steps = min(args.steps, 2000)
+    ht = ShmHostTeam(pb, rank, world, local_rank, tag=str(os.environ.get("MASTER_PORT", "0")), **config)
+    ht.run(40)
+    dist.barrier()
+    e2e_sec = ht.run(e2e_steps)
+    e2e_ms = torch.tensor([e2e_sec * 1e3 / e2e_steps], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_bytes = torch.tensor([float(ht.bytes) / e2e_steps], device=dev, dtype=torch.float64)
+    e2e_bytes = torch.tensor([float(ht.payload_bytes_per_step())], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e_bytes)
+    Xh = {a.id: a.getX() for a in ht.agents}
+    gathered_h = [None] * world
+    dist.all_gather_object(gathered_h, Xh)
     ht.close()
     # secondary figure: the asynchronous mode over the fabric -- every robot steps every tick, so the GPUs work
     # concurrently (this is where more GPUs add throughput; the synchronous schedule above is serial by design)
@@ -603,8 +678,10 @@ def bench_multi_gpu(args, config: dict, workload: str) -> int:
             "nccl_p2p_ms_per_step": float(nccl_ms.item()),
             "clocks": clk.summary(),
             "e2e": {"value": 1e3 / float(e2e_ms.item()), "unit": "iters/s",
-                    "h2d_bytes_per_step": float(e2e_bytes.item()) / 2, "d2h_bytes_per_step": float(e2e_bytes.item()) / 2,
-                    "note": f"per-robot C ABI with host buffers, gloo between the {world} processes, {e2e_steps} steps"},
+                    "h2d_bytes_per_step": float(e2e_bytes.item()), "d2h_bytes_per_step": float(e2e_bytes.item()),
+                    "final_cost_2f": _global_cost(pb, {k: v for g in gathered_h for k, v in g.items()}, config["r"]),
+                    "note": f"per-robot C ABI (iterate / getSharedPoseDict / updateNeighborPoses) with host buffers, one "
+                            f"OS thread per robot, shared memory between the {world} processes, {e2e_steps} steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "kernel": "k_team_run<5> (persistent, one per GPU)", "algorithmic_bytes_per_step": step_bytes,

@@ -230,6 +230,16 @@ int dpgo_b200_team_gnc_finish_update(dpgo_b200_team_t t);
 int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int num_agents, int steps, int accelerated,
                               double *seconds, long long *payload_bytes, int *terminated_at);
 
+/* The same replay with the robots spread over several processes of one node (one per GPU).  `shm` points to a
+ * zero-initialised shared-memory segment of dpgo_b200_sync_driver_shm_bytes(num_robots, max_shared_poses) bytes
+ * mapped by every process (with term = -1 written by its creator, see dpgo_ros_b200/dist.py); it holds the
+ * mailboxes, the barrier and the status board that stand in for the TCPROS transport between the reference's
+ * per-robot processes.  Every process passes its own robots; all pass the same steps / start_iter.            */
+size_t dpgo_b200_sync_driver_shm_bytes(int num_robots, int max_shared_poses);
+int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const int *robot_ids, int num_local, int num_robots,
+                                  void *shm, int max_shared_poses, int steps, int accelerated, int start_iter,
+                                  double *seconds, int *terminated_at);
+
 #ifdef __cplusplus
 }
 #endif

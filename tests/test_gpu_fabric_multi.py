@@ -34,3 +34,15 @@ def test_fabric_across_processes_matches_single_team(mode):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"fabric {mode} ok" in out.stdout
+
+
+def test_per_robot_api_across_processes_through_shared_memory():
+    """The e2e arm at N > 1 (dist.ShmHostTeam): stand-alone agents in several processes, host buffers, shared-memory
+    mailboxes.  Two processes also work on a single GPU (no device-side waiting between them)."""
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "_fabric_worker.py"), "shm"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "fabric shm ok" in out.stdout
