@@ -12,6 +12,9 @@ src/PGOAgentROS.cpp:662-690, 1255-1284):
   time (`build_plan` / `exchange` / `GpuRankTeam.step`) -- the library baseline
   the fabric is measured against.
 
+`ShmHostTeam` is the host-buffer (e2e) arm across processes: stand-alone agents
+behind the per-robot C ABI, poses through a shared-memory segment.
+
 The wiring / plan logic is pure host code and transport-agnostic: tests drive it
 on CPU with the gloo backend and mock endpoints (tests/test_dist_cpu.py).
 """
@@ -401,89 +404,6 @@ class GpuRankTeam:
             self.team.step(sel, 1)
             self.team.step(sel, 2)
             self.exchange([sel])
-
-
-class HostRankTeam:
-    """The e2e arm at N GPUs: every robot is a STAND-ALONE agent driven through the per-robot C ABI with HOST
-    buffers (iterate / getSharedPoseDictWithNeighbor / updateNeighborPoses, src/PGOAgentROS.cpp:160,1185,
-    662-690,1255-1284); poses for robots of other ranks cross processes as host tensors over a gloo group --
-    the one-process-per-robot deployment of the reference with its TCPROS transport swapped for gloo."""
-
-    def __init__(self, problem, rank: int, world: int, device: int, group, **params):
-        import torch
-        from . import agent as gpu
-        self.torch, self.group = torch, group
-        self.rank, self.world, self.N = rank, world, problem.num_robots
-        params = dict(params)
-        params["num_robots"] = self.N
-        self.accel = bool(params.get("acceleration", 0))
-        self.local = robots_of_rank(self.N, world, rank)
-        _, allagents = gpu.make_team(problem, device=device, colocate=False, **{k: v for k, v in params.items()
-                                                                                if k != "num_robots"})
-        self.agents = {a.id: a for a in allagents if a.id in self.local}
-        for a in allagents:
-            if a.id not in self.local:
-                a.close()
-        self.neighbors = problem_neighbors(problem)
-        self.r = int(params.get("r", 5))
-        self.bytes = 0
-        self.publish(range(self.N))
-
-    def publish(self, senders) -> None:
-        """publishPublicPoses of `senders` -> publicPosesCallback of their neighbours."""
-        import torch.distributed as dist
-        torch = self.torch
-        senders = set(senders)
-        ops, pending = [], []
-        for a in range(self.N):
-            if a not in senders:
-                continue
-            ra = rank_of_robot(self.N, self.world, a)
-            for b in self.neighbors[a]:
-                rb = rank_of_robot(self.N, self.world, b)
-                for aux in ((False, True) if self.accel else (False,)):
-                    if ra == self.rank:
-                        fr, poses = self.agents[a].getSharedPoseDictWithNeighbor(b, aux)      # D2H
-                        self.bytes += poses.nbytes
-                        if rb == self.rank:
-                            self.agents[b].updateNeighborPoses(a, fr, poses, aux)              # H2D (staged)
-                            self.bytes += poses.nbytes
-                        else:
-                            # the message carries pose ids + poses like PublicPoses.msg (pose_ids, poses)
-                            msg = np.concatenate([poses.reshape(len(fr), -1), fr.astype(np.float64)[:, None]], axis=1)
-                            ops.append(dist.P2POp(dist.isend, torch.from_numpy(np.ascontiguousarray(msg)), rb,
-                                                  group=self.group))
-                    elif rb == self.rank:
-                        cnt = self.agents[b].inboxDevicePtr(a, aux)[1] // (4 * self.r * 8)
-                        buf = torch.empty((cnt, 4 * self.r + 1), dtype=torch.float64)
-                        ops.append(dist.P2POp(dist.irecv, buf, ra, group=self.group))
-                        pending.append((b, a, buf, aux))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        for b, a, buf, aux in pending:
-            msg = buf.numpy()
-            self.agents[b].updateNeighborPoses(a, msg[:, -1].astype(np.int32), np.ascontiguousarray(msg[:, :-1]), aux)
-            self.bytes += (msg.size - len(msg)) * 8
-
-    def step(self, it: int) -> None:
-        sel = it % self.N
-        if self.accel:
-            for rid, ag in self.agents.items():
-                if rid != sel:
-                    ag.iterate(False)
-            self.publish([r for r in range(self.N) if r != sel])
-        else:
-            for rid, ag in self.agents.items():
-                if rid != sel:
-                    ag.iterate(False)
-        if sel in self.agents:
-            self.agents[sel].iterate(True)
-        self.publish([sel])
-
-    def close(self):
-        for a in self.agents.values():
-            a.close()
 
 
 class ShmHostTeam:
