@@ -38,6 +38,15 @@ def test_shim_host_side(tmp_path):
     assert "shim host checks ok" in res.stdout
 
 
+def test_wire_formats_and_iteration_log(tmp_path):
+    """ROS-free mirror of msg/*.msg + src/utils.cpp codecs + the CSV log columns (include/dpgo_ros_wire/wire.h); the
+    checks repeat the reference's own unit test (tests/testUtils.cpp:16-70)."""
+    exe = _compile("wire_checks.cpp", str(tmp_path / "wire_checks"), link=False)
+    res = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "wire checks ok" in res.stdout
+
+
 def test_shim_harness_builds_and_refuses_to_run_without_gpu(harness, tmp_path):
     from dpgo_ros_b200 import capi
     if capi.lib().dpgo_b200_device_count() > 0:
