@@ -109,6 +109,16 @@ class PGOAgent:
     def iterate(self, doOptimization: bool = True) -> None:
         check(self.L.dpgo_b200_iterate(self.h, int(doOptimization)), "iterate")
 
+    def initializeChordal(self) -> np.ndarray:
+        """Chordal local initialisation on the device; returns the local trajectory [n, 3, 4]."""
+        check(self.L.dpgo_b200_initialize_chordal(self.h), "initializeChordal")
+        return self.localTrajectory()
+
+    def localTrajectory(self) -> np.ndarray:
+        out = np.zeros((self.num_poses(), 3, 4))
+        check(self.L.dpgo_b200_get_local_trajectory(self.h, _dp(out)), "localTrajectory")
+        return out
+
     def getX(self, which: int = 0) -> np.ndarray:
         out = np.zeros((self.r, 4 * self.num_poses()), order="F")
         check(self.L.dpgo_b200_get_x(self.h, which, _dp(out)), "getX")

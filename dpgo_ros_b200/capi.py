@@ -83,6 +83,7 @@ SYMBOLS = [
     "dpgo_b200_team_fabric_close", "dpgo_b200_team_gnc_compute_weights", "dpgo_b200_team_gnc_finish_update",
     "dpgo_b200_get_shared_loop_closures", "dpgo_b200_team_set_schedule", "dpgo_b200_get_opt_result_lazy",
     "dpgo_b200_get_pose", "dpgo_b200_sync_driver_shm_bytes", "dpgo_b200_sync_driver_run_shm",
+    "dpgo_b200_initialize_chordal", "dpgo_b200_get_local_trajectory",
 ]
 
 
@@ -129,6 +130,8 @@ def lib():
     L.dpgo_b200_get_lifting_matrix.argtypes = [vp, dp]
     L.dpgo_b200_initialize.argtypes = [vp, dp]
     L.dpgo_b200_initialize_in_global_frame.argtypes = [vp, dp]
+    L.dpgo_b200_initialize_chordal.argtypes = [vp]
+    L.dpgo_b200_get_local_trajectory.argtypes = [vp, dp]
     L.dpgo_b200_iterate.argtypes = [vp, C.c_int]
     L.dpgo_b200_get_opt_result.argtypes = [vp, C.POINTER(OptResult)]
     L.dpgo_b200_get_status.argtypes = [vp, C.POINTER(Status)]

@@ -131,6 +131,20 @@ int dpgo_b200_initialize(dpgo_b200_agent_t h, const double *T) {
   A(h)->initialize(T);
   API_END
 }
+int dpgo_b200_initialize_chordal(dpgo_b200_agent_t h) {
+  API_BEGIN
+  A(h)->initialize_chordal();
+  API_END
+}
+int dpgo_b200_get_local_trajectory(dpgo_b200_agent_t h, double *out) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state == 0 || a->Tlocal.size() != (size_t)12 * a->n) fail(DPGO_B200_ERR_STATE, "no local trajectory yet");
+  for (int i = 0; i < a->n; ++i)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) out[(size_t)i * 12 + r * 4 + c] = a->Tlocal[(size_t)i * 12 + c * 3 + r];
+  API_END
+}
 int dpgo_b200_initialize_in_global_frame(dpgo_b200_agent_t h, const double *Tw) {
   API_BEGIN
   A(h)->initialize_in_global_frame(Tw);

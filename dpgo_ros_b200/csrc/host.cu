@@ -4,6 +4,7 @@
 #include "host.hpp"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -154,6 +155,118 @@ void Agent::initialize(const double *T) {
       }
     }
   }
+  state = 1;
+}
+
+// Chordal initialisation on the device (demo default, launch/dpgo_demo.launch:9): over the robot's
+// own odometry + private loop closures with pose 0 fixed to the identity,
+//   rotations   : rows x_i of R_i minimise sum k |x_j - x_i R_ij|^2      (linear), then the polar factor per pose,
+//   translations: sum t |p_j - p_i - R_i t_ij|^2                         (linear).
+// Both systems share one block matrix (blocks [-k R_ij 0; 0 -t], diagonal [sum k I3 0; 0 sum t]) whose dense inverse
+// comes from the preconditioner machinery (dense_inverse.cu); the host only assembles the sparse blocks and the two
+// right-hand sides.  Same arithmetic as oracle Agent::initializeChordal.
+void Agent::initialize_chordal() {
+  if (n == 0) fail(DPGO_B200_ERR_STATE, "initialize: empty pose graph");
+  cuda_check(use_device(device), "cudaSetDevice");
+  Tlocal.assign((size_t)12 * n, 0.0);
+  for (int c = 0; c < 3; ++c) Tlocal[c * 3 + c] = 1.0;
+  const int N = n - 1;
+  if (N > 0) {
+    std::vector<std::map<int, std::array<double, 16>>> cols(N);
+    auto blk = [&](int i, int j) -> std::array<double, 16> & {
+      auto it = cols[j].find(i);
+      if (it == cols[j].end()) it = cols[j].emplace(i, std::array<double, 16>{}).first;
+      return it->second;
+    };
+    std::vector<double> B1((size_t)3 * 4 * N, 0.0);  // 3 x 4N column-major
+    std::vector<const Meas *> edges;
+    for (const auto &m : odom) edges.push_back(&m);
+    for (const auto &m : plc) edges.push_back(&m);
+    for (const Meas *m : edges) {
+      const double k = m->weight * m->kappa, t = m->weight * m->tau;
+      const int i = m->p1 - 1, j = m->p2 - 1;
+      if (i >= 0) {
+        auto &D = blk(i, i);
+        D[0] += k; D[5] += k; D[10] += k; D[15] += t;
+      }
+      if (j >= 0) {
+        auto &D = blk(j, j);
+        D[0] += k; D[5] += k; D[10] += k; D[15] += t;
+      }
+      if (i >= 0 && j >= 0) {
+        auto &U = blk(i, j), &L = blk(j, i);
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < 3; ++a) {
+            U[c * 4 + a] -= k * m->R[c * 3 + a];
+            L[c * 4 + a] -= k * m->R[a * 3 + c];
+          }
+        U[15] -= t;
+        L[15] -= t;
+      } else if (i < 0 && j >= 0) {
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < 3; ++a) B1[((size_t)4 * j + c) * 3 + a] += k * m->R[c * 3 + a];
+      } else if (j < 0 && i >= 0) {
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < 3; ++a) B1[((size_t)4 * i + c) * 3 + a] += k * m->R[a * 3 + c];
+      }
+    }
+    std::vector<int> rowptr(N + 1, 0), colidx;
+    std::vector<double> vals;
+    for (int j = 0; j < N; ++j) {
+      for (const auto &kv : cols[j]) {
+        colidx.push_back(kv.first);
+        vals.insert(vals.end(), kv.second.begin(), kv.second.end());
+      }
+      rowptr[j + 1] = (int)colidx.size();
+    }
+    const size_t npad = roundup32((size_t)4 * N);
+    DevBuf<int> d_rp, d_ci, info;
+    DevBuf<double> d_v, P, work, dinv, dB, dZ;
+    d_rp.upload(rowptr);
+    d_ci.upload(colidx);
+    d_v.upload(vals);
+    P.alloc(npad * npad);
+    work.alloc(npad * npad, false);
+    dinv.alloc((npad / 32) * 1024, false);
+    info.alloc(1);
+    cuda_check(launch_scatter_blocks(P.p, npad, d_rp.p, d_ci.p, d_v.p, N, 0.0, (int)npad, 0), "scatter_blocks");
+    cuda_check(spd_inverse(P.p, work.p, dinv.p, (int)npad, info.p, 0), "spd_inverse");
+    int h_info = 0;
+    cuda_check(cudaMemcpy(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
+    if (h_info != 0) fail(DPGO_B200_ERR_NUMERIC, "Chordal initialisation: the pose graph is not connected to pose 0");
+    // stage 1: rotations
+    dB.upload(B1);
+    dZ.alloc((size_t)3 * 4 * N);
+    cuda_check(launch_rows_times_sym(dB.p, P.p, npad, 3, 4 * N, dZ.p, 0), "rows_times_sym");
+    cuda_check(launch_manifold_op(0, 3, N, dZ.p, nullptr, dB.p, std::max(1, std::min(148, (N + 31) / 32)), 0),
+               "polar factor");
+    std::vector<double> Rs((size_t)12 * N);
+    cuda_check(cudaMemcpy(Rs.data(), dB.p, Rs.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H rotations");
+    for (int i = 0; i < N; ++i)
+      for (int c = 0; c < 3; ++c)
+        for (int a = 0; a < 3; ++a) Tlocal[(size_t)(i + 1) * 12 + c * 3 + a] = Rs[((size_t)4 * i + c) * 3 + a];
+    // stage 2: translations
+    std::vector<double> B2((size_t)3 * 4 * N, 0.0);
+    for (const Meas *m : edges) {
+      const double t = m->weight * m->tau;
+      const int i = m->p1 - 1, j = m->p2 - 1;
+      const double *Ri = &Tlocal[(size_t)m->p1 * 12];
+      for (int a = 0; a < 3; ++a) {
+        double sum = 0;
+        for (int kk = 0; kk < 3; ++kk) sum += Ri[kk * 3 + a] * m->t[kk];
+        const double v = t * sum;
+        if (j >= 0) B2[((size_t)4 * j + 3) * 3 + a] += v;
+        if (i >= 0) B2[((size_t)4 * i + 3) * 3 + a] -= v;
+      }
+    }
+    dB.upload(B2);
+    cuda_check(launch_rows_times_sym(dB.p, P.p, npad, 3, 4 * N, dZ.p, 0), "rows_times_sym");
+    std::vector<double> Ts((size_t)12 * N);
+    cuda_check(cudaMemcpy(Ts.data(), dZ.p, Ts.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H translations");
+    for (int i = 0; i < N; ++i)
+      for (int a = 0; a < 3; ++a) Tlocal[(size_t)(i + 1) * 12 + 9 + a] = Ts[((size_t)4 * i + 3) * 3 + a];
+  }
+  drop_lookahead();
   state = 1;
 }
 

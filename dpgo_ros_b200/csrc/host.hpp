@@ -76,6 +76,7 @@ class Agent {
   // ---- lifecycle
   void set_lifting_matrix(const double *Y);
   void initialize(const double *T_rowmajor_or_null);
+  void initialize_chordal();  // local_initialization_method "Chordal" (src/PGOAgentROSNode.cpp:106-112)
   void initialize_in_global_frame(const double *Tw_rowmajor);
   void reset();
   bool iterate(bool do_opt);

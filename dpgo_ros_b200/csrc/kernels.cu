@@ -194,6 +194,21 @@ __global__ void __launch_bounds__(kThreads) k_manifold_op(int op, int r, int n, 
   }
 }
 
+// Z (rows x n4) = B (rows x n4) * P for a symmetric n4 x n4 matrix P (column-major, leading dimension ld): thread c
+// owns output column c and walks P's ROW c -- by symmetry its column c -- so neighbouring threads read neighbouring
+// addresses.  B and Z are column-major with `rows` (<= 8) rows.  Used by the Chordal initialisation (two solves per
+// round, not a hot path).
+__global__ void k_rows_times_sym(const double *B, const double *P, size_t ld, int rows, int n4, double *Z) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n4) return;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int q = 0; q < n4; ++q) {
+    const double p = P[(size_t)q * ld + c];
+    for (int a = 0; a < rows; ++a) acc[a] = fma(B[(size_t)q * rows + a], p, acc[a]);
+  }
+  for (int a = 0; a < rows; ++a) Z[(size_t)c * rows + a] = acc[a];
+}
+
 // publishPublicPoses for every local agent (src/PGOAgentROS.cpp:662-690): X -> reg, Y -> aux
 __global__ void __launch_bounds__(kThreads) k_publish_all(const __grid_constant__ TeamDev T) {
   PoseIter it;
@@ -373,6 +388,13 @@ cudaError_t launch_manifold_op(int op, int r, int n, const double *A, const doub
                                cudaStream_t s) {
   ++g_launches;
   k_manifold_op<<<grid, kThreads, 0, s>>>(op, r, n, A, B, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_rows_times_sym(const double *B, const double *P, size_t ld, int rows, int n4, double *Z,
+                                  cudaStream_t s) {
+  if (rows < 1 || rows > 8) return cudaErrorInvalidValue;
+  ++g_launches;
+  k_rows_times_sym<<<(n4 + 127) / 128, 128, 0, s>>>(B, P, ld, rows, n4, Z);
   return cudaGetLastError();
 }
 cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s) {

@@ -61,6 +61,9 @@ cudaError_t launch_manifold_op(int op, int r, int n, const double *A, const doub
 cudaError_t launch_barrier_bench(const GridSync &gs, int iters, int mode, unsigned epoch0, double *out, int grid,
                                  cudaStream_t s);
 cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s);
+// Z = B * P, P symmetric n4 x n4 (ld), B / Z column-major with rows <= 8 rows
+cudaError_t launch_rows_times_sym(const double *B, const double *P, size_t ld, int rows, int n4, double *Z,
+                                  cudaStream_t s);
 cudaError_t launch_gnc_weights(const LcDev &L, int r, const double *X, const double *inbox, double barc_sq,
                                double mu, int cost_type, cudaStream_t s);
 

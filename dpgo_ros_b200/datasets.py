@@ -362,6 +362,27 @@ def robust_frame_alignment(meas: Measurements, traj: Dict[int, Tuple[np.ndarray,
     return frames
 
 
+def with_local_initialization(problem: "Problem", local_trajectory) -> "Problem":
+    """`problem` with a new initial guess: `local_trajectory(rid)` -> [n, 3, 4] poses in the robot's own frame (e.g. the
+    Chordal initialisation of the oracle or of the GPU agent), placed in the global frame by robust_frame_alignment
+    over the shared loop closures (robot 0 = identity) -- the INITIALIZE round of the wrapper
+    (src/PGOAgentROS.cpp:322-366, 1091-1159) without its messaging."""
+    traj = {}
+    for rid in range(problem.num_robots):
+        T = np.asarray(local_trajectory(rid))
+        traj[rid] = (T[:, :, :3].copy(), T[:, :, 3].copy())
+    frames = robust_frame_alignment(problem.meas, traj, problem.num_robots)
+    T_init = []
+    for rid in range(problem.num_robots):
+        Rw, tw = frames[rid]
+        T = np.zeros((problem.n[rid], 3, 4))
+        T[:, :, :3] = np.einsum("ij,njk->nik", Rw, traj[rid][0])
+        T[:, :, 3] = traj[rid][1] @ Rw.T + tw
+        T_init.append(T)
+    return Problem(name=problem.name + "+init", num_robots=problem.num_robots, meas=problem.meas, n=list(problem.n),
+                   T_init=T_init)
+
+
 def fixed_lifting_matrix(r: int, d: int = 3) -> np.ndarray:
     """A fixed YLift in St(d, r), identical for oracle and GPU runs.
 

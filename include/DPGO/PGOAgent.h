@@ -137,8 +137,10 @@ class PGOAgent {
           for (int c = 0; c < 4; ++c) T[(size_t)i * 12 + a * 4 + c] = P(a, c);
       }
       check(dpgo_b200_initialize(h_, T.data()), "initialize");
+    } else if (mParams.localInitializationMethod == InitializationMethod::Chordal) {
+      check(dpgo_b200_initialize_chordal(h_), "initialize (Chordal)");               // PGOAgentROSNode.cpp:108-109
     } else {
-      check(dpgo_b200_initialize(h_, nullptr), "initialize");
+      check(dpgo_b200_initialize(h_, nullptr), "initialize");                          // Odometry
     }
     mState = PGOAgentState::WAIT_FOR_INITIALIZATION;
     mStatus.state = mState;

@@ -105,6 +105,12 @@ int dpgo_b200_measurement_counts(dpgo_b200_agent_t a, int *odometry, int *privat
 int dpgo_b200_set_lifting_matrix(dpgo_b200_agent_t a, const double *Y);   /* :928 */
 int dpgo_b200_get_lifting_matrix(dpgo_b200_agent_t a, double *Y);         /* :404 */
 int dpgo_b200_initialize(dpgo_b200_agent_t a, const double *T_local_or_null);   /* :348 */
+/* local_initialization_method "Chordal" (src/PGOAgentROSNode.cpp:106-112; demo default, launch/dpgo_demo.launch:9):
+ * chordal relaxation of the rotations + linear translations over the robot's own edges, pose 0 = identity, solved
+ * with the dense-inverse machinery on the device.  Leaves the agent in WAIT_FOR_INITIALIZATION like initialize(). */
+int dpgo_b200_initialize_chordal(dpgo_b200_agent_t a);
+/* the local-frame trajectory produced by initialize / initialize_chordal: n x 3 x 4 doubles, row-major per pose */
+int dpgo_b200_get_local_trajectory(dpgo_b200_agent_t a, double *T_local);
 int dpgo_b200_initialize_in_global_frame(dpgo_b200_agent_t a, const double *T_world_robot); /* :353,358 */
 
 /* ---- the hot call: iterate(bool), :160 (true) and :1185 (false) -------------- */

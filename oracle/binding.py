@@ -97,6 +97,8 @@ def lib():
     L.orc_initialize_in_global_frame.argtypes = [C.c_void_p, C.c_int, dp]
     L.orc_exchange_all.argtypes = [C.c_void_p]
     L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
+    L.orc_initialize_chordal.argtypes = [C.c_void_p, C.c_int]
+    L.orc_get_local_trajectory.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.orc_run_parallel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
     L.orc_agent_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_get_x.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
@@ -193,6 +195,16 @@ class OracleTeam:
         else:
             T = _f64(T_local)
             _chk(self.L.orc_initialize(self.h, rid, _dp(T)), "initialize")
+
+    def initialize_chordal(self, rid):
+        """Chordal local initialisation (Agent::initializeChordal); returns the local trajectory [n, 3, 4]."""
+        _chk(self.L.orc_initialize_chordal(self.h, rid), "initialize_chordal")
+        return self.local_trajectory(rid)
+
+    def local_trajectory(self, rid) -> np.ndarray:
+        out = np.zeros((self.n[rid], 3, 4))
+        _chk(self.L.orc_get_local_trajectory(self.h, rid, _dp(out)), "local_trajectory")
+        return out
 
     def initialize_in_global_frame(self, rid, Tw):
         T = _f64(Tw)

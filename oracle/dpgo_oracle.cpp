@@ -4,6 +4,7 @@
 #include "dpgo_oracle.hpp"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cassert>
 #include <chrono>
@@ -11,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <stdexcept>
 #include <thread>
 
@@ -810,6 +812,94 @@ void Agent::initialize(const double *T_local) {
         Tlocal_(a, 4 * (i + 1) + 3) = s;
       }
     }
+  }
+  state_ = AgentState::WAIT_FOR_INITIALIZATION;
+}
+
+void Agent::initializeChordal() {
+  const int n = pg_->n();
+  if (n == 0) return;
+  Tlocal_ = Mat(3, 4 * n);
+  for (int c = 0; c < 3; ++c) Tlocal_(c, c) = 1.0;  // pose 0: the anchor
+  const int N = n - 1;                               // unknown poses 1 .. n-1 -> blocks 0 .. N-1
+  if (N > 0) {
+    // One block matrix serves both stages: block (i, j) = [ -k R_ij  0 ; 0  -t ] , diagonal [ sum k I3  0 ; 0  sum t ]
+    // (k = w kappa, t = w tau).  Row-vector convention: unknown rows x_i (1x3 rows of R_i), cost |x_j - x_i R_ij|^2.
+    std::vector<std::map<int, std::array<double, 16>>> cols(N);
+    auto blk = [&](int i, int j) -> std::array<double, 16> & {
+      auto it = cols[j].find(i);
+      if (it == cols[j].end()) it = cols[j].emplace(i, std::array<double, 16>{}).first;
+      return it->second;
+    };
+    Mat B1(3, 4 * N);
+    std::vector<const Measurement *> edges;
+    for (const auto &m : pg_->odometry()) edges.push_back(&m);
+    for (const auto &m : pg_->privateLoopClosures()) edges.push_back(&m);
+    for (const Measurement *m : edges) {
+      const double k = m->weight * m->kappa, t = m->weight * m->tau;
+      const int i = m->p1 - 1, j = m->p2 - 1;
+      if (i >= 0) {
+        auto &D = blk(i, i);
+        D[0] += k; D[5] += k; D[10] += k; D[15] += t;
+      }
+      if (j >= 0) {
+        auto &D = blk(j, j);
+        D[0] += k; D[5] += k; D[10] += k; D[15] += t;
+      }
+      if (i >= 0 && j >= 0) {
+        auto &U = blk(i, j), &L = blk(j, i);
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < 3; ++a) {
+            U[c * 4 + a] -= k * m->R[c * 3 + a];   // (i, j) = -k R
+            L[c * 4 + a] -= k * m->R[a * 3 + c];   // (j, i) = -k R^T
+          }
+        U[15] -= t;
+        L[15] -= t;
+      } else if (i < 0 && j >= 0) {  // 0 -> j : x_j should equal I * R
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < 3; ++a) B1(a, 4 * j + c) += k * m->R[c * 3 + a];
+      } else if (j < 0 && i >= 0) {  // i -> 0 : x_i R should equal I
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < 3; ++a) B1(a, 4 * i + c) += k * m->R[a * 3 + c];
+      }
+    }
+    std::vector<std::vector<int>> rows(N);
+    std::vector<std::vector<double>> vals(N);
+    for (int j = 0; j < N; ++j)
+      for (const auto &kv : cols[j]) {
+        rows[j].push_back(kv.first);
+        vals[j].insert(vals[j].end(), kv.second.begin(), kv.second.end());
+      }
+    BlockCholesky chol;
+    chol.factor(N, rows, vals);
+    chol.solveRows(B1);
+    for (int i = 0; i < N; ++i) {
+      double M[9], Rp[9];
+      for (int c = 0; c < 3; ++c)
+        for (int a = 0; a < 3; ++a) M[c * 3 + a] = B1(a, 4 * i + c);
+      projectToStiefel(M, 3, Rp);  // polar factor of the 3x3 block
+      for (int c = 0; c < 3; ++c)
+        for (int a = 0; a < 3; ++a) Tlocal_(a, 4 * (i + 1) + c) = Rp[c * 3 + a];
+    }
+    // translations: sum t |p_j - p_i - R_i t_ij|^2, p_0 = 0
+    Mat B2(3, 4 * N);
+    for (const Measurement *m : edges) {
+      const double t = m->weight * m->tau;
+      const int i = m->p1 - 1, j = m->p2 - 1;
+      double v[3];
+      for (int a = 0; a < 3; ++a) {
+        double sum = 0;
+        for (int kk = 0; kk < 3; ++kk) sum += Tlocal_(a, 4 * m->p1 + kk) * m->t[kk];
+        v[a] = t * sum;
+      }
+      for (int a = 0; a < 3; ++a) {
+        if (j >= 0) B2(a, 4 * j + 3) += v[a];
+        if (i >= 0) B2(a, 4 * i + 3) -= v[a];
+      }
+    }
+    chol.solveRows(B2);
+    for (int i = 0; i < N; ++i)
+      for (int a = 0; a < 3; ++a) Tlocal_(a, 4 * (i + 1) + 3) = B2(a, 4 * i + 3);
   }
   state_ = AgentState::WAIT_FOR_INITIALIZATION;
 }

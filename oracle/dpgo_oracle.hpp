@@ -248,6 +248,12 @@ class Agent {
   // Local initialisation (:348).  T = d x (d+1) per pose, column-major, n poses,
   // in the robot-local frame; null => chain odometry from identity.
   void initialize(const double *T_local);
+  // local_initialization_method "Chordal" (src/PGOAgentROSNode.cpp:106-112; the demos' default,
+  // launch/dpgo_demo.launch:9): two linear solves over the robot's own odometry + private loop closures with pose 0
+  // fixed to the identity -- rotations from the chordal relaxation (then the polar factor of every 3x3 block),
+  // translations from the resulting linear least squares.  [UPSTREAM-RECALL of the method, not of its code.]
+  void initializeChordal();
+  const Mat &localTrajectory() const { return Tlocal_; }
   // :353,358 -- T_world_robot is d x (d+1) column-major.
   void initializeInGlobalFrame(const double *T_world_robot);
   bool iterate(bool doOptimization);                            // :160 (true), :1185 (false)

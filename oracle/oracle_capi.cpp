@@ -142,6 +142,21 @@ int orc_initialize(void *t, int agent, const double *T_local) {
   ORC_CATCH
 }
 
+int orc_initialize_chordal(void *t, int agent) {
+  ORC_TRY((Team *)t)->agent(agent).initializeChordal();
+  ORC_CATCH
+}
+
+// local-frame trajectory after initialize / initializeChordal: n x 3 x 4 row-major per pose
+int orc_get_local_trajectory(void *t, int agent, double *out) {
+  ORC_TRY const Mat &T = ((Team *)t)->agent(agent).localTrajectory();
+  const int n = T.cols / 4;
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 4; ++c) out[(size_t)i * 12 + a * 4 + c] = T(a, 4 * i + c);
+  ORC_CATCH
+}
+
 int orc_initialize_in_global_frame(void *t, int agent, const double *Tw /*3x4 row-major*/) {
   ORC_TRY std::vector<double> cm;
   rowMajorPosesToColMajor(Tw, 1, cm);

@@ -87,3 +87,34 @@ def test_unsupported_configurations_are_refused():
     team.add(a5[0])
     with pytest.raises(DpgoError):
         team.add(a6[1])
+
+
+@pytest.mark.parametrize("name,robots", [("smallGrid3D", 2), ("sphere2500", 8), ("tinyGrid3D", 1)])
+def test_chordal_initialization_matches_oracle(name, robots):
+    """local_initialization_method Chordal (src/PGOAgentROSNode.cpp:106-112) on the device: dense inverse of the
+    anchored block Laplacian, two products, polar factors -- against oracle Agent::initializeChordal."""
+    pb = datasets.load_g2o_problem(name, robots)
+    o = orc.OracleTeam(pb, r=5, initialize=False)
+    P = gpu.make_params(r=5, num_robots=robots)
+    locals_gpu = {}
+    for rid in range(robots):
+        ag = gpu.PGOAgent(rid, P, 0)
+        ag.addMeasurements(pb.robot_measurements(rid))
+        T = ag.initializeChordal()
+        To = o.initialize_chordal(rid)
+        assert T.shape == To.shape
+        assert np.abs(T - To).max() < 1e-9 * max(1.0, np.abs(To).max()), rid
+        locals_gpu[rid] = T
+        ag.close()
+    # the whole pipeline from that guess: same iteration count and iterate as the oracle from ITS Chordal guess
+    if robots > 1:
+        pg = datasets.with_local_initialization(pb, lambda rid: locals_gpu[rid])
+        po = datasets.with_local_initialization(pb, lambda rid: o.local_trajectory(rid))
+        kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2, max_num_iters=300)
+        team, agents = gpu.make_team(pg, **kw)
+        oteam = orc.OracleTeam(po, **kw)
+        res = team.run(300, stop_on_terminate=True)
+        ores = oteam.run(300, stop_on_terminate=True)
+        assert res.iterations == ores.iterations and res.terminated
+        for rid in range(robots):
+            assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6, rid
