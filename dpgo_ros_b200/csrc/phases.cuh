@@ -63,6 +63,28 @@ __device__ __forceinline__ void publish_range(int e0, int e1, double *const *dst
   for (int e = e0; e < e1; ++e) st4(dst[e], r, a, act, x);
 }
 
+// The first two destinations of a pose's publication entries, requested as soon as the entry range is known so that
+// the pointer loads overlap the pose's arithmetic instead of forming a dependent L2 trip right before the stores
+// (a pose is public towards at most two neighbours in the chain / ring splits; further entries take the loop).
+struct PubPtrs {
+  double *d0, *d1;
+  int e0, e1;
+};
+__device__ __forceinline__ PubPtrs pub_prefetch(double *const *dst, int e0, int e1) {
+  PubPtrs p;
+  p.e0 = e0;
+  p.e1 = e1;
+  p.d0 = (e0 < e1) ? dst[e0] : nullptr;
+  p.d1 = (e0 + 1 < e1) ? dst[e0 + 1] : nullptr;
+  return p;
+}
+__device__ __forceinline__ void publish_pre(const PubPtrs &p, double *const *dst, int r, int a, bool act,
+                                            const double (&x)[4]) {
+  if (p.d0) st4(p.d0, r, a, act, x);
+  if (p.d1) st4(p.d1, r, a, act, x);
+  for (int e = p.e0 + 2; e < p.e1; ++e) st4(dst[e], r, a, act, x);
+}
+
 // out_row(1x4) += x_row(1x4) * B(4x4 col-major)
 __device__ __forceinline__ void row_times_block(const double (&x)[4], const double *B, double (&acc)[4]) {
 #pragma unroll
@@ -124,6 +146,8 @@ __device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, b
     return;
   }
   if (!lc.X) ld4(A.V + off, r, a, act, v);
+  const PubPtrs paux = pub_prefetch(A.pub_dst_aux, pe0, pe1);
+  const PubPtrs preg = (ai != sel_local) ? pub_prefetch(A.pub_dst_reg, pe0, pe1) : PubPtrs{nullptr, nullptr, 0, 0};
 #pragma unroll
   for (int c = 0; c < 4; ++c) m[c] = (1.0 - alpha) * x[c] + alpha * v[c];
   if (!valid) {  // keep idle groups on the fast path of sym3_invsqrt
@@ -134,10 +158,10 @@ __device__ __forceinline__ void nesterov_pose(const TeamDev &T, int ai, int j, b
   stiefel_project_row(m);
   if (valid) {
     st4(A.Y + off, r, a, act, m);
-    publish_range(pe0, pe1, A.pub_dst_aux, r, a, act, m);
+    publish_pre(paux, A.pub_dst_aux, r, a, act, m);
     if (ai != sel_local) {
       st4(A.X + off, r, a, act, m);
-      publish_range(pe0, pe1, A.pub_dst_reg, r, a, act, m);
+      publish_pre(preg, A.pub_dst_reg, r, a, act, m);
     }
   }
 }
@@ -670,6 +694,7 @@ __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid
     ld4(A.Y + off, r, a, act, y);
     ld4(A.V + off, r, a, act, v);
   }
+  const PubPtrs preg = pub_prefetch(A.pub_dst_reg, pe0, pe1);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const double d = xnew[c] - xold[c];
@@ -678,7 +703,7 @@ __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid
   if (valid) {
     st4(A.X + off, r, a, act, xnew);
     if (xcopy) st4(xcopy + off, r, a, act, xnew);
-    publish_range(pe0, pe1, A.pub_dst_reg, r, a, act, xnew);
+    publish_pre(preg, A.pub_dst_reg, r, a, act, xnew);
   }
   if (accel) {
     if (restart) {
