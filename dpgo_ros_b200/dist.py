@@ -436,7 +436,13 @@ class ShmHostTeam:
         nbytes = int(self.L.dpgo_b200_sync_driver_shm_bytes(self.N, self.cap))
         name = f"dpgo_b200_{tag}"
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+            try:
+                self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+            except FileExistsError:  # left behind by a run that died: start from a fresh segment
+                stale = shared_memory.SharedMemory(name=name, create=False)
+                stale.close()
+                stale.unlink()
+                self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
             self.shm.buf[:nbytes] = bytes(nbytes)
             struct.pack_into("i", self.shm.buf, 12, -1)   # ShmHeader::term
         dist.barrier()
