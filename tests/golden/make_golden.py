@@ -37,7 +37,27 @@ CASES = {
                               params=dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2, cost_type=5, gnc_barc=3.0,
                                           gnc_mu_step=2.0, gnc_init_mu=1e-5, robust_opt_num_weight_updates=3,
                                           robust_opt_num_resets=3, robust_opt_inner_iters=10, max_num_iters=38)),
+    # BASELINE config 5 at a size the oracle finishes in seconds: synthetic lattice graph (seed 0), 8 agents, the
+    # asynchronous mode as parallel ticks (schedule 1), RGD 0.2 + preconditioner (launch/asapp_demo.launch:7-8)
+    "config5_synthetic2000_8_parallel": dict(dataset="synthetic:2000:20000", robots=8, max_run=40, schedule=1,
+                                             params=dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1,
+                                                         acceleration=0, rel_change_tol=0.0, max_num_iters=10 ** 9)),
+    # README demo from the Chordal initialisation (launch/dpgo_demo.launch:9): sphere2500, 5 agents, RTR, tol 0.2
+    "readme_sphere2500_5_chordal_rtr": dict(dataset="sphere2500", robots=5, max_run=1000, init="chordal",
+                                            params=dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2)),
 }
+
+
+def load_problem(c):
+    if c["dataset"].startswith("synthetic:"):
+        _, n, m = c["dataset"].split(":")
+        pb = datasets.make_synthetic_problem(int(n), int(m), c["robots"], seed=0)
+    else:
+        pb = datasets.load_g2o_problem(c["dataset"], c["robots"])
+    if c.get("init") == "chordal":
+        o = orc.OracleTeam(pb, r=c["params"]["r"], initialize=False)
+        pb = datasets.with_local_initialization(pb, lambda rid: o.initialize_chordal(rid))
+    return pb
 
 
 def fingerprint(X):
@@ -48,10 +68,11 @@ def fingerprint(X):
 def main():
     out = {}
     for name, c in CASES.items():
-        pb = datasets.load_g2o_problem(c["dataset"], c["robots"])
+        pb = load_problem(c)
         team = orc.OracleTeam(pb, **c["params"])
-        res = team.run(c["max_run"], threads=4)
+        res = team.run_parallel(c["max_run"], threads=4) if c.get("schedule") else team.run(c["max_run"], threads=4)
         out[name] = {"dataset": c["dataset"], "robots": c["robots"], "params": c["params"], "max_run": c["max_run"],
+                     "schedule": c.get("schedule", 0), "init": c.get("init", "odometry"),
                      "iterations": res.iterations, "terminated": bool(res.terminated),
                      "weight_updates": res.weight_updates, "final_cost_2f": team.global_cost(),
                      "X": [fingerprint(team.get_x(r)) for r in range(c["robots"])]}

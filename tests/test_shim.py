@@ -47,6 +47,27 @@ def test_wire_formats_and_iteration_log(tmp_path):
     assert "wire checks ok" in res.stdout
 
 
+def test_cmake_package_finds_the_shim(tmp_path):
+    """`find_package(DPGO REQUIRED)` + `target_link_libraries(... DPGO)` -- the two lines dpgo_ros's own build uses
+    (CMakeLists.txt:6, 151-154) -- resolve against cmake/DPGOConfig.cmake."""
+    import shutil
+    if shutil.which("cmake") is None:
+        pytest.skip("cmake not available")
+    from dpgo_ros_b200 import capi
+    capi.lib()
+    (tmp_path / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.10)\nproject(shimcheck CXX)\nfind_package(DPGO REQUIRED)\n"
+        f"add_executable(shim_harness {os.path.join(ROOT, 'tests', 'cpp', 'shim_harness.cpp')})\n"
+        "target_link_libraries(shim_harness DPGO)\n")
+    b = tmp_path / "build"
+    r1 = subprocess.run(["cmake", "-S", str(tmp_path), "-B", str(b), "-DDPGO_DIR=" + os.path.join(ROOT, "cmake")],
+                        capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0, r1.stdout[-2000:] + r1.stderr[-2000:]
+    r2 = subprocess.run(["cmake", "--build", str(b)], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    assert (b / "shim_harness").exists()
+
+
 def test_shim_harness_builds_and_refuses_to_run_without_gpu(harness, tmp_path):
     from dpgo_ros_b200 import capi
     if capi.lib().dpgo_b200_device_count() > 0:
