@@ -12,11 +12,18 @@ public (+ auxiliary) poses are exchanged (src/PGOAgentROS.cpp:1161-1189,
 acceleration (restart 50), RoundRobin, odometry initial guess, fixed YLift.
 
 `value`  : all 8 agents resident on the GPU(s), the persistent kernel runs the K
-           steps with device-side exchange; timed with CUDA events inside the
-           library around the launches (on the launching stream).
+           steps with device-side exchange (N > 1: one persistent kernel per GPU,
+           public poses stored into peer memory over NVLink -- the fabric); timed
+           with CUDA events inside the library around the launches (on the
+           launching stream), max over ranks.
 `e2e`    : the same K steps driven through the per-robot C ABI that PGOAgentROS
            would call (iterate / getSharedPoseDictWithNeighbor / updateNeighborPoses)
-           with HOST buffers: every step's public poses cross PCIe both ways.
+           with HOST buffers, one OS thread per robot: every step's public poses
+           cross PCIe both ways (N > 1: and a shared-memory segment between the
+           per-GPU processes).
+Secondary objects on the same line: `async_mode` (the reference's asynchronous
+demo configuration as parallel ticks) and, at N = 1, `hbm_bound_regime` (one rank
+of BASELINE config 5 at the named size -- the HBM-bound regime of this path).
 """
 from __future__ import annotations
 
