@@ -439,7 +439,8 @@ __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, do
 // fabric barrier (multi-GPU).  arrive: call right after a grid barrier that follows this rank's
 // last stores into peer memory -- thread s of CTA 0 then fences at system scope and writes this
 // rank's flag in peer s's window (release/acquire chain: peer stores of any CTA -> grid barrier
-// -> fence.sys -> flag).  wait: lanes 0..world-1 of every CTA poll their peer's flag in the LOCAL
+// -> fence.sys -> flag; every thread that stored into peer memory also fences at system scope before that grid
+// barrier, so the chain does not lean on cumulativity across SMs over NVLink).  wait: lanes 0..world-1 of every CTA poll their peer's flag in the LOCAL
 // window.  Split arrive / wait lets a rank announce "I am done reading my inbox" early.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {

@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           defer_store(T, ai, 4, prel);
           __syncthreads();  // the slab buffer and zs are reused by the next agent
         }
+        if (fab) __threadfence_system();
         grid_barrier(gs, bs);
         if (fab) {  // every rank's X+ has reached its neighbours' inboxes
           fabric_arrive(F, fs, 0);
@@ -501,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha, lc);
         PROF(1)
+        if (fab) __threadfence_system();  // my stores into peer inboxes are performed before I arrive (see fabric_arrive)
         grid_barrier(gs, bs);
         if (fab) {  // every rank's Y (and X) of this iteration has reached its neighbours' inboxes
           fabric_arrive(F, fs, 0);
@@ -562,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         pend_ai = sel_local;
         touched |= 1u << sel_local;
         rel_due |= 1u << sel_local;
+        if (fab) __threadfence_system();  // X+ stored into peer inboxes: performed before the next fabric arrival
         if (!accel) grid_barrier(gs, bs);  // plain RBCD has no Nesterov phase (and its sync) before the next gradient
         PROF(6)
       } else {
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const RtrOut ro = rtr_solve<R>(A, sel_local, P, gs, bs, Xs, inbox, ss, mbar, L, sm_slab, sm_red);
         double v[1] = {0};
         phase_commit<R>(A, ro.x, accel, restart, gamma, v[0]);
+        if (fab) __threadfence_system();
         if (schedule) {
           const int nxt = T.local_of_robot[(sel_robot + 1) % N];
           if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, mbar, L.slab, L.slab_cap);
@@ -710,6 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
   }
   if (ss.pending) slab_wait(mbar, ss.parity);  // do not exit with a bulk copy in flight
+  if (fab) __threadfence_system();
   grid_barrier(gs, bs);  // every CTA's result-block writes (outboxes, stats) are ordered before the flag
   if (fab && !dead) {
     // leave together: on return every publication of every rank has landed in its destination inbox
