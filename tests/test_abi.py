@@ -59,3 +59,20 @@ def test_no_cpu_fallback_without_gpu():
     assert L.dpgo_b200_manifold_project(0, 5, 2, M.ctypes.data_as(dp), out.ctypes.data_as(dp)) == -3
     t = C.c_void_p()
     assert L.dpgo_b200_team_create(0, C.byref(t)) == -3
+
+
+def test_library_is_built_for_sm_100a_only():
+    """Every cubin in the shared library targets sm_100a (write for B200 only; no multi-arch fallback), and the hot
+    kernel carries the TMA bulk copy of the preconditioner slab (UBLKCP in SASS)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "--list-elf", capi.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    elfs = [l for l in out.splitlines() if l.startswith("ELF file")]
+    assert len(elfs) >= 20
+    assert all("sm_100a" in l for l in elfs), [l for l in elfs if "sm_100a" not in l]
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4dpgo10k_team_runILi5ELi1ELb0EEEvNS_7TeamDevENS_7RunArgsE",
+                           capi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert sass.count("UBLKCP") >= 1 and sass.count("DFMA") > 500
+    assert "ATOM" not in sass.replace("ATOMIC", "")   # no atomics on data in the hot kernel
