@@ -370,3 +370,19 @@ def test_config4_tunnels_gnc_tls():
         assert np.max(np.abs(wg - wo)) < 1e-3, np.max(np.abs(wg - wo))
         assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-3, rel(agents[rid].getX(), oteam.get_x(rid))
     assert abs(team.global_cost() - oteam.global_cost()) < 1e-3 * oteam.global_cost()
+
+
+def test_native_sync_driver_rtr_accelerated(small_problem):
+    """Per-robot API with the RTR local solver AND acceleration: the lookahead after an RTR solve serves the
+    iterate(false) calls (restart interval 5 puts restart iterations inside the speculated steps)."""
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, acceleration=1, restart_interval=5, rel_change_tol=0.0,
+              max_num_iters=1000)
+    oteam = orc.OracleTeam(small_problem, **kw)
+    _, agents = gpu.make_team(small_problem, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=True)
+    gpu.sync_driver_run(agents, 12, True)
+    oteam.run(12, stop_on_terminate=False)
+    for rid in range(2):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6, rid
+        assert rel(agents[rid].getX(2), oteam.get_x(rid, 2)) < 1e-6, rid
+        assert agents[rid].iteration_number() == 12
