@@ -13,17 +13,28 @@
  *
  * What stays on the host is bookkeeping (status maps, active-robot flags) and the once-per-round
  * global-frame read-out (rounding).  Header-only; link with -ldpgo_b200.
+ *
+ * Threading: in synchronous mode the wrapper is single-threaded.  With `asynchronous = true`
+ * (src/PGOAgentROSNode.cpp:80-93) this class owns the optimisation thread, as upstream does: it is started by
+ * initializeInGlobalFrame, runs iterate(true) on a Poisson clock of rate asynchronousOptimizationRate and raises
+ * mPublishAsynchronousRequested, which runOnceAsynchronous polls (src/PGOAgentROS.cpp:119-127).  Every public method
+ * takes the agent's mutex, so the wrapper's callbacks may run next to that thread.
  */
 #ifndef DPGO_SHIM_PGOAGENT_H
 #define DPGO_SHIM_PGOAGENT_H
 
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <iostream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
+#include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "DPGO/DPGO_robust.h"
@@ -72,6 +83,8 @@ class PGOAgentParameters {
   }
 };
 
+#define DPGO_SHIM_LOCK std::lock_guard<std::recursive_mutex> dpgo_shim_lock_(mMutex)
+
 class PGOAgent {
  public:
   PGOAgent(unsigned ID, const PGOAgentParameters &params)
@@ -81,8 +94,34 @@ class PGOAgent {
     createHandle();
   }
   virtual ~PGOAgent() {
+    endOptimizationLoop();
     if (h_) dpgo_b200_agent_destroy(h_);
   }
+
+  // ---- asynchronous mode: the library-owned optimisation thread
+  void startOptimizationLoop(double freq) {
+    if (mOptimizationThread) return;
+    mEndLoopRequested = false;
+    mOptimizationThread.reset(new std::thread([this, freq] {
+      std::mt19937 rng(mID + 1);
+      std::exponential_distribution<double> gap(freq > 0 ? freq : 1.0);
+      while (!mEndLoopRequested) {
+        std::this_thread::sleep_for(std::chrono::duration<double>(gap(rng)));
+        if (mEndLoopRequested) break;
+        DPGO_SHIM_LOCK;
+        if (mState != PGOAgentState::INITIALIZED) continue;
+        iterate(true);
+        mPublishAsynchronousRequested = true;   // polled at src/PGOAgentROS.cpp:120
+      }
+    }));
+  }
+  void endOptimizationLoop() {
+    if (!mOptimizationThread) return;
+    mEndLoopRequested = true;
+    mOptimizationThread->join();
+    mOptimizationThread.reset();
+  }
+  bool isOptimizationRunning() const { return (bool)mOptimizationThread; }
   PGOAgent(const PGOAgent &) = delete;
   PGOAgent &operator=(const PGOAgent &) = delete;
 
@@ -100,6 +139,7 @@ class PGOAgent {
 
   // ---- pose graph
   void addMeasurement(const RelativeSEMeasurement &m) {                        // :277, :1307
+    DPGO_SHIM_LOCK;
     rebindGraphIfReplaced();
     if (mState != PGOAgentState::WAIT_FOR_DATA) return;  // measurements are fixed once a round has started
     if (!mPoseGraph->addMeasurement(m)) return;
@@ -116,6 +156,7 @@ class PGOAgent {
 
   // ---- lifecycle
   void setLiftingMatrix(const Matrix &M) {                                     // :928
+    DPGO_SHIM_LOCK;
     if (M.rows() != r || M.cols() != d) throw std::invalid_argument("setLiftingMatrix: expected r x d");
     YLift.emplace(M);
     check(dpgo_b200_set_lifting_matrix(h_, M.data()), "setLiftingMatrix");
@@ -127,6 +168,7 @@ class PGOAgent {
   }
   // local initialisation: odometry chain, or the trajectory estimate handed over by the front end (:285-303)
   void initialize(const PoseArray *TInitPtr = nullptr) {                       // :348
+    DPGO_SHIM_LOCK;
     rebindGraphIfReplaced();
     if (mPoseGraph->n() == 0) return;
     if (TInitPtr && TInitPtr->n() == num_poses()) {
@@ -146,6 +188,7 @@ class PGOAgent {
     mStatus.state = mState;
   }
   void initializeInGlobalFrame(const Pose &T_world_robot) {                    // :353, :358
+    DPGO_SHIM_LOCK;
     if (mState == PGOAgentState::WAIT_FOR_DATA) return;
     if (!YLift.has_value()) throw std::runtime_error("initializeInGlobalFrame: lifting matrix not set");
     double T[12];
@@ -155,6 +198,7 @@ class PGOAgent {
     mState = PGOAgentState::INITIALIZED;
     mStatus.state = mState;
     if (mID == 0) anchorFirstPose();
+    if (mParams.asynchronous) startOptimizationLoop(mParams.asynchronousOptimizationRate);   // (upstream starts it here too)
   }
   // use this robot's first pose as the global anchor (:360)
   void anchorFirstPose() {
@@ -162,10 +206,13 @@ class PGOAgent {
     if (getSharedPose(0, X0)) setGlobalAnchor(X0);
   }
   void setGlobalAnchor(const Matrix &M) {                                      // :939, :1466
+    DPGO_SHIM_LOCK;
     if (M.rows() != r || M.cols() != d + 1) throw std::invalid_argument("setGlobalAnchor: expected r x (d+1)");
     globalAnchor.emplace(LiftedPose(M));
   }
   virtual void reset() {                                                       // :223
+    endOptimizationLoop();
+    DPGO_SHIM_LOCK;
     check(dpgo_b200_reset(h_), "reset");
     mInstanceNumber++;
     mIterationNumber = 0;
@@ -188,6 +235,7 @@ class PGOAgent {
 
   // ---- the hot call
   bool iterate(bool doOptimization = true) {                                   // :160 (true), :1185 (false)
+    DPGO_SHIM_LOCK;
     const int rc = dpgo_b200_iterate(h_, doOptimization ? 1 : 0);
     if (rc != 0) return false;
     dpgo_b200_status s;
@@ -219,6 +267,7 @@ class PGOAgent {
 
   // ---- public poses (a9)
   bool getSharedPose(unsigned index, Matrix &Mout) {                           // :424
+    DPGO_SHIM_LOCK;
     if (mState != PGOAgentState::INITIALIZED || index >= num_poses()) return false;
     Mout = Matrix(r, d + 1);
     return dpgo_b200_get_pose(h_, 0, (int)index, Mout.data()) == 0;
@@ -229,6 +278,7 @@ class PGOAgent {
   void updateAuxNeighborPoses(unsigned neighborID, const PoseDict &poseDict) { putDict(neighborID, poseDict, 1); }    // :1278
   void setNeighborPoses(unsigned neighborID, const PoseDict &poseDict) { updateNeighborPoses(neighborID, poseDict); } // north-star alias
   Matrix getX() {                                                              // north-star alias: r x (d+1) n
+    DPGO_SHIM_LOCK;
     Matrix X(r, (size_t)(d + 1) * num_poses());
     check(dpgo_b200_get_x(h_, 0, X.data()), "getX");
     return X;
@@ -236,6 +286,7 @@ class PGOAgent {
 
   // ---- global-frame read-out (a11): T_i = (proj_SO(3)(Ya^T Yi), Ya^T (pi - pa)) with the anchor [Ya | pa]
   bool getTrajectoryInGlobalFrame(PoseArray &Trajectory) {                     // :624, :657
+    DPGO_SHIM_LOCK;
     if (!globalAnchor.has_value() || mState != PGOAgentState::INITIALIZED) return false;
     const Matrix X = getX();
     PoseArray T(d, num_poses());
@@ -244,12 +295,14 @@ class PGOAgent {
     return true;
   }
   bool getPoseInGlobalFrame(unsigned poseID, Matrix &T) {                      // :774-775, :807, :811
+    DPGO_SHIM_LOCK;
     Matrix Xi;
     if (!globalAnchor.has_value() || !getSharedPose(poseID, Xi)) return false;
     T = roundPose(Xi);
     return true;
   }
   bool getNeighborPoseInGlobalFrame(unsigned neighborID, unsigned poseID, Matrix &T) {   // :808, :812, :1395
+    DPGO_SHIM_LOCK;
     if (!globalAnchor.has_value()) return false;
     auto it = neighborPoseDict.find(PoseID(neighborID, poseID));
     if (it == neighborPoseDict.end()) return false;
@@ -259,6 +312,7 @@ class PGOAgent {
 
   // ---- status / termination (a10)
   PGOAgentStatus getStatus() {                                                 // :616
+    DPGO_SHIM_LOCK;
     mStatus.agentID = mID;
     mStatus.state = mState;
     mStatus.instanceNumber = mInstanceNumber;
@@ -266,6 +320,7 @@ class PGOAgent {
     return mStatus;
   }
   void setNeighborStatus(const PGOAgentStatus &status) {                       // :965
+    DPGO_SHIM_LOCK;
     mTeamStatus[status.agentID] = status;
     dpgo_b200_status s{(int)status.agentID, (int)status.state, (int)status.instanceNumber, (int)status.iterationNumber,
                        status.readyToTerminate ? 1 : 0, status.relativeChange};
@@ -289,6 +344,7 @@ class PGOAgent {
     return k;
   }
   bool shouldTerminate() {                                                                 // :208
+    DPGO_SHIM_LOCK;
     mStatus.iterationNumber = mIterationNumber;
     return dpgo_b200_should_terminate(h_) == 1;
   }
@@ -296,12 +352,14 @@ class PGOAgent {
   // ---- GNC (a8)
   bool shouldUpdateMeasurementWeights() { return dpgo_b200_should_update_measurement_weights(h_) == 1; }   // :210
   void updateMeasurementWeights() {                                                        // :1218
+    DPGO_SHIM_LOCK;
     check(dpgo_b200_update_measurement_weights(h_), "updateMeasurementWeights");
     pullWeights();
     mWeightUpdateCount = (unsigned)dpgo_b200_weight_update_count(h_);
     mRobustOptInnerIter = 0;
   }
   bool setMeasurementWeight(const PoseID &src_ID, const PoseID &dst_ID, double weight, bool fixed_weight = false) {  // :1341
+    DPGO_SHIM_LOCK;
     RelativeSEMeasurement *m = mPoseGraph->findMeasurement(src_ID, dst_ID);
     if (!m) return false;
     m->weight = weight;
@@ -310,6 +368,7 @@ class PGOAgent {
                                             (int)dst_ID.frame_id, weight, fixed_weight ? 1 : 0) == 0;
   }
   bool computeMeasurementResidual(const RelativeSEMeasurement &measurement, double *residual) {   // :1049
+    DPGO_SHIM_LOCK;
     return dpgo_b200_compute_measurement_residual(h_, (int)measurement.r1, (int)measurement.p1, (int)measurement.r2,
                                                   (int)measurement.p2, residual) == 0;
   }
@@ -330,7 +389,7 @@ class PGOAgent {
   std::map<unsigned, PGOAgentStatus> mTeamStatus;   // :196-199
   RobustCost mRobustCost;                           // :1050
   bool mPublishPublicPosesRequested = false;        // :109, :112
-  bool mPublishAsynchronousRequested = false;       // :120, :125
+  std::atomic<bool> mPublishAsynchronousRequested{false};   // :120, :125 (raised by the optimisation thread)
   std::optional<Matrix> YLift;                      // :1408, :1419, :1459
   std::optional<LiftedPose> globalAnchor;           // :426-429
   PoseDict neighborPoseDict, neighborAuxPoseDict;   // :1422
@@ -397,6 +456,7 @@ class PGOAgent {
     for (unsigned e = 0; e < ns; ++e) mPoseGraph->sharedLoopClosures()[e].weight = w[np + e];
   }
   bool getDict(PoseDict &map, unsigned nbr, int aux) {
+    DPGO_SHIM_LOCK;
     if (mState != PGOAgentState::INITIALIZED) return false;
     const int cap = dpgo_b200_num_shared_poses(h_, (int)nbr);
     if (cap < 0) return false;
@@ -414,6 +474,7 @@ class PGOAgent {
     return true;
   }
   void putDict(unsigned nbr, const PoseDict &dict, int aux) {
+    DPGO_SHIM_LOCK;
     std::vector<int> ids;
     std::vector<double> buf;
     ids.reserve(dict.size());
@@ -441,7 +502,12 @@ class PGOAgent {
 
   dpgo_b200_agent_t h_ = nullptr;
   const PoseGraph *mBoundGraph = nullptr;
+  std::recursive_mutex mMutex;
+  std::unique_ptr<std::thread> mOptimizationThread;
+  std::atomic<bool> mEndLoopRequested{false};
 };
+
+#undef DPGO_SHIM_LOCK
 
 }  // namespace DPGO
 #endif

@@ -7,6 +7,7 @@
 // Prints one line per fact the Python test checks and dumps every robot's X as raw doubles.
 //
 //   shim_harness <file.g2o> <num_robots> <max_iters> <rgd|rtr> <out_prefix> [device]
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -33,6 +34,8 @@ class WrapperAgent : public PGOAgent {  // plays PGOAgentROS
   unsigned numOdom() const { return mPoseGraph->numOdometry(); }
   unsigned numPrivateLCs() const { return mPoseGraph->numPrivateLoopClosures(); }
   bool accelerated() const { return mParams.acceleration; }
+  bool publishAsyncRequested() const { return mPublishAsynchronousRequested; }  // :120
+  void clearPublishAsyncRequest() { mPublishAsynchronousRequested = false; }    // :125
   std::set<unsigned> activeNeighbors() const { return mPoseGraph->activeNeighborIDs(); }   // :137
 };
 
@@ -64,6 +67,13 @@ int main(int argc, char **argv) {
       params.localOptimizationParams.RGD_use_preconditioner = true;
       params.acceleration = true;
       params.restartInterval = 50;
+    } else if (mode == "async") {  // launch/asapp_demo.launch:7-9: asynchronous, RGD 0.2 + preconditioner, no acceleration
+      params.asynchronous = true;
+      params.asynchronousOptimizationRate = 2000;
+      params.localOptimizationParams.method = ROptParameters::ROptMethod::RGD;
+      params.localOptimizationParams.RGD_stepsize = 0.2;
+      params.localOptimizationParams.RGD_use_preconditioner = true;
+      params.acceleration = false;
     } else {
       params.localOptimizationParams.method = ROptParameters::ROptMethod::RTR;
       params.localOptimizationParams.gradnorm_tol = 0.5;
@@ -127,6 +137,22 @@ int main(int argc, char **argv) {
     for (unsigned a = 1; a < N; ++a) agents[a]->setGlobalAnchor(anchor);
 
     int it = 0, terminated_at = -1;
+    if (mode == "async") {
+      // runOnceAsynchronous (:119-127): every robot's own thread optimises; the wrapper publishes when asked to.
+      // max_iters is the wall time in milliseconds here.
+      const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(max_iters);
+      long published = 0;
+      while (std::chrono::steady_clock::now() < t_end)
+        for (unsigned a = 0; a < N; ++a)
+          if (agents[a]->publishAsyncRequested()) {
+            agents[a]->clearPublishAsyncRequest();
+            publish(a);
+            ++published;
+          }
+      for (unsigned a = 0; a < N; ++a) agents[a]->endOptimizationLoop();
+      std::printf("async: %ld publications\n", published);
+      it = max_iters;
+    }
     for (; it < max_iters; ++it) {
       const unsigned sel = (unsigned)it % N;                                          // RoundRobin, :464-472
       for (unsigned a = 0; a < N; ++a)
