@@ -76,6 +76,8 @@ class Matrix {
         for (size_t r = 0; r < p_; ++r) M_(i_ + r, j_ + c) = B(r, c);
       return *this;
     }
+    Block &operator=(const Block &B) { return *this = static_cast<Matrix>(B); }   // element copy, like Eigen
+    Block(const Block &) = default;
     operator Matrix() const {
       Matrix B(p_, q_);
       for (size_t c = 0; c < q_; ++c)
@@ -84,6 +86,8 @@ class Matrix {
     }
     double operator()(size_t r, size_t c) const { return M_(i_ + r, j_ + c); }
     double operator()(size_t k) const { return q_ == 1 ? M_(i_ + k, j_) : M_(i_, j_ + k); }  // vector blocks
+    Matrix transpose() const { return static_cast<Matrix>(*this).transpose(); }
+    double norm() const { return static_cast<Matrix>(*this).norm(); }
 
    private:
     Matrix &M_;

@@ -109,6 +109,53 @@ inline Matrix projectToRotationGroup(const Matrix &M) {
   return X;
 }
 
+// Robust single-transform averaging used by the cross-robot initialisation (multirobot_initialization,
+// src/PGOAgentROSNode.cpp:120; robustInitMinInliers :220): every shared loop closure with an initialised neighbour
+// votes for this robot's world-frame transform; the candidate with the largest consensus set (rotation within rotTol
+// in Frobenius norm, translation within tranTol) wins and its consensus set is chordal-averaged.  Returns false when
+// the best consensus set has fewer than minInliers members.  Candidates are 3 x 4 [R | t].
+inline bool robustTransformAverage(const std::vector<Matrix> &candidates, double rotTol, double tranTol,
+                                   unsigned minInliers, Matrix &out, unsigned *numInliers = nullptr) {
+  size_t best = 0, bestCount = 0;
+  std::vector<size_t> bestSet;
+  for (size_t c = 0; c < candidates.size(); ++c) {
+    std::vector<size_t> set;
+    for (size_t k = 0; k < candidates.size(); ++k) {
+      const Matrix D = candidates[k] - candidates[c];
+      if (D.block(0, 0, 3, 3).norm() < rotTol && D.block(0, 3, 3, 1).norm() < tranTol) set.push_back(k);
+    }
+    if (set.size() > bestCount) {
+      best = c;
+      bestCount = set.size();
+      bestSet = set;
+    }
+  }
+  (void)best;
+  if (numInliers) *numInliers = (unsigned)bestCount;
+  if (bestCount == 0 || bestCount < minInliers) return false;
+  Matrix mean(3, 4);
+  for (size_t k : bestSet) mean = mean + candidates[k];
+  mean = (1.0 / (double)bestCount) * mean;
+  out = Matrix(3, 4);
+  out.block(0, 0, 3, 3) = projectToRotationGroup(mean.block(0, 0, 3, 3));
+  out.block(0, 3, 3, 1) = mean.block(0, 3, 3, 1);
+  return true;
+}
+// rigid transforms as 3 x 4 [R | t]
+inline Matrix se3Compose(const Matrix &A, const Matrix &B) {
+  Matrix C(3, 4);
+  C.block(0, 0, 3, 3) = A.block(0, 0, 3, 3) * B.block(0, 0, 3, 3);
+  C.block(0, 3, 3, 1) = A.block(0, 0, 3, 3) * B.block(0, 3, 3, 1) + A.block(0, 3, 3, 1);
+  return C;
+}
+inline Matrix se3Inverse(const Matrix &A) {
+  Matrix C(3, 4);
+  const Matrix Rt = A.block(0, 0, 3, 3).transpose();
+  C.block(0, 0, 3, 3) = Rt;
+  C.block(0, 3, 3, 1) = -1.0 * (Rt * A.block(0, 3, 3, 1));
+  return C;
+}
+
 // regularised lower incomplete gamma P(a, x) and the chi-square quantile built on it
 inline double gammaP(double a, double x) {
   if (x <= 0) return 0.0;

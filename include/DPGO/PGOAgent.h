@@ -490,6 +490,44 @@ class PGOAgent {
     if (!ids.empty())
       check(dpgo_b200_update_neighbor_poses(h_, (int)nbr, aux, ids.data(), buf.data(), (int)ids.size()),
             "updateNeighborPoses");
+    // cross-robot initialisation: a robot that only has its local trajectory places itself in the global frame from
+    // the first initialised neighbour whose public poses it hears (INITIALIZE round, src/PGOAgentROS.cpp:1091-1159)
+    if (!aux && mState == PGOAgentState::WAIT_FOR_INITIALIZATION && mParams.multirobotInitialization)
+      tryInitializeFromNeighbor(nbr);
+  }
+  void tryInitializeFromNeighbor(unsigned nbr) {
+    if (!YLift.has_value() || num_poses() == 0) return;
+    std::vector<double> Tl((size_t)12 * num_poses());
+    if (dpgo_b200_get_local_trajectory(h_, Tl.data()) != 0) return;
+    auto localPose = [&](size_t i) {
+      Matrix T(3, 4);
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 4; ++c) T(a, c) = Tl[i * 12 + a * 4 + c];
+      return T;
+    };
+    const Matrix YT = YLift.value().transpose();
+    std::vector<Matrix> candidates;
+    for (const auto &m : mPoseGraph->sharedLoopClosures()) {
+      Matrix meas(3, 4);
+      meas.block(0, 0, 3, 3) = m.R;
+      meas.block(0, 3, 3, 1) = m.t;
+      if (m.r1 == nbr && m.r2 == mID) {          // neighbour pose -> my pose
+        auto it = neighborPoseDict.find(PoseID(nbr, (unsigned)m.p1));
+        if (it == neighborPoseDict.end()) continue;
+        Matrix Tw = YT * it->second.getData();    // unlift: X = YLift T
+        Tw.block(0, 0, 3, 3) = projectToRotationGroup(Tw.block(0, 0, 3, 3));
+        candidates.push_back(se3Compose(se3Compose(Tw, meas), se3Inverse(localPose(m.p2))));
+      } else if (m.r2 == nbr && m.r1 == mID) {   // my pose -> neighbour pose
+        auto it = neighborPoseDict.find(PoseID(nbr, (unsigned)m.p2));
+        if (it == neighborPoseDict.end()) continue;
+        Matrix Tw = YT * it->second.getData();
+        Tw.block(0, 0, 3, 3) = projectToRotationGroup(Tw.block(0, 0, 3, 3));
+        candidates.push_back(se3Compose(se3Compose(Tw, se3Inverse(meas)), se3Inverse(localPose(m.p1))));
+      }
+    }
+    Matrix Tworld;
+    if (!robustTransformAverage(candidates, 0.2, 1.0, mParams.robustInitMinInliers, Tworld)) return;
+    initializeInGlobalFrame(Pose(Tworld));
   }
   Matrix roundPose(const Matrix &Xi) const {
     const Matrix Ya = globalAnchor.value().rotation(), pa = globalAnchor.value().translation();

@@ -44,7 +44,12 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "usage: shim_harness <file.g2o> <num_robots> <max_iters> <rgd|rtr> <out_prefix> [device]\n");
     return 2;
   }
-  const std::string file = argv[1], mode = argv[4], prefix = argv[5];
+  const std::string file = argv[1], prefix = argv[5];
+  std::string mode = argv[4];
+  // "<mode>_multi": no global-frame guess is handed over -- every robot initialises in its own frame and robots
+  // other than 0 place themselves in the global frame from their neighbours' public poses (multirobot_initialization)
+  const bool multi_init = mode.size() > 6 && mode.substr(mode.size() - 6) == "_multi";
+  if (multi_init) mode = mode.substr(0, mode.size() - 6);
   const unsigned N = (unsigned)std::atoi(argv[2]);
   const int max_iters = std::atoi(argv[3]);
   const int device = argc > 6 ? std::atoi(argv[6]) : 0;
@@ -61,6 +66,7 @@ int main(int argc, char **argv) {
     params.device = device;
     params.relChangeTol = 0.1;
     params.maxNumIters = 100000;
+    if (multi_init) params.robustInitMinInliers = 1;  // (the Python harness' alignment has no inlier floor either)
     if (mode == "rgd") {
       params.localOptimizationParams.method = ROptParameters::ROptMethod::RGD;
       params.localOptimizationParams.RGD_stepsize = 0.2;
@@ -112,8 +118,13 @@ int main(int argc, char **argv) {
         TInit.translation(i) = tg[a * per + i];
       }
       agents[a]->setLiftingMatrix(YLift);                                             // :928
-      agents[a]->initialize(&TInit);                                                  // :348
-      agents[a]->initializeInGlobalFrame(Pose(d));                                    // :353
+      if (multi_init) {
+        agents[a]->initialize();                                                      // :348 (local frame, odometry)
+        if (a == 0) agents[a]->initializeInGlobalFrame(Pose(d));                      // :353 (robot 0 only)
+      } else {
+        agents[a]->initialize(&TInit);                                                // :348
+        agents[a]->initializeInGlobalFrame(Pose(d));                                  // :353
+      }
       std::printf("robot %u: %u poses, %u odometry, %u private LC, %u shared LC, state %d\n", a, n, agents[a]->numOdom(),
                   agents[a]->numPrivateLCs(), agents[a]->numSharedLCs(), (int)agents[a]->state());
     }
@@ -130,6 +141,16 @@ int main(int argc, char **argv) {
       }
       agents[a]->clearPublishRequest();
     };
+    if (multi_init) {
+      // INITIALIZE rounds (:1091-1159): initialised robots publish; the others initialise themselves inside
+      // updateNeighborPoses; the leader re-issues INITIALIZE until everybody is in (:1133-1136)
+      for (unsigned round = 0; round < N; ++round)
+        for (unsigned a = 0; a < N; ++a)
+          if (agents[a]->state() == PGOAgentState::INITIALIZED) publish(a);
+      for (unsigned a = 0; a < N; ++a)
+        if (agents[a]->state() != PGOAgentState::INITIALIZED) throw std::runtime_error("cross-robot initialisation failed");
+      std::printf("multi-robot initialisation: all %u robots initialized\n", N);
+    }
     for (unsigned a = 0; a < N; ++a) publish(a);                                      // INITIALIZE, :1100
     // the leader's anchor reaches everyone (publishAnchor :412-441 -> setGlobalAnchor :939)
     Matrix anchor;

@@ -92,6 +92,33 @@ int main(int argc, char **argv) {
   CHECK(std::fabs((Rp * Rp.transpose() - Matrix::Identity(3, 3)).norm()) < 1e-12 && (Rp - meas[3].R).norm() < 2e-3);
   const Matrix Y = fixedStiefelVariable(3, 5);
   CHECK(std::fabs((Y.transpose() * Y - Matrix::Identity(3, 3)).norm()) < 1e-14);
+  // robust transform averaging (cross-robot initialisation): 7 consistent votes + 3 outliers
+  {
+    Matrix T0(3, 4);
+    T0.block(0, 0, 3, 3) = meas[5].R;
+    T0.block(0, 3, 3, 1) = tcol;
+    std::vector<Matrix> cands;
+    for (int k = 0; k < 7; ++k) {
+      Matrix C = T0;
+      C(0, 3) += 0.01 * (k - 3);
+      C(1, 0) += 1e-3 * (k - 3);
+      cands.push_back(C);
+    }
+    for (int k = 0; k < 3; ++k) {
+      Matrix C = T0;
+      C.block(0, 0, 3, 3) = meas[20 + k].R;
+      C(2, 3) += 5.0 + k;
+      cands.push_back(C);
+    }
+    Matrix avg;
+    unsigned inl = 0;
+    CHECK(robustTransformAverage(cands, 0.2, 1.0, 2, avg, &inl) && inl == 7);
+    CHECK((avg - T0).norm() < 5e-3);
+    const Matrix Ra = static_cast<const Matrix &>(avg).block(0, 0, 3, 3);
+    CHECK(std::fabs((Ra * Ra.transpose() - Matrix::Identity(3, 3)).norm()) < 1e-12);
+    CHECK(!robustTransformAverage(cands, 0.2, 1.0, 8, avg));   // not enough inliers
+    CHECK((se3Compose(T0, se3Inverse(T0)) - Matrix::Identity(3, 4)).norm() < 1e-12);
+  }
   std::printf("shim host checks ok\n");
   return 0;
 }

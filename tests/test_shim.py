@@ -146,3 +146,33 @@ def test_asynchronous_mode_through_the_shim(harness, tmp_path):
     assert len(its) == 4 and min(its) > 20, res.stdout
     assert "async:" in res.stdout and int(res.stdout.split("async:")[1].split()[0]) > 20
     assert c1 < 0.1 * c0, (c0, c1)
+
+
+@pytest.mark.gpu
+def test_cross_robot_initialization_through_the_shim(harness, tmp_path):
+    """multirobot_initialization (src/PGOAgentROSNode.cpp:120): only robot 0 is placed in the global frame; the others
+    start from their local odometry chain and initialise themselves inside updateNeighborPoses from the shared loop
+    closures with an initialised neighbour (robust transform averaging).  Same result as the Python harness'
+    alignment (datasets.robust_frame_alignment) fed to the oracle."""
+    from dpgo_ros_b200 import datasets
+    from oracle import binding as orc
+    prefix = str(tmp_path / "multi")
+    res = subprocess.run([harness, os.path.join(DATA, "smallGrid3D.g2o"), "2", "12", "rtr_multi", prefix],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "multi-robot initialisation: all 2 robots initialized" in res.stdout
+    pb = datasets.load_g2o_problem("smallGrid3D", 2)
+
+    def local(rid):
+        R, t = datasets.odometry_chain(pb.robot_measurements(rid), rid, pb.n[rid])
+        return np.concatenate([R, t[:, :, None]], axis=2)
+    pbl = datasets.with_local_initialization(pb, local)
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, acceleration=0, rel_change_tol=0.1, max_num_iters=100000)
+    oteam = orc.OracleTeam(pbl, **kw)
+    ores = oteam.run(12, stop_on_terminate=True)
+    line = [l for l in res.stdout.splitlines() if l.startswith("iterations")][0].split()
+    assert int(line[1]) == ores.iterations
+    for rid in range(2):
+        X = np.fromfile(f"{prefix}_X{rid}.bin").reshape((5, -1), order="F")
+        Xo = oteam.get_x(rid)
+        assert np.linalg.norm(X - Xo) / np.linalg.norm(Xo) < 1e-6, rid
