@@ -109,6 +109,10 @@ class PGOAgent:
     def iterate(self, doOptimization: bool = True) -> None:
         check(self.L.dpgo_b200_iterate(self.h, int(doOptimization)), "iterate")
 
+    def setIterationNumber(self, iteration: int) -> None:
+        """What the RECOVER handler does to mIterationNumber (src/PGOAgentROS.cpp:1196)."""
+        check(self.L.dpgo_b200_set_iteration_number(self.h, int(iteration)), "setIterationNumber")
+
     def initializeChordal(self) -> np.ndarray:
         """Chordal local initialisation on the device; returns the local trajectory [n, 3, 4]."""
         check(self.L.dpgo_b200_initialize_chordal(self.h), "initializeChordal")

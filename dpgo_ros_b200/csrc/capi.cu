@@ -204,6 +204,20 @@ int dpgo_b200_get_x(dpgo_b200_agent_t h, int which, double *out) {
   cuda_check(cudaMemcpy(out, b.p, sizeof(double) * a->r * 4 * a->n, cudaMemcpyDeviceToHost), "D2H X");
   API_END
 }
+int dpgo_b200_set_iteration_number(dpgo_b200_agent_t h, int iteration) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (iteration < 0) fail(DPGO_B200_ERR_INVALID, "iteration number must be non-negative");
+  if (a->state == 2) {
+    cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+    a->materialize_lookahead();  // speculated steps belong to the old numbering (restart iterations depend on it)
+  }
+  a->drop_lookahead();
+  a->iter = iteration;
+  a->status.iteration_number = iteration;
+  if (a->team) a->team->ctl.iter = iteration;
+  API_END
+}
 int dpgo_b200_get_pose(dpgo_b200_agent_t h, int which, int index, double *out) {
   API_BEGIN
   Agent *a = A(h);

@@ -215,7 +215,7 @@ class PGOAgent {
     DPGO_SHIM_LOCK;
     check(dpgo_b200_reset(h_), "reset");
     mInstanceNumber++;
-    mIterationNumber = 0;
+    mIterationNumber = mLastIterationSeen = 0;
     mWeightUpdateCount = 0;
     mRobustOptInnerIter = 0;
     mState = PGOAgentState::WAIT_FOR_DATA;
@@ -236,11 +236,13 @@ class PGOAgent {
   // ---- the hot call
   bool iterate(bool doOptimization = true) {                                   // :160 (true), :1185 (false)
     DPGO_SHIM_LOCK;
+    if (mIterationNumber != mLastIterationSeen)   // the wrapper rewound mIterationNumber (RECOVER, :1196)
+      dpgo_b200_set_iteration_number(h_, (int)mIterationNumber);
     const int rc = dpgo_b200_iterate(h_, doOptimization ? 1 : 0);
     if (rc != 0) return false;
     dpgo_b200_status s;
     dpgo_b200_get_status(h_, &s);
-    mIterationNumber = (unsigned)s.iteration_number;
+    mIterationNumber = mLastIterationSeen = (unsigned)s.iteration_number;
     mStatus.iterationNumber = mIterationNumber;
     mStatus.instanceNumber = mInstanceNumber;
     mStatus.state = mState;
@@ -540,6 +542,7 @@ class PGOAgent {
 
   dpgo_b200_agent_t h_ = nullptr;
   const PoseGraph *mBoundGraph = nullptr;
+  unsigned mLastIterationSeen = 0;
   std::recursive_mutex mMutex;
   std::unique_ptr<std::thread> mOptimizationThread;
   std::atomic<bool> mEndLoopRequested{false};

@@ -97,6 +97,8 @@ int dpgo_b200_add_measurements(dpgo_b200_agent_t a, int m, const int *r1, const 
                                const double *tau, const double *weight, const unsigned char *fixed);
 int dpgo_b200_num_poses(dpgo_b200_agent_t a);                   /* num_poses(), :285 */
 int dpgo_b200_iteration_number(dpgo_b200_agent_t a);            /* iteration_number(), :139 */
+/* the RECOVER handler rewinds the protected member mIterationNumber (:1196); the shim forwards the new value */
+int dpgo_b200_set_iteration_number(dpgo_b200_agent_t a, int iteration);
 int dpgo_b200_num_neighbors(dpgo_b200_agent_t a);               /* getNeighbors(), :663 */
 int dpgo_b200_get_neighbors(dpgo_b200_agent_t a, int *ids, int cap);
 /* PoseGraph counters read at :343-345 */

@@ -98,6 +98,7 @@ def lib():
     L.orc_exchange_all.argtypes = [C.c_void_p]
     L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
     L.orc_initialize_chordal.argtypes = [C.c_void_p, C.c_int]
+    L.orc_set_iteration_number.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_get_local_trajectory.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.orc_run_parallel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
     L.orc_agent_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -195,6 +196,9 @@ class OracleTeam:
         else:
             T = _f64(T_local)
             _chk(self.L.orc_initialize(self.h, rid, _dp(T)), "initialize")
+
+    def set_iteration_number(self, rid, it):
+        _chk(self.L.orc_set_iteration_number(self.h, rid, int(it)), "set_iteration_number")
 
     def initialize_chordal(self, rid):
         """Chordal local initialisation (Agent::initializeChordal); returns the local trajectory [n, 3, 4]."""

@@ -240,6 +240,7 @@ class Agent {
   const Params &params() const { return params_; }
   int numPoses() const { return pg_->n(); }
   int iterationNumber() const { return iter_; }
+  void setIterationNumber(int it) { iter_ = it; }  // what the RECOVER handler does to mIterationNumber (:1196)
   AgentState state() const { return state_; }
   PoseGraph &poseGraph() { return *pg_; }
 

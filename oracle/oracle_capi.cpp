@@ -142,6 +142,11 @@ int orc_initialize(void *t, int agent, const double *T_local) {
   ORC_CATCH
 }
 
+int orc_set_iteration_number(void *t, int agent, int it) {
+  ORC_TRY((Team *)t)->agent(agent).setIterationNumber(it);
+  ORC_CATCH
+}
+
 int orc_initialize_chordal(void *t, int agent) {
   ORC_TRY((Team *)t)->agent(agent).initializeChordal();
   ORC_CATCH

@@ -118,3 +118,37 @@ def test_chordal_initialization_matches_oracle(name, robots):
         assert res.iterations == ores.iterations and res.terminated
         for rid in range(robots):
             assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6, rid
+
+
+def test_recover_rewinds_the_iteration_number():
+    """RECOVER (src/PGOAgentROS.cpp:1191-1209) writes mIterationNumber: the restart schedule of the acceleration follows
+    the new numbering, and steps speculated under the old one are discarded."""
+    pb = datasets.load_g2o_problem("sphere2500", 8)
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=7,
+              rel_change_tol=0.0, max_num_iters=10 ** 6)
+    oteam = orc.OracleTeam(pb, **kw)
+    _, agents = gpu.make_team(pb, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=True)
+
+    def steps(first, count):
+        for it in range(first, first + count):
+            sel = it % 8
+            for a in agents:
+                if a.id != sel:
+                    a.iterate(False)
+                    oteam.iterate(a.id, False)
+            gpu.exchange_host(agents, accel=True, only=[a.id for a in agents if a.id != sel])
+            oteam.exchange_all()
+            agents[sel].iterate(True)
+            oteam.iterate(sel, True)
+            gpu.exchange_host(agents, accel=True, only=[sel])
+            oteam.exchange_all()
+
+    steps(0, 11)
+    for a in agents:
+        a.setIterationNumber(3)
+        oteam.set_iteration_number(a.id, 3)
+    steps(3, 10)
+    for a in agents:
+        assert a.iteration_number() == 13
+        assert rel(a.getX(), oteam.get_x(a.id)) < 1e-9, a.id
