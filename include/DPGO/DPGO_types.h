@@ -24,7 +24,17 @@
 #include <utility>
 #include <vector>
 
+// upstream's headers pull glog in: src/utils.cpp:284 uses CHECK with no include of its own
+#if defined(__has_include)
+#if __has_include(<glog/logging.h>)
+#include <glog/logging.h>
+#endif
+#endif
+
 namespace DPGO {
+
+// the wrapper says `using namespace DPGO;` and then writes `vector<...>` unqualified (src/PGOAgentROS.cpp:288)
+using std::vector;
 
 class Matrix {
  public:
@@ -307,7 +317,7 @@ struct ROptParameters {
   double RGD_stepsize = 1e-3;
   bool RGD_use_preconditioner = true;
   double RTR_initial_radius = 100;
-  unsigned RTR_iterations = 3, RTR_tCG_iterations = 50;
+  int RTR_iterations = 3, RTR_tCG_iterations = 50;   // int: read with ros::param::get (src/PGOAgentROSNode.cpp:98-99)
 };
 
 // mLocalOptResult (src/PGOAgentROS.cpp:169-172)

@@ -40,6 +40,7 @@
 #include "DPGO/DPGO_robust.h"
 #include "DPGO/DPGO_types.h"
 #include "DPGO/DPGO_utils.h"
+#include "DPGO/PGOLogger.h"
 #include "DPGO/PoseGraph.h"
 #include "DPGO/RelativeSEMeasurement.h"
 #include "dpgo_b200.h"
@@ -58,8 +59,8 @@ class PGOAgentParameters {
   bool acceleration = false;                       // :126
   unsigned restartInterval = 30;                   // :129
   RobustCostParameters robustCostParams;           // :178-211
-  unsigned robustOptNumWeightUpdates = 4;          // :212
-  unsigned robustOptNumResets = 0;                 // :213
+  int robustOptNumWeightUpdates = 4;               // :212 (int: read with ros::param::get)
+  int robustOptNumResets = 0;                      // :213
   unsigned robustOptInnerIters = 30;               // :217
   double robustOptMinConvergenceRatio = 0.8;       // :214
   unsigned robustInitMinInliers = 2;               // :220
@@ -92,6 +93,10 @@ class PGOAgent {
         mRobustCost(params.robustCostParams), mTeamRobotActive(params.numRobots, true) {
     mPoseGraph = std::make_shared<PoseGraph>(mID, r, d);
     createHandle();
+    // Robot 0 owns the lifting matrix of the team: the wrapper only ever READS it from the leader (getLiftingMatrix,
+    // src/PGOAgentROS.cpp:404) and broadcasts it to the others (liftingMatrixCallback -> setLiftingMatrix, :928), so
+    // the base class has to create it.  Upstream draws a random point of St(d, r); a fixed one keeps runs reproducible.
+    if (mID == 0) setLiftingMatrix(fixedStiefelVariable(d, r));
   }
   virtual ~PGOAgent() {
     endOptimizationLoop();
@@ -143,15 +148,7 @@ class PGOAgent {
     rebindGraphIfReplaced();
     if (mState != PGOAgentState::WAIT_FOR_DATA) return;  // measurements are fixed once a round has started
     if (!mPoseGraph->addMeasurement(m)) return;
-    const int r1 = (int)m.r1, p1 = (int)m.p1, r2 = (int)m.r2, p2 = (int)m.p2;
-    double Rrm[9], tv[3];
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j) Rrm[i * 3 + j] = m.R(i, j);
-      tv[i] = m.t(i, 0);
-    }
-    const unsigned char fixed = m.fixedWeight ? 1 : 0;
-    check(dpgo_b200_add_measurements(h_, 1, &r1, &p1, &r2, &p2, Rrm, tv, &m.kappa, &m.tau, &m.weight, &fixed),
-          "addMeasurement");
+    uploadMeasurement(m);
   }
 
   // ---- lifecycle
@@ -227,9 +224,11 @@ class PGOAgent {
     globalAnchor.reset();
     neighborPoseDict.clear();
     neighborAuxPoseDict.clear();
-    std::fill(mTeamRobotActive.begin(), mTeamRobotActive.end(), true);
-    // the wrapper keeps the lifting matrix across rounds (it is re-broadcast); measurements go with the graph
-    mPoseGraph = std::make_shared<PoseGraph>(mID, r, d);
+    for (unsigned id = 0; id < mTeamRobotActive.size(); ++id) setRobotActive(id, true);
+    // The lifting matrix and the MEASUREMENTS survive a reset: the wrapper's next round only adds what
+    // hasMeasurement() does not know yet (src/PGOAgentROS.cpp:268-280) and relies on the weights it fixed in the
+    // TERMINATE handler (m->weight = 0, m->fixedWeight = true, :1051-1054) still being there; it swaps in a fresh
+    // PoseGraph itself when it wants a clean slate (completeReset, :237).  The device agent is rebuilt from the mirror.
     recreateHandle();
   }
 
@@ -340,8 +339,8 @@ class PGOAgent {
     auto it = mTeamStatus.find(id);
     return it != mTeamStatus.end() && it->second.state == PGOAgentState::INITIALIZED;
   }
-  unsigned numActiveRobots() const {                                                       // :554, :885
-    unsigned k = 0;
+  size_t numActiveRobots() const {                                                       // :554, :885
+    size_t k = 0;
     for (bool b : mTeamRobotActive) k += b;
     return k;
   }
@@ -442,6 +441,20 @@ class PGOAgent {
     h_ = nullptr;
     createHandle();
     if (YLift.has_value()) dpgo_b200_set_lifting_matrix(h_, YLift.value().data());
+    // measurements already in the host mirror (kept across reset(), or pre-loaded into a graph the wrapper swapped in)
+    for (auto *vec : {&mPoseGraph->odometry(), &mPoseGraph->privateLoopClosures(), &mPoseGraph->sharedLoopClosures()})
+      for (const auto &m : *vec) uploadMeasurement(m);
+  }
+  void uploadMeasurement(const RelativeSEMeasurement &m) {
+    const int r1 = (int)m.r1, p1 = (int)m.p1, r2 = (int)m.r2, p2 = (int)m.p2;
+    double Rrm[9], tv[3];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rrm[i * 3 + j] = m.R(i, j);
+      tv[i] = m.t(i, 0);
+    }
+    const unsigned char fixed = m.fixedWeight ? 1 : 0;
+    check(dpgo_b200_add_measurements(h_, 1, &r1, &p1, &r2, &p2, Rrm, tv, &m.kappa, &m.tau, &m.weight, &fixed),
+          "addMeasurement");
   }
   // the wrapper swaps in a fresh PoseGraph on a complete reset (:237): follow it with a fresh device agent
   void rebindGraphIfReplaced() {

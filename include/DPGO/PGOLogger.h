@@ -15,8 +15,8 @@ namespace DPGO {
 class PGOLogger {
  public:
   explicit PGOLogger(std::string logDir = "") : logDirectory(std::move(logDir)) {}
-  // load_weight = false: weights come back as 1 (the publisher calls it that way)
-  std::vector<RelativeSEMeasurement> loadMeasurements(const std::string &filename, bool load_weight = false) {
+  // load_weight = false: weights come back as 1 (the publisher calls it that way, and statically)
+  static std::vector<RelativeSEMeasurement> loadMeasurements(const std::string &filename, bool load_weight = false) {
     std::vector<RelativeSEMeasurement> out;
     std::ifstream in(filename);
     if (!in) return out;

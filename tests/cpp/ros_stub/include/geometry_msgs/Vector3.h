@@ -1,0 +1,1 @@
+#include "geometry_msgs/Point.h"

@@ -1,0 +1,210 @@
+"""The reference's OWN wrapper, unmodified, on top of the DPGO:: shim ("drops on unchanged").
+
+oracle/Makefile.ref compiles src/utils.cpp, src/PGOAgentROS.cpp, src/PGOAgentROSNode.cpp, src/PGODatasetPublisherNode.cpp and
+tests/testUtils.cpp from where they lie under /root/reference against include/DPGO (the shim) and the single-process ROS
+stand-in of tests/cpp/ros_stub (roscpp / messages / tf / glog / gtest are not in this image; message structs are generated
+from the reference's msg/*.msg at build time).  The binaries land in oracle/_ref/ (git-ignored, travels to the GPU box):
+
+  dpgo_ros_test_utils     the reference's unit test (tests/testUtils.cpp) -- its three cases pin the value types at the boundary
+  dpgo_ros_inproc_oracle  launch/dpgo_demo.launch / dpgo_gnc_demo.launch in one process; DPGO:: backed by the CPU oracle
+  dpgo_ros_inproc_b200    the same, DPGO:: backed by libdpgo_b200.so (the product; needs a B200)
+
+What is checked:
+  * CPU: the wrapper's real control flow (REQUEST_POSE_GRAPH -> INITIALIZE -> UPDATE ... -> TERMINATE, src/PGOAgentROS.cpp:
+    1000-1253) produces exactly the iteration counts and final cost of the oracle's in-process restatement of that
+    schedule (oracle Team::run) -- this pins the restatement every other parity test leans on;
+  * GPU: the wrapper on the CUDA library terminates at the same iteration as the wrapper on the oracle and publishes the
+    same trajectories (<= 1e-6 relative, the north-star tolerance).
+The file sorts last on purpose: it is the longest-reaching test and should not mask the unit-level parity tests under -x.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from dpgo_ros_b200 import datasets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "oracle", "_ref")
+BIN_ORACLE = os.path.join(OUT, "dpgo_ros_inproc_oracle")
+BIN_B200 = os.path.join(OUT, "dpgo_ros_inproc_b200")
+BIN_TEST = os.path.join(OUT, "dpgo_ros_test_utils")
+DATA = os.path.join(ROOT, "data")
+
+
+@pytest.fixture(scope="module")
+def ref_build():
+    """Build oracle/_ref from the reference's sources when they are present (this container); on the GPU box the
+    prebuilt binaries travel with the snapshot and /root/reference does not exist."""
+    if os.path.isdir(os.path.join(REF, "src")):
+        from dpgo_ros_b200 import capi
+        capi.build()   # dpgo_ros_inproc_b200 links libdpgo_b200.so
+        subprocess.run(["make", "-s", "-f", os.path.join(ROOT, "oracle", "Makefile.ref"), "-j8"], check=True, cwd=ROOT)
+    for b in (BIN_ORACLE, BIN_B200, BIN_TEST):
+        if not os.path.exists(b):
+            pytest.skip("oracle/_ref is not built and /root/reference is not available to build it from")
+    return OUT
+
+
+def run_wrapper(binary, tmp_path, tag, robots, preset, g2o=None, measurements=None, rounds=1, params=(), timeout=600):
+    out = os.path.join(str(tmp_path), tag + ".json")
+    cmd = [binary, "--robots", str(robots), "--preset", preset, "--out", out, "--log", "0", "--rounds", str(rounds)]
+    cmd += ["--g2o", os.path.join(DATA, g2o)] if g2o else ["--measurements", os.path.join(DATA, measurements)]
+    for kv in params:
+        cmd += ["--param", kv]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    assert p.returncode == 0, f"{os.path.basename(binary)} failed ({p.returncode}):\n{p.stderr[-3000:]}"
+    with open(out) as f:
+        return json.load(f)
+
+
+def ros_message_path_problem(name, robots):
+    """What the agents hold after the pose graph crossed the ROS messages: kappa = 10000, tau = 100 for every edge and
+    odometry marked as a known inlier (src/utils.cpp:141-149)."""
+    pb = datasets.load_g2o_problem(name, robots)
+    m = pb.meas
+    m.kappa[:] = 10000.0
+    m.tau[:] = 100.0
+    m.fixed[:] = ((m.r1 == m.r2) & (m.p1 + 1 == m.p2)).astype(np.uint8)
+    return pb
+
+
+def trajectories(result):
+    R, t = {}, {}
+    for rb in result["robots"]:
+        a = np.array(rb["trajectory"]).reshape(-1, 7)
+        t[rb["id"]] = a[:, :3]
+        R[rb["id"]] = np.stack([datasets.quat_to_rot(q) for q in a[:, 3:7]])
+    return R, t
+
+
+def trajectory_cost(pb, result):
+    """2 f over every edge of the team graph at the SE(3) trajectories the wrapper published."""
+    R, t = trajectories(result)
+    m = pb.meas
+    c = 0.0
+    for e in range(len(m)):
+        Ri, ti = R[int(m.r1[e])][int(m.p1[e])], t[int(m.r1[e])][int(m.p1[e])]
+        Rj, tj = R[int(m.r2[e])][int(m.p2[e])], t[int(m.r2[e])][int(m.p2[e])]
+        c += m.weight[e] * (m.kappa[e] * np.sum((Rj - Ri @ m.R[e]) ** 2) + m.tau[e] * np.sum((tj - ti - Ri @ m.t[e]) ** 2))
+    return c
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU
+# ----------------------------------------------------------------------------------------------------------------------
+def test_reference_sources_compile_unmodified_against_the_shim(ref_build):
+    """The build itself is the check: four wrapper sources + the unit test, no patch, no -D tricks beyond renaming the
+    two main() functions so that they can share a process."""
+    for b in (BIN_ORACLE, BIN_B200, BIN_TEST):
+        assert os.access(b, os.X_OK)
+    ldd = subprocess.run(["ldd", BIN_B200], stdout=subprocess.PIPE, text=True).stdout
+    assert "libdpgo_b200.so" in ldd, ldd                      # the product library, not the oracle
+    assert "libdpgo_b200.so" not in subprocess.run(["ldd", BIN_ORACLE], stdout=subprocess.PIPE, text=True).stdout
+
+
+def test_reference_unit_test_passes_unmodified(ref_build):
+    """tests/testUtils.cpp:16-70 -- the only test the reference ships: MatrixMsg round trip, PoseGraphEdge round trip,
+    Status round trip + the PGOAgentState enum values."""
+    p = subprocess.run([BIN_TEST], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert p.returncode == 0, p.stdout
+    assert "3 tests ran, 0 failed" in p.stdout, p.stdout
+
+
+@pytest.mark.parametrize("name,robots,accel", [("smallGrid3D", 2, False), ("sphere2500", 5, False), ("sphere2500", 5, True)])
+def test_wrapper_control_flow_pins_the_oracle_schedule(ref_build, tmp_path, name, robots, accel):
+    """launch/dpgo_demo.launch (5 robots on sphere2500 is the README demo, README.md:30-44) through the real wrapper on
+    the oracle back end, against the oracle's own restatement of the schedule (Team::run) on the same problem with the
+    same Chordal + cross-robot initialisation: identical iteration count, identical final cost."""
+    from oracle import binding as orc
+
+    res = run_wrapper(BIN_ORACLE, tmp_path, "w", robots, "dpgo_demo", g2o=name + ".g2o",
+                      params=["acceleration=" + ("true" if accel else "false")])
+    assert not res["timed_out"] and "oracle" in res["backend"]
+    assert len(res["round_iterations"]) == 1 and res["commands"]["2"] == 1    # one TERMINATE
+
+    pb = ros_message_path_problem(name, robots)
+    o = orc.OracleTeam(pb, r=5, initialize=False)
+    for rid in range(robots):
+        o.initialize_chordal(rid)
+    po = datasets.with_local_initialization(pb, lambda rid: o.local_trajectory(rid))
+    team = orc.OracleTeam(po, r=5, method=0, rtr_iterations=3, rtr_tcg_iterations=50, gradnorm_tol=0.5, rel_change_tol=0.2,
+                          max_num_iters=1000, acceleration=int(accel), restart_interval=50)
+    tres = team.run(1000, stop_on_terminate=True)
+    assert tres.terminated
+    assert res["round_iterations"] == [tres.iterations]
+    assert all(rb["max_iteration"] == tres.iterations for rb in res["robots"])
+    # the wrapper publishes ROUNDED poses (projection of Ya^T Yi to SO(3)); the team cost is that of the rank-5 iterate:
+    # equal to 13 digits on sphere2500 (iterate already of rank 3), to 1e-6 on smallGrid3D after its 3 iterations
+    c_wrapper, c_team = trajectory_cost(pb, res), team.global_cost()
+    assert abs(c_wrapper - c_team) <= 1e-5 * c_team, (c_wrapper, c_team)
+
+
+def test_wrapper_gnc_demo_pins_the_oracle_gnc_schedule(ref_build, tmp_path):
+    """launch/dpgo_gnc_demo.launch (BASELINE config 4: tunnels, 8 robots, GNC_TLS, 3 weight updates, 3 resets, 400 inner
+    iterations per stage) through the real wrapper: same number of iterations and weight updates as oracle Team::run."""
+    from oracle import binding as orc
+
+    res = run_wrapper(BIN_ORACLE, tmp_path, "g", 8, "gnc_demo", measurements="tunnels")
+    assert not res["timed_out"]
+    assert res["commands"]["5"] == 3                      # UPDATE_WEIGHT
+    assert all(rb["weights_msgs"] > 0 for rb in res["robots"][:-1]) and res["robots"][-1]["weights_msgs"] == 0   # owner = lower ID
+
+    team = orc.OracleTeam(datasets.load_tunnels_problem(), r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2, cost_type=5,
+                          gnc_barc=3.0, gnc_mu_step=2.0, gnc_init_mu=1e-5, robust_opt_num_weight_updates=3,
+                          robust_opt_num_resets=3, robust_opt_inner_iters=400, robust_opt_min_convergence_ratio=0.8,
+                          max_num_iters=1598)
+    tres = team.run(2000, stop_on_terminate=True)
+    assert tres.terminated and tres.weight_updates == 3
+    assert res["round_iterations"] == [tres.iterations]
+
+
+def test_wrapper_second_round_reuses_the_measurements(ref_build, tmp_path):
+    """After TERMINATE the wrapper resets and, 10 s later, the leader opens a new round (src/PGOAgentROS.cpp:1381-1385):
+    the pose graph must have survived PGOAgent::reset() (requestPoseGraph only adds what hasMeasurement() does not know,
+    :268-280) and the second round must reproduce the first."""
+    res = run_wrapper(BIN_ORACLE, tmp_path, "r2", 2, "dpgo_demo", g2o="smallGrid3D.g2o", rounds=2)
+    assert not res["timed_out"]
+    assert res["round_iterations"] == [3, 3]
+    assert res["commands"]["0"] == 2                      # two REQUEST_POSE_GRAPH rounds
+    assert [rb["trajectories"] for rb in res["robots"]] == [2, 2]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU: the same wrapper binary on libdpgo_b200.so
+# ----------------------------------------------------------------------------------------------------------------------
+def _compare(gpu_res, cpu_res, tol):
+    assert "sm_100a" in gpu_res["backend"] and gpu_res["kernel_launches"] > 0, gpu_res["backend"]
+    assert not gpu_res["timed_out"]
+    assert gpu_res["round_iterations"] == cpu_res["round_iterations"]
+    Rg, tg = trajectories(gpu_res)
+    Rc, tc = trajectories(cpu_res)
+    for rid in Rc:
+        assert Rg[rid].shape == Rc[rid].shape
+        num = np.sqrt(np.sum((Rg[rid] - Rc[rid]) ** 2) + np.sum((tg[rid] - tc[rid]) ** 2))
+        den = np.sqrt(np.sum(Rc[rid] ** 2) + np.sum(tc[rid] ** 2))
+        assert num <= tol * den, (rid, num / den)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,robots,accel", [("smallGrid3D", 2, False), ("sphere2500", 5, True)])
+def test_wrapper_on_b200_matches_wrapper_on_oracle(ref_build, tmp_path, name, robots, accel):
+    """BASELINE config 1 / the README demo through the reference's wrapper with the CUDA library underneath."""
+    params = ["acceleration=" + ("true" if accel else "false")]
+    g = run_wrapper(BIN_B200, tmp_path, "gpu", robots, "dpgo_demo", g2o=name + ".g2o", params=params)
+    c = run_wrapper(BIN_ORACLE, tmp_path, "cpu", robots, "dpgo_demo", g2o=name + ".g2o", params=params)
+    _compare(g, c, 1e-6)
+
+
+@pytest.mark.gpu
+def test_wrapper_gnc_demo_on_b200(ref_build, tmp_path):
+    """BASELINE config 4 through the wrapper on the GPU: three weight updates, termination, and -- RTR trajectories over
+    hundreds of iterations being sensitive to rounding -- an iteration count within 5 % of the oracle run."""
+    g = run_wrapper(BIN_B200, tmp_path, "gpu", 8, "gnc_demo", measurements="tunnels")
+    c = run_wrapper(BIN_ORACLE, tmp_path, "cpu", 8, "gnc_demo", measurements="tunnels")
+    assert "sm_100a" in g["backend"] and g["kernel_launches"] > 0
+    assert not g["timed_out"] and g["commands"]["5"] == 3 and g["commands"]["2"] == 1
+    assert abs(g["round_iterations"][0] - c["round_iterations"][0]) <= 0.05 * c["round_iterations"][0], (g["round_iterations"], c["round_iterations"])
