@@ -16,6 +16,7 @@
 #ifndef ROS_STUB_ROS_H
 #define ROS_STUB_ROS_H
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdint>
@@ -50,6 +51,7 @@ struct Node {
   std::vector<std::shared_ptr<TimerRec>> timers;
   double wake = 0;
   bool alive = false;
+  std::condition_variable cv;                 // signalled when this node gets the processor
 };
 struct SubRec {
   Node *node;
@@ -63,7 +65,6 @@ struct ServiceRec {
 };
 struct World {
   std::mutex mu;
-  std::condition_variable cv;
   double now = 0;
   int current = -1;          // id of the node that holds the processor
   bool shutdown = false;
@@ -72,6 +73,8 @@ struct World {
   std::map<std::string, ServiceRec> services;
   std::map<std::string, unsigned long> published;   // messages per topic (statistics)
   int log_level = 1;         // 0 silent, 1 warnings + errors, 2 everything
+  // wall-clock instant at which the message now being delivered was published (for monitors that time a run)
+  std::chrono::steady_clock::time_point delivering_published_at;
 };
 inline World &world() {
   static World w;
@@ -105,8 +108,8 @@ inline void dispatch_locked(World &w) {
   } else {
     if (best->wake > w.now) w.now = best->wake;
     w.current = best->id;
+    best->cv.notify_one();
   }
-  w.cv.notify_all();
 }
 // called first thing by a node's thread: wait for the processor
 inline void enter(Node *n) {
@@ -114,7 +117,7 @@ inline void enter(Node *n) {
   World &w = world();
   std::unique_lock<std::mutex> lk(w.mu);
   if (w.current < 0) dispatch_locked(w);
-  w.cv.wait(lk, [&] { return w.current == n->id; });
+  n->cv.wait(lk, [&] { return w.current == n->id; });
 }
 // called last thing by a node's thread
 inline void leave() {
@@ -131,7 +134,7 @@ inline void sleep_for(double seconds) {
   std::unique_lock<std::mutex> lk(w.mu);
   n->wake = w.now + (seconds > 0 ? seconds : 0);
   dispatch_locked(w);
-  w.cv.wait(lk, [&] { return w.current == n->id; });
+  if (w.current != n->id) n->cv.wait(lk, [&] { return w.current == n->id; });
 }
 inline std::string resolve(const std::string &ns, const std::string &name) {
   if (!name.empty() && name[0] == '/') return name;
@@ -217,12 +220,14 @@ class Publisher {
     auto it = w.subs.find(topic_);
     if (it == w.subs.end()) return;
     std::shared_ptr<const void> copy = std::make_shared<const M>(msg);
+    const auto published_at = std::chrono::steady_clock::now();
     for (auto &s : it->second) {
       if (!*s.active || !s.node->alive) continue;
       if (s.type != type_) throw std::logic_error("ros stub: subscriber / publisher type mismatch on " + topic_);
       auto deliver = s.deliver;
       auto active = s.active;
-      s.node->queue.push_back([deliver, active, copy] {
+      s.node->queue.push_back([deliver, active, copy, published_at] {
+        sim::world().delivering_published_at = published_at;
         if (*active) deliver(copy);
       });
     }
@@ -425,7 +430,7 @@ inline void spinOnce() {
 inline void spin() {
   while (ok()) {
     spinOnce();
-    sim::sleep_for(0.001);
+    sim::sleep_for(0.01);
   }
 }
 }  // namespace ros

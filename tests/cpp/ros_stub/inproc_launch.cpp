@@ -24,6 +24,7 @@
 
 #include "dpgo_b200.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -139,6 +140,9 @@ class Monitor {
       subs_.push_back(nh.subscribe<dpgo_ros::Command>(prefix + "command", 100, [this](const dpgo_ros::CommandConstPtr &m) {
         commands_[m->command]++;
         if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration > last_update_iteration_) last_update_iteration_ = m->executing_iteration;
+        if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration == 1) round_start_ = ros::sim::world().delivering_published_at;
+        if (m->command == dpgo_ros::Command::TERMINATE)
+          round_wall_seconds_.push_back(std::chrono::duration<double>(ros::sim::world().delivering_published_at - round_start_).count());
         if (m->command == dpgo_ros::Command::TERMINATE) {
           terminate_time_ = ros::sim::world().now;
           round_iterations_.push_back(last_update_iteration_);
@@ -162,6 +166,10 @@ class Monitor {
       << ",\n  \"timed_out\": " << (timed_out ? "true" : "false") << ",\n  \"sim_seconds\": " << ros::sim::world().now
       << ",\n  \"terminate_sim_seconds\": " << terminate_time_ << ",\n  \"round_iterations\": [";
     for (size_t k = 0; k < round_iterations_.size(); ++k) f << (k ? ", " : "") << round_iterations_[k];
+    // real (wall-clock) time between the publication of the first UPDATE command and that of TERMINATE: simulated time
+    // costs nothing, so this is the compute + host protocol time of the optimisation itself
+    f << "],\n  \"round_wall_seconds\": [";
+    for (size_t k = 0; k < round_wall_seconds_.size(); ++k) f << (k ? ", " : "") << round_wall_seconds_[k];
     f << "],\n  \"commands\": {";
     bool first = true;
     for (const auto &kv : commands_) {
@@ -191,6 +199,8 @@ class Monitor {
   std::vector<RobotRecord> rec_;
   std::vector<ros::Subscriber> subs_;
   std::vector<unsigned> round_iterations_;   // iteration number of the last UPDATE command of every finished round
+  std::vector<double> round_wall_seconds_;
+  std::chrono::steady_clock::time_point round_start_ = std::chrono::steady_clock::now();
   std::map<int, unsigned long> commands_;
   unsigned last_update_iteration_ = 0;
   double terminate_time_ = -1;
