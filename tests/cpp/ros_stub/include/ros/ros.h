@@ -29,6 +29,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <typeindex>
 #include <variant>
 #include <vector>
@@ -73,6 +74,9 @@ struct World {
   std::map<std::string, ServiceRec> services;
   std::map<std::string, unsigned long> published;   // messages per topic (statistics)
   int log_level = 1;         // 0 silent, 1 warnings + errors, 2 everything
+  // > 0: pace the simulated clock against the wall clock (simulated seconds per real second).  Needed when something
+  // outside the cooperative schedule runs in real time -- the optimisation thread PGOAgent owns in asynchronous mode.
+  double realtime_factor = 0;
   // wall-clock instant at which the message now being delivered was published (for monitors that time a run)
   std::chrono::steady_clock::time_point delivering_published_at;
 };
@@ -106,6 +110,8 @@ inline void dispatch_locked(World &w) {
   if (!best) {
     w.current = -1;
   } else {
+    if (best->wake > w.now && w.realtime_factor > 0)   // every cooperative thread is parked here or on its cv
+      std::this_thread::sleep_for(std::chrono::duration<double>((best->wake - w.now) / w.realtime_factor));
     if (best->wake > w.now) w.now = best->wake;
     w.current = best->id;
     best->cv.notify_one();

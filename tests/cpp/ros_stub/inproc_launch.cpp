@@ -11,6 +11,10 @@
  * usage: dpgo_ros_inproc_<backend> --robots N (--g2o FILE | --measurements DIR) --out FILE.json
  *            [--preset dpgo_demo|gnc_demo] [--param key=value ...] [--rounds R] [--max-sim-seconds T] [--log 0|1|2]
  *
+ * --preset asapp_demo runs the asynchronous demo (launch/asapp_demo.launch): there is no TERMINATE in that mode, so the run
+ * is stopped after --run-sim-seconds T and the first / last trajectory every robot published (publish_iterate) are kept;
+ * --realtime F paces the simulated clock at F simulated seconds per real second, because the optimisation threads that
+ * DPGO::PGOAgent owns in this mode run in real time.
  * --rounds R: keep the nodes alive until every robot has published R optimised trajectories (the leader starts a new
  * round 10 s after a reset, src/PGOAgentROS.cpp:1381-1385).
  */
@@ -94,6 +98,15 @@ void applyPreset(const std::string &preset, ParamMap &p) {
     p["robust_opt_num_resets"] = 3;
     p["robust_opt_inner_iters_per_robot"] = 50;
     p["synchronize_measurements"] = false;
+  } else if (preset == "asapp_demo") {   // launch/asapp_demo.launch:2-37
+    p["asynchronous"] = true;
+    p["asynchronous_rate"] = 100.0;
+    p["verbose"] = true;
+    p["publish_iterate"] = true;
+    p["RGD_stepsize"] = 0.2;
+    p["RGD_use_preconditioner"] = true;
+    p["local_initialization_method"] = std::string("Chordal");
+    p["synchronize_measurements"] = true;
   } else if (!preset.empty()) {
     std::fprintf(stderr, "unknown preset %s\n", preset.c_str());
     std::exit(2);
@@ -105,6 +118,8 @@ struct RobotRecord {
   int trajectories = 0;             // optimised trajectories published so far (one per round)
   bool awaiting = false;            // a TERMINATE command was seen and this robot's result has not arrived yet
   std::vector<double> trajectory;   // latest, n x 7: x y z qx qy qz qw
+  std::vector<double> first_trajectory;
+  unsigned long trajectory_msgs = 0;
   unsigned max_iteration = 0;       // largest iteration_number this robot reported while INITIALIZED
   unsigned status_msgs = 0;
   double last_relative_change = 0;
@@ -124,10 +139,14 @@ class Monitor {
         r.have_trajectory = true;
         if (r.awaiting) r.trajectories++;
         r.awaiting = false;
+        r.trajectory_msgs++;
+        if (r.trajectory_msgs == 1) first_only_ = true;
         r.trajectory.clear();
         for (const auto &p : m->poses)
           for (double v : {p.position.x, p.position.y, p.position.z, p.orientation.x, p.orientation.y, p.orientation.z, p.orientation.w})
             r.trajectory.push_back(v);
+        if (first_only_) r.first_trajectory = r.trajectory;
+        first_only_ = false;
       }));
       subs_.push_back(nh.subscribe<dpgo_ros::Status>(prefix + "status", 100, [this, k](const dpgo_ros::StatusConstPtr &m) {
         RobotRecord &r = rec_[k];
@@ -187,7 +206,9 @@ class Monitor {
       const RobotRecord &r = rec_[k];
       f << "    {\"id\": " << k << ", \"max_iteration\": " << r.max_iteration << ", \"status_msgs\": " << r.status_msgs
         << ", \"weights_msgs\": " << r.weights_msgs << ", \"last_relative_change\": " << r.last_relative_change
-        << ", \"trajectories\": " << r.trajectories << ", \"trajectory\": [";
+        << ", \"trajectories\": " << r.trajectories << ", \"trajectory_msgs\": " << r.trajectory_msgs << ", \"first_trajectory\": [";
+      for (size_t i = 0; i < r.first_trajectory.size(); ++i) f << (i ? ", " : "") << r.first_trajectory[i];
+      f << "], \"trajectory\": [";
       for (size_t i = 0; i < r.trajectory.size(); ++i) f << (i ? ", " : "") << r.trajectory[i];
       f << "]}" << (k + 1 < rec_.size() ? "," : "") << "\n";
     }
@@ -196,6 +217,7 @@ class Monitor {
 
  private:
   int rounds_;
+  bool first_only_ = false;
   std::vector<RobotRecord> rec_;
   std::vector<ros::Subscriber> subs_;
   std::vector<unsigned> round_iterations_;   // iteration number of the last UPDATE command of every finished round
@@ -210,7 +232,7 @@ class Monitor {
 int main(int argc, char **argv) {
   int robots = 0, rounds = 1;
   std::string g2o, measurements_dir, out = "inproc_result.json", preset;
-  double max_sim_seconds = 3600;
+  double max_sim_seconds = 3600, run_sim_seconds = -1;
   std::vector<std::pair<std::string, std::string>> overrides;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -227,6 +249,8 @@ int main(int argc, char **argv) {
     else if (a == "--out") out = next();
     else if (a == "--preset") preset = next();
     else if (a == "--rounds") rounds = std::atoi(next().c_str());
+    else if (a == "--run-sim-seconds") run_sim_seconds = std::atof(next().c_str());
+    else if (a == "--realtime") ros::sim::world().realtime_factor = std::atof(next().c_str());
     else if (a == "--max-sim-seconds") max_sim_seconds = std::atof(next().c_str());
     else if (a == "--log") ros::sim::world().log_level = std::atoi(next().c_str());
     else if (a == "--param") {
@@ -297,13 +321,14 @@ int main(int argc, char **argv) {
     Monitor mon(robots, rounds);
     while (ros::ok() && !mon.done()) {
       ros::spinOnce();
+      if (run_sim_seconds > 0 && ros::sim::world().now > run_sim_seconds) break;   // fixed-length run (asynchronous mode)
       if (ros::sim::world().now > max_sim_seconds) {
         timed_out = true;
         break;
       }
       ros::Duration(0.05).sleep();
     }
-    const bool ok = mon.done();
+    const bool ok = mon.done() || run_sim_seconds > 0;
     mon.write(out, timed_out || !ok);
     timed_out = timed_out || !ok;
   }

@@ -49,9 +49,10 @@ def ref_build():
     return OUT
 
 
-def run_wrapper(binary, tmp_path, tag, robots, preset, g2o=None, measurements=None, rounds=1, params=(), timeout=600):
+def run_wrapper(binary, tmp_path, tag, robots, preset, g2o=None, measurements=None, rounds=1, params=(), timeout=600, extra=()):
     out = os.path.join(str(tmp_path), tag + ".json")
     cmd = [binary, "--robots", str(robots), "--preset", preset, "--out", out, "--log", "0", "--rounds", str(rounds)]
+    cmd += list(extra)
     cmd += ["--g2o", os.path.join(DATA, g2o)] if g2o else ["--measurements", os.path.join(DATA, measurements)]
     for kv in params:
         cmd += ["--param", kv]
@@ -171,6 +172,22 @@ def test_wrapper_second_round_reuses_the_measurements(ref_build, tmp_path):
     assert res["round_iterations"] == [3, 3]
     assert res["commands"]["0"] == 2                      # two REQUEST_POSE_GRAPH rounds
     assert [rb["trajectories"] for rb in res["robots"]] == [2, 2]
+
+
+def test_wrapper_asynchronous_demo_on_oracle(ref_build, tmp_path):
+    """launch/asapp_demo.launch (asynchronous = true, RGD 0.2 + preconditioner, 100 Hz): DPGO::PGOAgent owns one optimisation
+    thread per robot (started by initializeInGlobalFrame, Poisson clock) next to the wrapper's callbacks, which only poll
+    mPublishAsynchronousRequested (src/PGOAgentROS.cpp:119-127).  No TERMINATE exists in this mode: run a fixed stretch,
+    paced against the wall clock because those threads run in real time, and look at what the robots published."""
+    res = run_wrapper(BIN_ORACLE, tmp_path, "a", 5, "asapp_demo", g2o="sphere2500.g2o",
+                      extra=["--realtime", "10", "--run-sim-seconds", "60"], timeout=120)
+    assert not res["timed_out"] and res["commands"].get("1", 0) == 0          # no UPDATE token in this mode
+    assert all(rb["max_iteration"] > 50 and rb["trajectory_msgs"] > 50 for rb in res["robots"]), \
+        [(rb["max_iteration"], rb["trajectory_msgs"]) for rb in res["robots"]]
+    pb = ros_message_path_problem("sphere2500", 5)
+    first = trajectory_cost(pb, dict(res, robots=[dict(rb, trajectory=rb["first_trajectory"]) for rb in res["robots"]]))
+    last = trajectory_cost(pb, res)
+    assert last < 0.8 * first and last < 1.05e5, (first, last)     # the synchronous RTR run stops at 9.996e4
 
 
 # ----------------------------------------------------------------------------------------------------------------------
