@@ -21,7 +21,8 @@ acceleration (restart 50), RoundRobin, odometry initial guess, fixed YLift.
            with HOST buffers, one OS thread per robot: every step's public poses
            cross PCIe both ways (N > 1: and a shared-memory segment between the
            per-GPU processes).
-Secondary objects on the same line: `async_mode` (the reference's asynchronous
+Secondary objects on the same line: `reference_wrapper` (the reference's unmodified
+PGOAgentROS running its demo launch file on both back ends), `async_mode` (the reference's asynchronous
 demo configuration as parallel ticks) and, at N = 1, `hbm_bound_regime` (one rank
 of BASELINE config 5 at the named size -- the HBM-bound regime of this path).
 """
@@ -119,6 +120,40 @@ def async_mode_single_gpu(pb, device, ticks=2000):
                         "every tick (asynchronous mode, equal-rate unit-delay schedule)",
             "ticks_per_s": tps, "robot_updates_per_s": tps * pb.num_robots, "us_per_tick": 1e6 / tps,
             "final_cost_2f": cost}
+
+
+def reference_wrapper_e2e(timeout_s=40):
+    """Secondary figure: the reference's OWN wrapper (unmodified sources built by oracle/Makefile.ref into oracle/_ref,
+    DESIGN.md 5.1 / 6.1) running launch/dpgo_demo.launch on sphere2500 / 5 robots from the odometry guess in one process,
+    once on libdpgo_b200.so and once on the CPU oracle: wall-clock seconds between the first UPDATE command and TERMINATE.
+    RTR 3x50 (what the ROS node forces in synchronous mode), so this is NOT the headline workload; it is the only number
+    that runs the reference's real host code.  Never fails the bench line."""
+    import subprocess
+    import tempfile
+
+    out = {"workload": "launch/dpgo_demo.launch through the unmodified PGOAgentROS: sphere2500.g2o / 5 robots / RTR 3x50 / "
+                       "Odometry guess / RoundRobin (kappa = 10000, tau = 100 on the message path)"}
+    for arm in ("b200", "oracle"):
+        exe = os.path.join(ROOT, "oracle", "_ref", "dpgo_ros_inproc_" + arm)
+        if not os.path.exists(exe):
+            out[arm] = {"unavailable": "oracle/_ref is not built (needs the reference sources at build time)"}
+            continue
+        try:
+            with tempfile.TemporaryDirectory() as tmp:
+                res = os.path.join(tmp, "r.json")
+                cmd = [exe, "--robots", "5", "--g2o", os.path.join(ROOT, "data", "sphere2500.g2o"), "--preset", "dpgo_demo",
+                       "--param", "local_initialization_method=Odometry", "--out", res, "--log", "0"]
+                p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=timeout_s)
+                if p.returncode != 0:
+                    out[arm] = {"error": (p.stderr or "")[-200:]}
+                    continue
+                d = json.load(open(res))
+            it, wall = d["round_iterations"][0], d["round_wall_seconds"][0]
+            out[arm] = {"backend": d["backend"], "iterations": it, "wall_seconds": wall, "iters_per_s": it / wall,
+                        "gpu_kernel_launches": d["kernel_launches"]}
+        except Exception as e:  # noqa: BLE001
+            out[arm] = {"error": str(e)[:200]}
+    return out
 
 
 def load_peaks():
@@ -356,6 +391,7 @@ def main():
                                    f"agent ({cpu['threads']} threads, {cpu['cores']} host cores)"},
         "async_mode": async_mode,
         "hbm_bound_regime": hbm_regime,
+        "reference_wrapper": reference_wrapper_e2e(),
     }
     print(json.dumps(line))
     return 0
