@@ -95,7 +95,8 @@ class PoseGraph {
     Statistics st;
     for (auto *vec : {&private_lcs_, &shared_lcs_})
       for (const auto &m : *vec) {
-        if (m.fixedWeight) continue;
+        // fixed weights count too: the wrapper prints these numbers right after it has turned its rejects into
+        // (weight 0, fixedWeight) (src/PGOAgentROS.cpp:1051-1067)
         st.total_loop_closures += 1;
         if (m.weight == 1.0)
           st.accept_loop_closures += 1;

@@ -174,6 +174,18 @@ def test_wrapper_second_round_reuses_the_measurements(ref_build, tmp_path):
     assert [rb["trajectories"] for rb in res["robots"]] == [2, 2]
 
 
+def test_wrapper_rejected_loop_closures_persist_into_the_next_round(ref_build, tmp_path):
+    """With a positive weight_convergence_threshold the TERMINATE handler turns low-weight loop closures into
+    (weight 0, fixedWeight) through the pointers of activeLoopClosures() (src/PGOAgentROS.cpp:1044-1057) and the next
+    round must still see them that way -- the pose graph and its weights survive PGOAgent::reset().  After three weight
+    updates at mu = 8e-5 every tunnels loop closure is below 0.5, so round 2 optimises odometry only and stops early."""
+    res = run_wrapper(BIN_ORACLE, tmp_path, "p", 8, "gnc_demo", measurements="tunnels", rounds=2,
+                      params=["weight_convergence_threshold=0.5"])
+    assert not res["timed_out"] and len(res["round_iterations"]) == 2
+    assert res["round_iterations"][0] == 809
+    assert res["round_iterations"][1] < 100, res["round_iterations"]
+
+
 def test_wrapper_asynchronous_demo_on_oracle(ref_build, tmp_path):
     """launch/asapp_demo.launch (asynchronous = true, RGD 0.2 + preconditioner, 100 Hz): DPGO::PGOAgent owns one optimisation
     thread per robot (started by initializeInGlobalFrame, Poisson clock) next to the wrapper's callbacks, which only poll
