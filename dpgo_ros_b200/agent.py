@@ -113,6 +113,10 @@ class PGOAgent:
         """What the RECOVER handler does to mIterationNumber (src/PGOAgentROS.cpp:1196)."""
         check(self.L.dpgo_b200_set_iteration_number(self.h, int(iteration)), "setIterationNumber")
 
+    def setRobotActive(self, robot: int, active: bool) -> None:
+        """setRobotActive (src/PGOAgentROS.cpp:382 ... :1582): a deactivated robot no longer counts in shouldTerminate."""
+        check(self.L.dpgo_b200_set_robot_active(self.h, int(robot), 1 if active else 0), "setRobotActive")
+
     def initializeChordal(self) -> np.ndarray:
         """Chordal local initialisation on the device; returns the local trajectory [n, 3, 4]."""
         check(self.L.dpgo_b200_initialize_chordal(self.h), "initializeChordal")

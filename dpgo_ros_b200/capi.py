@@ -83,7 +83,7 @@ SYMBOLS = [
     "dpgo_b200_team_fabric_close", "dpgo_b200_team_gnc_compute_weights", "dpgo_b200_team_gnc_finish_update",
     "dpgo_b200_get_shared_loop_closures", "dpgo_b200_team_set_schedule", "dpgo_b200_get_opt_result_lazy",
     "dpgo_b200_get_pose", "dpgo_b200_sync_driver_shm_bytes", "dpgo_b200_sync_driver_run_shm",
-    "dpgo_b200_initialize_chordal", "dpgo_b200_get_local_trajectory", "dpgo_b200_set_iteration_number",
+    "dpgo_b200_initialize_chordal", "dpgo_b200_get_local_trajectory", "dpgo_b200_set_iteration_number", "dpgo_b200_set_robot_active",
 ]
 
 
@@ -126,6 +126,7 @@ def lib():
         getattr(L, "dpgo_b200_" + name).argtypes = [vp]
     L.dpgo_b200_get_neighbors.argtypes = [vp, ip, C.c_int]
     L.dpgo_b200_set_iteration_number.argtypes = [vp, C.c_int]
+    L.dpgo_b200_set_robot_active.argtypes = [vp, C.c_int, C.c_int]
     L.dpgo_b200_measurement_counts.argtypes = [vp, ip, ip, ip]
     L.dpgo_b200_set_lifting_matrix.argtypes = [vp, dp]
     L.dpgo_b200_get_lifting_matrix.argtypes = [vp, dp]

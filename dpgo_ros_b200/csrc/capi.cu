@@ -177,6 +177,16 @@ int dpgo_b200_set_neighbor_status(dpgo_b200_agent_t h, const dpgo_b200_status *s
   A(h)->team_status[s->agent_id] = *s;
   API_END
 }
+int dpgo_b200_set_robot_active(dpgo_b200_agent_t h, int robot, int active) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (robot < 0 || robot >= a->P.num_robots) fail(DPGO_B200_ERR_INVALID, "setRobotActive: robot id out of range");
+  if (active)
+    a->inactive_robots.erase(robot);
+  else
+    a->inactive_robots.insert(robot);
+  API_END
+}
 int dpgo_b200_should_terminate(dpgo_b200_agent_t h) {
   try {
     return A(h)->should_terminate() ? 1 : 0;

@@ -315,6 +315,7 @@ void Agent::reset() {
   status.agent_id = id;
   status.instance_number = instance;
   team_status.clear();
+  inactive_robots.clear();
   std::fill(inbox_valid_reg.begin(), inbox_valid_reg.end(), 0);
   std::fill(inbox_valid_aux.begin(), inbox_valid_aux.end(), 0);
   weight_update_count = 0;
@@ -809,6 +810,7 @@ bool Agent::should_terminate() const {
   if (iter > P.max_num_iters) return true;
   if (P.cost_type != 0 && weight_update_count < P.robust_opt_num_weight_updates) return false;
   for (int rid = 0; rid < P.num_robots; ++rid) {
+    if (inactive_robots.count(rid)) continue;   // a robot the leader has deactivated no longer has a say (src/PGOAgentROS.cpp:195)
     auto it = team_status.find(rid);
     if (it == team_status.end()) return false;
     if (it->second.state != 2 || !it->second.ready_to_terminate) return false;
@@ -821,6 +823,7 @@ bool Agent::should_update_weights() const {
   if (weight_update_count >= P.robust_opt_num_weight_updates) return false;
   if (robust_inner_iter >= P.robust_opt_inner_iters) return true;
   for (int rid = 0; rid < P.num_robots; ++rid) {
+    if (inactive_robots.count(rid)) continue;   // a robot the leader has deactivated no longer has a say (src/PGOAgentROS.cpp:195)
     auto it = team_status.find(rid);
     if (it == team_status.end()) return false;
     if (it->second.state != 2 || !it->second.ready_to_terminate) return false;

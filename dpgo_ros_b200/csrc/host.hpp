@@ -132,6 +132,7 @@ class Agent {
   dpgo_b200_opt_result opt{};
   dpgo_b200_status status{};
   std::map<int, dpgo_b200_status> team_status;
+  std::set<int> inactive_robots;   // setRobotActive(id, false): excluded from the leader's termination / re-weighting tests
   int weight_update_count = 0, robust_inner_iter = 0;
   double mu;
   bool publish_requested = false;

@@ -332,6 +332,7 @@ class PGOAgent {
   void setRobotActive(unsigned id, bool active) {                                          // :382 ... :1582
     if (id < mTeamRobotActive.size()) mTeamRobotActive[id] = active;
     mPoseGraph->setNeighborActive(id, active);
+    if (h_ && id < mParams.numRobots) dpgo_b200_set_robot_active(h_, (int)id, active ? 1 : 0);
   }
   bool isRobotActive(unsigned id) const { return id < mTeamRobotActive.size() && mTeamRobotActive[id]; }   // :195
   bool isRobotInitialized(unsigned id) const {                                             // :451, :468, :1144
@@ -441,6 +442,8 @@ class PGOAgent {
     h_ = nullptr;
     createHandle();
     if (YLift.has_value()) dpgo_b200_set_lifting_matrix(h_, YLift.value().data());
+    for (unsigned id = 0; id < mTeamRobotActive.size() && id < mParams.numRobots; ++id)
+      if (!mTeamRobotActive[id]) dpgo_b200_set_robot_active(h_, (int)id, 0);
     // measurements already in the host mirror (kept across reset(), or pre-loaded into a graph the wrapper swapped in)
     for (auto *vec : {&mPoseGraph->odometry(), &mPoseGraph->privateLoopClosures(), &mPoseGraph->sharedLoopClosures()})
       for (const auto &m : *vec) uploadMeasurement(m);

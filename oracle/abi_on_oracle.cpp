@@ -213,6 +213,10 @@ int dpgo_b200_set_neighbor_status(dpgo_b200_agent_t h, const dpgo_b200_status *s
   h->a->setNeighborStatus(q);
   return DPGO_B200_OK;
 }
+int dpgo_b200_set_robot_active(dpgo_b200_agent_t h, int robot, int active) {
+  h->a->setRobotActive(robot, active != 0);
+  return DPGO_B200_OK;
+}
 int dpgo_b200_should_terminate(dpgo_b200_agent_t h) { return h->a->shouldTerminate() ? 1 : 0; }
 int dpgo_b200_should_update_measurement_weights(dpgo_b200_agent_t h) { return h->a->shouldUpdateMeasurementWeights() ? 1 : 0; }
 

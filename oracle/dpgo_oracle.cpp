@@ -942,6 +942,7 @@ void Agent::reset() {
   status_.agentID = id_;
   status_.instanceNumber = instance_;
   teamStatus_.clear();
+  inactive_.clear();
   nbrPoses_.clear();
   nbrAuxPoses_.clear();
   weightUpdateCount_ = 0;
@@ -1081,6 +1082,7 @@ bool Agent::shouldTerminate() const {
   if (iter_ > params_.maxNumIters) return true;
   if (params_.costType != CostType::L2 && weightUpdateCount_ < params_.robustOptNumWeightUpdates) return false;
   for (int rid = 0; rid < params_.numRobots; ++rid) {
+    if (inactive_.count(rid)) continue;
     auto it = teamStatus_.find(rid);
     if (it == teamStatus_.end()) return false;
     if (it->second.state != AgentState::INITIALIZED) return false;
@@ -1094,6 +1096,7 @@ bool Agent::shouldUpdateMeasurementWeights() const {
   if (robustInnerIter_ >= params_.robustOptInnerIters) return true;
   // otherwise only when every robot reports readyToTerminate
   for (int rid = 0; rid < params_.numRobots; ++rid) {
+    if (inactive_.count(rid)) continue;
     auto it = teamStatus_.find(rid);
     if (it == teamStatus_.end()) return false;
     if (it->second.state != AgentState::INITIALIZED || !it->second.readyToTerminate) return false;

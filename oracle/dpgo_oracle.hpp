@@ -270,6 +270,10 @@ class Agent {
   // a10
   Status getStatus() const;                                     // :616
   void setNeighborStatus(const Status &s) { teamStatus_[s.agentID] = s; }  // :965
+  // setRobotActive (:382 ... :1582): deactivated robots are left out of the leader's termination / re-weighting tests
+  void setRobotActive(int robot, bool active) {
+    if (active) inactive_.erase(robot); else inactive_.insert(robot);
+  }
   bool shouldTerminate() const;                                 // :208
   bool shouldUpdateMeasurementWeights() const;                  // :210
   // a8
@@ -310,6 +314,7 @@ class Agent {
   PoseDict nbrPoses_, nbrAuxPoses_;
   Status status_;
   std::map<int, Status> teamStatus_;
+  std::set<int> inactive_;
   OptResult optResult_;
   RobustCost robust_;
   int weightUpdateCount_ = 0, robustInnerIter_ = 0;

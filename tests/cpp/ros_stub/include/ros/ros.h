@@ -52,6 +52,7 @@ struct Node {
   std::vector<std::shared_ptr<TimerRec>> timers;
   double wake = 0;
   bool alive = false;
+  bool partitioned = false;                   // network partition: topics neither reach nor leave this node
   std::condition_variable cv;                 // signalled when this node gets the processor
 };
 struct SubRec {
@@ -227,8 +228,10 @@ class Publisher {
     if (it == w.subs.end()) return;
     std::shared_ptr<const void> copy = std::make_shared<const M>(msg);
     const auto published_at = std::chrono::steady_clock::now();
+    sim::Node *from = sim::self();
     for (auto &s : it->second) {
       if (!*s.active || !s.node->alive) continue;
+      if (s.node != from && (s.node->partitioned || (from && from->partitioned))) continue;   // lost on the air
       if (s.type != type_) throw std::logic_error("ros stub: subscriber / publisher type mismatch on " + topic_);
       auto deliver = s.deliver;
       auto active = s.active;

@@ -15,6 +15,8 @@
  * is stopped after --run-sim-seconds T and the first / last trajectory every robot published (publish_iterate) are kept;
  * --realtime F paces the simulated clock at F simulated seconds per real second, because the optimisation threads that
  * DPGO::PGOAgent owns in this mode run in real time.
+ * --disconnect K@T: at simulated time T robot K drops off the network (its topics neither arrive nor leave) and the other
+ * robots' connectivity topics (/kimeraJ/connected_peer_ids, src/PGOAgentROS.cpp:61-63, 910-923) stop listing it.
  * --rounds R: keep the nodes alive until every robot has published R optimised trajectories (the leader starts a new
  * round 10 s after a reset, src/PGOAgentROS.cpp:1381-1385).
  */
@@ -25,6 +27,7 @@
 #include <dpgo_ros/RelativeMeasurementWeights.h>
 #include <dpgo_ros/Status.h>
 #include <geometry_msgs/PoseArray.h>
+#include <std_msgs/UInt16MultiArray.h>
 
 #include "dpgo_b200.h"
 
@@ -173,9 +176,10 @@ class Monitor {
           prefix + "measurement_weights", 100, [this, k](const dpgo_ros::RelativeMeasurementWeightsConstPtr &) { rec_[k].weights_msgs++; }));
     }
   }
+  void expectNothingFrom(int robot) { ignored_ = robot; }
   bool done() const {
-    for (const auto &r : rec_)
-      if (r.trajectories < rounds_) return false;
+    for (size_t k = 0; k < rec_.size(); ++k)
+      if ((int)k != ignored_ && rec_[k].trajectories < rounds_) return false;
     return true;
   }
   void write(const std::string &path, bool timed_out) const {
@@ -217,6 +221,7 @@ class Monitor {
 
  private:
   int rounds_;
+  int ignored_ = -1;
   bool first_only_ = false;
   std::vector<RobotRecord> rec_;
   std::vector<ros::Subscriber> subs_;
@@ -232,7 +237,8 @@ class Monitor {
 int main(int argc, char **argv) {
   int robots = 0, rounds = 1;
   std::string g2o, measurements_dir, out = "inproc_result.json", preset;
-  double max_sim_seconds = 3600, run_sim_seconds = -1;
+  double max_sim_seconds = 3600, run_sim_seconds = -1, disconnect_at = -1;
+  int disconnect_robot = -1;
   std::vector<std::pair<std::string, std::string>> overrides;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -250,6 +256,16 @@ int main(int argc, char **argv) {
     else if (a == "--preset") preset = next();
     else if (a == "--rounds") rounds = std::atoi(next().c_str());
     else if (a == "--run-sim-seconds") run_sim_seconds = std::atof(next().c_str());
+    else if (a == "--disconnect") {
+      const std::string v = next();
+      const size_t at = v.find('@');
+      if (at == std::string::npos) {
+        std::fprintf(stderr, "--disconnect expects ROBOT@SIM_SECONDS\n");
+        return 2;
+      }
+      disconnect_robot = std::atoi(v.substr(0, at).c_str());
+      disconnect_at = std::atof(v.substr(at + 1).c_str());
+    }
     else if (a == "--realtime") ros::sim::world().realtime_factor = std::atof(next().c_str());
     else if (a == "--max-sim-seconds") max_sim_seconds = std::atof(next().c_str());
     else if (a == "--log") ros::sim::world().log_level = std::atoi(next().c_str());
@@ -319,8 +335,23 @@ int main(int argc, char **argv) {
   bool timed_out = false;
   {
     Monitor mon(robots, rounds);
+    if (disconnect_robot >= 0) mon.expectNothingFrom(disconnect_robot);
     while (ros::ok() && !mon.done()) {
       ros::spinOnce();
+      if (disconnect_robot >= 0 && disconnect_at >= 0 && ros::sim::world().now >= disconnect_at) {
+        ros::NodeHandle nh;
+        for (int k = 0; k < robots; ++k) {   // what the network layer of every OTHER robot reports from now on
+          if (k == disconnect_robot) continue;
+          std_msgs::UInt16MultiArray peers;
+          for (int j = 0; j < robots; ++j)
+            if (j != disconnect_robot && j != k) peers.data.push_back((uint16_t)j);
+          nh.advertise<std_msgs::UInt16MultiArray>("/kimera" + std::to_string(k) + "/connected_peer_ids", 5).publish(peers);
+        }
+        std_msgs::UInt16MultiArray alone;    // ... and what the lost robot's own reports
+        nh.advertise<std_msgs::UInt16MultiArray>("/kimera" + std::to_string(disconnect_robot) + "/connected_peer_ids", 5).publish(alone);
+        agents[disconnect_robot]->partitioned = true;
+        disconnect_at = -1;
+      }
       if (run_sim_seconds > 0 && ros::sim::world().now > run_sim_seconds) break;   // fixed-length run (asynchronous mode)
       if (ros::sim::world().now > max_sim_seconds) {
         timed_out = true;

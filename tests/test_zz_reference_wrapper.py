@@ -186,6 +186,21 @@ def test_wrapper_rejected_loop_closures_persist_into_the_next_round(ref_build, t
     assert res["round_iterations"][1] < 100, res["round_iterations"]
 
 
+def test_wrapper_recovers_from_a_lost_robot(ref_build, tmp_path):
+    """enable_recovery: robot 3 drops off the network in the middle of the optimisation (iteration ~45).  The UPDATE token
+    is lost with it; 15 s later the leader times out, finds the robot disconnected, deactivates it, and RECOVER rewinds
+    mIterationNumber on everybody (src/PGOAgentROS.cpp:1191-1209, 1499-1545).  The remaining four robots must resume --
+    the deactivated robot no longer has a say in shouldTerminate -- and terminate by convergence, not by max iterations."""
+    res = run_wrapper(BIN_ORACLE, tmp_path, "d", 5, "dpgo_demo", g2o="sphere2500.g2o",
+                      params=["local_initialization_method=Odometry", "enable_recovery=true"], extra=["--disconnect", "3@36.2"])
+    assert not res["timed_out"]
+    assert res["commands"].get("6", 0) == 1 and res["commands"]["2"] == 1          # one RECOVER, one TERMINATE
+    its = [rb["max_iteration"] for rb in res["robots"]]
+    assert its[3] < 60 and res["robots"][3]["trajectories"] == 0                 # the lost robot stopped where it was
+    assert 60 < res["round_iterations"][0] < 1000, res["round_iterations"]       # resumed, converged before max_iteration_number
+    assert all(res["robots"][k]["trajectories"] == 1 for k in (0, 1, 2, 4))
+
+
 def test_wrapper_asynchronous_demo_on_oracle(ref_build, tmp_path):
     """launch/asapp_demo.launch (asynchronous = true, RGD 0.2 + preconditioner, 100 Hz): DPGO::PGOAgent owns one optimisation
     thread per robot (started by initializeInGlobalFrame, Poisson clock) next to the wrapper's callbacks, which only poll
