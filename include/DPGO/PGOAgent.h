@@ -178,6 +178,12 @@ class PGOAgent {
       check(dpgo_b200_initialize(h_, T.data()), "initialize");
     } else if (mParams.localInitializationMethod == InitializationMethod::Chordal) {
       check(dpgo_b200_initialize_chordal(h_), "initialize (Chordal)");               // PGOAgentROSNode.cpp:108-109
+    } else if (mParams.localInitializationMethod == InitializationMethod::GNC_TLS) {
+      std::vector<double> T;                                                            // PGOAgentROSNode.cpp:110-111
+      if (robustLocalInitialization(T))
+        check(dpgo_b200_initialize(h_, T.data()), "initialize (GNC_TLS)");
+      else
+        check(dpgo_b200_initialize_chordal(h_), "initialize (GNC_TLS -> Chordal)");
     } else {
       check(dpgo_b200_initialize(h_, nullptr), "initialize");                          // Odometry
     }
@@ -512,6 +518,80 @@ class PGOAgent {
     // the first initialised neighbour whose public poses it hears (INITIALIZE round, src/PGOAgentROS.cpp:1091-1159)
     if (!aux && mState == PGOAgentState::WAIT_FOR_INITIALIZATION && mParams.multirobotInitialization)
       tryInitializeFromNeighbor(nbr);
+  }
+  // local_initialization_method "GNC_TLS": robust pose graph optimisation over the robot's OWN odometry and private loop
+  // closures before it meets the team -- graduated non-convexity with the truncated-least-squares cost (Yang et al., RA-L
+  // 2020) around the same RTR solver: solve, re-weight every loop closure from its residual, tighten mu, until every
+  // weight has settled at 0 or 1.  Composed from the library's own entry points on a scratch single-robot agent
+  // (odometry keeps weight 1: fixedWeight, src/utils.cpp:147-149).  Returns the local trajectory (pose 0 = identity),
+  // n x 3 x 4 row-major.  [UPSTREAM-RECALL of the method; the constants below are this repo's.]
+  bool robustLocalInitialization(std::vector<double> &T) {
+    const unsigned n = num_poses();
+    if (n == 0 || mPoseGraph->numPrivateLoopClosures() == 0) return false;   // nothing to reject: Chordal is the same guess
+    dpgo_b200_params q = toC();
+    q.method = 0;                    // RTR
+    q.rtr_iterations = 20;
+    q.rtr_tcg_iterations = 100;
+    q.gradnorm_tol = 1.0;
+    q.acceleration = 0;
+    q.cost_type = (int)RobustCostParameters::Type::GNC_TLS;
+    q.robust_opt_num_weight_updates = 1 << 30;
+    q.robust_opt_num_resets = 0;
+    q.robust_opt_inner_iters = 1;
+    q.max_num_iters = 1 << 30;
+    q.rel_change_tol = 0;
+    dpgo_b200_agent_t tmp = nullptr;
+    if (dpgo_b200_agent_create((int)mID, &q, mParams.device, &tmp) != 0) return false;
+    bool ok = true;
+    auto upload = [&](const RelativeSEMeasurement &m) {
+      const int r1 = (int)m.r1, p1 = (int)m.p1, r2 = (int)m.r2, p2 = (int)m.p2;
+      double Rrm[9], tv[3];
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Rrm[i * 3 + j] = m.R(i, j);
+        tv[i] = m.t(i, 0);
+      }
+      const unsigned char fixed = m.fixedWeight ? 1 : 0;
+      ok = ok && dpgo_b200_add_measurements(tmp, 1, &r1, &p1, &r2, &p2, Rrm, tv, &m.kappa, &m.tau, &m.weight, &fixed) == 0;
+    };
+    for (const auto &m : mPoseGraph->odometry()) upload(m);
+    for (const auto &m : mPoseGraph->privateLoopClosures()) upload(m);
+    const Matrix Y0 = fixedStiefelVariable(d, r);   // any lifting matrix serves a single-robot problem
+    const double eye[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    ok = ok && dpgo_b200_set_lifting_matrix(tmp, Y0.data()) == 0 && dpgo_b200_initialize_chordal(tmp) == 0 &&
+         dpgo_b200_initialize_in_global_frame(tmp, eye) == 0;
+    const unsigned np = mPoseGraph->numPrivateLoopClosures();
+    std::vector<double> w(np, 1.0);
+    // For small mu every loop closure is weak (w ~ barc sqrt(mu) / residual): the surrogate is nearly convex and close
+    // to the odometry solution.  mu grows by GNCMuStep per round; the weights only mean "inlier / outlier" once the
+    // transition band [mu / (mu + 1), (mu + 1) / mu] barc^2 has closed in on barc^2, so never stop before mu >= 1.
+    double mu = q.gnc_init_mu;
+    for (unsigned it = 0; ok && it < 100; ++it) {
+      ok = dpgo_b200_iterate(tmp, 1) == 0 && dpgo_b200_update_measurement_weights(tmp) == 0 &&
+           dpgo_b200_get_lc_weights(tmp, w.data(), (int)np) == (int)np;
+      mu *= q.gnc_mu_step;
+      bool settled = mu >= 1.0;
+      for (double v : w) settled = settled && (v < 1e-3 || v > 1.0 - 1e-3);
+      if (settled) break;
+    }
+    if (ok) {
+      ok = dpgo_b200_iterate(tmp, 1) == 0;          // one more solve under the final weights
+      Matrix X(r, (size_t)(d + 1) * n);
+      ok = ok && dpgo_b200_get_x(tmp, 0, X.data()) == 0;
+      if (ok) {
+        const Matrix Ya = X.block(0, 0, r, d), pa = X.block(0, d, r, 1), YaT = Ya.transpose();
+        T.assign((size_t)12 * n, 0.0);
+        for (unsigned i = 0; i < n; ++i) {
+          const Matrix Ri = projectToRotationGroup(YaT * X.block(0, (size_t)i * (d + 1), r, d));
+          const Matrix ti = YaT * (X.block(0, (size_t)i * (d + 1) + d, r, 1) - pa);
+          for (int a = 0; a < 3; ++a) {
+            for (int c = 0; c < 3; ++c) T[(size_t)i * 12 + a * 4 + c] = Ri(a, c);
+            T[(size_t)i * 12 + a * 4 + 3] = ti(a, 0);
+          }
+        }
+      }
+    }
+    dpgo_b200_agent_destroy(tmp);
+    return ok;
   }
   void tryInitializeFromNeighbor(unsigned nbr) {
     if (!YLift.has_value() || num_poses() == 0) return;

@@ -201,6 +201,24 @@ def test_wrapper_recovers_from_a_lost_robot(ref_build, tmp_path):
     assert all(res["robots"][k]["trajectories"] == 1 for k in (0, 1, 2, 4))
 
 
+def test_robust_local_initialization_rejects_corrupted_loop_closures(ref_build, tmp_path):
+    """local_initialization_method GNC_TLS (src/PGOAgentROSNode.cpp:110-111) in the shim: GNC-TLS around the library's own
+    RTR solve on a scratch single-robot agent.  smallGrid3D as one robot with 8 loop closures replaced by garbage: the
+    robust guess stays within 0.5 m RMS of the clean problem's, the Chordal guess on the same data is metres off.  Here on
+    the oracle back end (tests/cpp/robust_init_check.cpp links whichever back end it is given)."""
+    exe = os.path.join(str(tmp_path), "robust_init_check")
+    objs = [os.path.join(OUT, "build", o) for o in ("abi_on_oracle.o", "dpgo_oracle.o")]
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "robust_init_check.cpp"), *objs, "-o", exe, "-pthread"], check=True)
+    out = subprocess.run([exe, os.path.join(DATA, "smallGrid3D.g2o")], stdout=subprocess.PIPE, text=True, check=True, timeout=120).stdout
+    corrupted, chordal_err, robust_err = out.split()
+    assert int(corrupted) == 8
+    assert float(robust_err) < 0.5 and float(chordal_err) > 4 * float(robust_err), out
+    # and the demo still runs end to end with that initialisation method selected
+    res = run_wrapper(BIN_ORACLE, tmp_path, "gi", 8, "gnc_demo", measurements="tunnels", params=["local_initialization_method=GNC_TLS"])
+    assert not res["timed_out"] and res["commands"]["5"] == 3 and res["commands"]["2"] == 1
+
+
 def test_wrapper_asynchronous_demo_on_oracle(ref_build, tmp_path):
     """launch/asapp_demo.launch (asynchronous = true, RGD 0.2 + preconditioner, 100 Hz): DPGO::PGOAgent owns one optimisation
     thread per robot (started by initializeInGlobalFrame, Poisson clock) next to the wrapper's callbacks, which only poll
