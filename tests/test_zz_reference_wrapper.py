@@ -32,6 +32,7 @@ OUT = os.path.join(ROOT, "oracle", "_ref")
 BIN_ORACLE = os.path.join(OUT, "dpgo_ros_inproc_oracle")
 BIN_B200 = os.path.join(OUT, "dpgo_ros_inproc_b200")
 BIN_TEST = os.path.join(OUT, "dpgo_ros_test_utils")
+BIN_WIRE = os.path.join(OUT, "dpgo_ros_wire_vs_reference")
 DATA = os.path.join(ROOT, "data")
 
 
@@ -43,7 +44,7 @@ def ref_build():
         from dpgo_ros_b200 import capi
         capi.build()   # dpgo_ros_inproc_b200 links libdpgo_b200.so
         subprocess.run(["make", "-s", "-f", os.path.join(ROOT, "oracle", "Makefile.ref"), "-j8"], check=True, cwd=ROOT)
-    for b in (BIN_ORACLE, BIN_B200, BIN_TEST):
+    for b in (BIN_ORACLE, BIN_B200, BIN_TEST, BIN_WIRE):
         if not os.path.exists(b):
             pytest.skip("oracle/_ref is not built and /root/reference is not available to build it from")
     return OUT
@@ -113,6 +114,21 @@ def test_reference_unit_test_passes_unmodified(ref_build):
     p = subprocess.run([BIN_TEST], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
     assert p.returncode == 0, p.stdout
     assert "3 tests ran, 0 failed" in p.stdout, p.stdout
+
+
+def test_wire_mirror_matches_the_reference_codecs(ref_build, tmp_path):
+    """include/dpgo_ros_wire/wire.h against the reference's own src/utils.cpp in one binary: MatrixMsg
+    values bit for bit in both directions, the float32 Status round trip, what survives the PoseGraphEdge message
+    (kappa = 10000, tau = 100, odometry fixed), and the CSV header of a log the unmodified wrapper wrote."""
+    logdir = str(tmp_path) + "/"
+    run_wrapper(BIN_ORACLE, tmp_path, "log", 2, "dpgo_demo", g2o="smallGrid3D.g2o", params=["log_output_path=" + logdir])
+    logs = sorted(f for f in os.listdir(logdir) if f.startswith("dpgo_log_") and f.endswith(".csv"))
+    assert logs, os.listdir(logdir)
+    with open(os.path.join(logdir, logs[0])) as f:
+        lines = f.read().splitlines()
+    assert lines[0].startswith("robot_id, cluster_id, num_active_robots, iteration") and "TERMINATE" in lines
+    p = subprocess.run([BIN_WIRE, os.path.join(logdir, logs[0])], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert p.returncode == 0 and "wire vs reference ok" in p.stdout, p.stdout
 
 
 @pytest.mark.parametrize("name,robots,accel", [("smallGrid3D", 2, False), ("sphere2500", 5, False), ("sphere2500", 5, True)])
