@@ -181,10 +181,11 @@ int dpgo_b200_set_robot_active(dpgo_b200_agent_t h, int robot, int active) {
   API_BEGIN
   Agent *a = A(h);
   if (robot < 0 || robot >= a->P.num_robots) fail(DPGO_B200_ERR_INVALID, "setRobotActive: robot id out of range");
-  if (active)
-    a->inactive_robots.erase(robot);
-  else
-    a->inactive_robots.insert(robot);
+  const bool changed = active ? a->inactive_robots.erase(robot) != 0 : a->inactive_robots.insert(robot).second;
+  if (changed) {   // the robot's shared loop closures enter / leave Q, G and the preconditioner
+    a->values_dirty = a->precon_dirty = true;
+    if (a->team) a->team->team_dirty = true;
+  }
   API_END
 }
 int dpgo_b200_should_terminate(dpgo_b200_agent_t h) {

@@ -470,6 +470,9 @@ void Agent::build_values() {
         for (int i = 0; i < 4; ++i) ji[j * 4 + i] -= TOm[i * 4 + j];      // Q_ji = -(T Om)^T
     }
   for (const auto &m : slc) {
+    // shared loop closures with a deactivated neighbour leave the problem (upstream's default; the alternative,
+    // useInactiveNeighbors(true), is commented out in the wrapper: src/PGOAgentROS.cpp:151-156)
+    if (inactive_robots.count(m.r1 == id ? m.r2 : m.r1)) continue;
     prep(m);
     if (m.r1 == id) {
       double *ii = entry(m.p1, m.p1);
@@ -519,6 +522,10 @@ void Agent::build_values() {
         const auto &m = slc[e];
         edge_blocks(m, T, Om);
         double *M = &sv[k * 16];
+        if (inactive_robots.count(m.r1 == id ? m.r2 : m.r1)) {   // block stays zero: no pull towards a lost neighbour
+          ++k;
+          continue;
+        }
         if (m.r1 == id) {  // outgoing: G_i -= X_j Om T^T
           for (int jj = 0; jj < 4; ++jj)
             for (int ii = 0; ii < 4; ++ii) M[jj * 4 + ii] = -Om[ii] * T[ii * 4 + jj];

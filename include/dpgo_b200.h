@@ -124,8 +124,9 @@ int dpgo_b200_get_opt_result_lazy(dpgo_b200_agent_t a, dpgo_b200_opt_result *out
 int dpgo_b200_get_status(dpgo_b200_agent_t a, dpgo_b200_status *out);           /* getStatus, :616 */
 int dpgo_b200_set_neighbor_status(dpgo_b200_agent_t a, const dpgo_b200_status *s);  /* :965 */
 /* setRobotActive(id, active), :382 ... :1582: robots the leader has deactivated (disconnected, left the cluster) are
- * left out of shouldTerminate / shouldUpdateMeasurementWeights.  All robots are active after create / reset.  Shared
- * loop closures with a deactivated neighbour keep the last poses received from it. */
+ * left out of shouldTerminate / shouldUpdateMeasurementWeights, and the shared loop closures with a deactivated
+ * neighbour leave Q, G and the preconditioner (upstream's default; the wrapper's alternative is commented out, :151-156).
+ * All robots are active after create / reset. */
 int dpgo_b200_set_robot_active(dpgo_b200_agent_t a, int robot, int active);
 int dpgo_b200_should_terminate(dpgo_b200_agent_t a);                            /* :208  (1/0, <0 error) */
 int dpgo_b200_should_update_measurement_weights(dpgo_b200_agent_t a);           /* :210 */

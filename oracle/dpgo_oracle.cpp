@@ -496,6 +496,7 @@ void PoseGraph::buildQ() {
       add(m.p2, m.p1, OmTt, -1.0);   // Q_ji  = -Om T^T
     }
   for (const auto &m : sharedLC_) {  // only my diagonal block
+    if (!neighborActive(m.r1 == id_ ? m.r2 : m.r1)) continue;
     prep(m);
     if (m.r1 == id_)
       add(m.p1, m.p1, TOmTt, 1.0);
@@ -529,6 +530,7 @@ bool PoseGraph::constructDataMatrices(const PoseDict &nbrPoses, bool needPrecond
   G_ = Mat(r_, 4 * n_);
   double T[16], Om[4], M[16];
   for (const auto &m : sharedLC_) {
+    if (!neighborActive(m.r1 == id_ ? m.r2 : m.r1)) continue;
     edgeBlocks(m, T, Om);
     if (m.r1 == id_) {  // outgoing: G_i -= X_j Om T^T
       auto it = nbrPoses.find({m.r2, m.p2});
@@ -942,7 +944,7 @@ void Agent::reset() {
   status_.agentID = id_;
   status_.instanceNumber = instance_;
   teamStatus_.clear();
-  inactive_.clear();
+  for (int rid : std::set<int>(inactive_)) setRobotActive(rid, true);
   nbrPoses_.clear();
   nbrAuxPoses_.clear();
   weightUpdateCount_ = 0;

@@ -174,6 +174,12 @@ class PoseGraph {
   Measurement *findMeasurement(int r1, int p1, int r2, int p2);
 
   void clearDataMatrices() { haveQ_ = false; havePrecon_ = false; }  // src/PGOAgentROS.cpp:1351
+  // setRobotActive(id, false): the shared loop closures with that neighbour leave the problem (upstream's default,
+  // useInactiveNeighbors(false); the alternative is commented out in the wrapper, src/PGOAgentROS.cpp:151-156)
+  void setNeighborActive(int robot, bool active) {
+    if (active ? inactive_.erase(robot) != 0 : inactive_.insert(robot).second) clearDataMatrices();
+  }
+  bool neighborActive(int robot) const { return inactive_.count(robot) == 0; }
   // Builds Q if stale; always rebuilds G from `nbrPoses`.  Returns false if a
   // needed neighbour pose is missing.
   bool constructDataMatrices(const PoseDict &nbrPoses, bool needPreconditioner, double lambda);
@@ -189,7 +195,7 @@ class PoseGraph {
   int id_, r_, d_;
   int n_ = 0;
   std::vector<Measurement> odom_, privateLC_, sharedLC_;
-  std::set<int> nbrs_;
+  std::set<int> nbrs_, inactive_;
   std::set<std::pair<std::pair<int, int>, std::pair<int, int>>> have_;
   bool haveQ_ = false, havePrecon_ = false;
   // block-CSC of Q: for column block j: sorted row blocks + values
@@ -273,6 +279,7 @@ class Agent {
   // setRobotActive (:382 ... :1582): deactivated robots are left out of the leader's termination / re-weighting tests
   void setRobotActive(int robot, bool active) {
     if (active) inactive_.erase(robot); else inactive_.insert(robot);
+    pg_->setNeighborActive(robot, active);
   }
   bool shouldTerminate() const;                                 // :208
   bool shouldUpdateMeasurementWeights() const;                  // :210
