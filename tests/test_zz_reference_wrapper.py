@@ -98,6 +98,19 @@ def trajectory_cost(pb, result):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU
 # ----------------------------------------------------------------------------------------------------------------------
+def test_ros_stand_in_selftest(tmp_path):
+    """The stand-in's own contract (tests/cpp/ros_stub/selftest.cpp): one node at a time on a simulated clock, publish-order
+    delivery including to the publisher itself, timers, services, typed private parameters, partitions -- and a trace that
+    is identical from run to run."""
+    exe = os.path.join(str(tmp_path), "selftest")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread", "-I",
+                    os.path.join(ROOT, "tests", "cpp", "ros_stub", "include"),
+                    os.path.join(ROOT, "tests", "cpp", "ros_stub", "selftest.cpp"), "-o", exe], check=True)
+    runs = [subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=60) for _ in range(3)]
+    assert all(r.returncode == 0 and "selftest ok" in r.stdout for r in runs), runs[0].stdout
+    assert runs[0].stdout == runs[1].stdout == runs[2].stdout
+
+
 def test_reference_sources_compile_unmodified_against_the_shim(ref_build):
     """The build itself is the check: four wrapper sources + the unit test, no patch, no -D tricks beyond renaming the
     two main() functions so that they can share a process."""
