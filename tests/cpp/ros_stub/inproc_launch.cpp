@@ -282,6 +282,10 @@ int main(int argc, char **argv) {
       return 2;
     }
   }
+  if (disconnect_robot >= robots) {
+    std::fprintf(stderr, "--disconnect: robot %d does not exist\n", disconnect_robot);
+    return 2;
+  }
   if (robots <= 0 || (g2o.empty() == measurements_dir.empty())) {
     std::fprintf(stderr, "usage: %s --robots N (--g2o FILE | --measurements DIR) --out FILE.json [--preset dpgo_demo|gnc_demo] "
                          "[--param key=value ...] [--rounds R] [--max-sim-seconds T] [--log 0|1|2]\n", argv[0]);
