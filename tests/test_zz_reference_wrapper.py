@@ -248,6 +248,27 @@ def test_robust_local_initialization_rejects_corrupted_loop_closures(ref_build, 
     assert not res["timed_out"] and res["commands"]["5"] == 3 and res["commands"]["2"] == 1
 
 
+def _golden_runs():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_wrapper.json")) as f:
+        return json.load(f)["runs"]
+
+
+def _run_golden(binary, tmp_path, run):
+    args = [os.path.join(DATA, a) if a.endswith(".g2o") or a == "tunnels" else a for a in run["args"]]
+    out = os.path.join(str(tmp_path), run["name"] + ".json")
+    p = subprocess.run([binary, *args, "--out", out, "--log", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    with open(out) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("run", _golden_runs(), ids=lambda r: r["name"])
+def test_wrapper_on_oracle_reproduces_the_golden_iteration_counts(ref_build, tmp_path, run):
+    """tests/golden/reference_wrapper.json: iteration-to-termination counts of the demo launch files through the reference's
+    wrapper (generated by tests/golden/make_wrapper_golden.sh)."""
+    assert _run_golden(BIN_ORACLE, tmp_path, run)["round_iterations"] == [run["iterations"]]
+
+
 def test_wrapper_asynchronous_demo_on_oracle(ref_build, tmp_path):
     """launch/asapp_demo.launch (asynchronous = true, RGD 0.2 + preconditioner, 100 Hz): DPGO::PGOAgent owns one optimisation
     thread per robot (started by initializeInGlobalFrame, Poisson clock) next to the wrapper's callbacks, which only poll
@@ -299,3 +320,14 @@ def test_wrapper_gnc_demo_on_b200(ref_build, tmp_path):
     assert "sm_100a" in g["backend"] and g["kernel_launches"] > 0
     assert not g["timed_out"] and g["commands"]["5"] == 3 and g["commands"]["2"] == 1
     assert abs(g["round_iterations"][0] - c["round_iterations"][0]) <= 0.05 * c["round_iterations"][0], (g["round_iterations"], c["round_iterations"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("run", [r for r in _golden_runs() if r["name"] in ("sphere2500_5_odom", "sphere2500_8", "torus3D_4_r6")],
+                         ids=lambda r: r["name"])
+def test_wrapper_on_b200_reproduces_the_golden_iteration_counts(ref_build, tmp_path, run):
+    """The committed counts (produced on the CPU oracle back end) from the same wrapper on libdpgo_b200.so: 196 / 17 / 9
+    iterations, as measured on a B200 in profiles/wrapper_e2e_r1.json."""
+    res = _run_golden(BIN_B200, tmp_path, run)
+    assert "sm_100a" in res["backend"] and res["kernel_launches"] > 0
+    assert res["round_iterations"] == [run["iterations"]]
