@@ -122,7 +122,7 @@ def async_mode_single_gpu(pb, device, ticks=2000):
             "final_cost_2f": cost}
 
 
-def reference_wrapper_e2e(timeout_s=40):
+def reference_wrapper_e2e(timeout_s=40, arms=("b200", "oracle")):
     """Secondary figure: the reference's OWN wrapper (unmodified sources built by oracle/Makefile.ref into oracle/_ref,
     DESIGN.md 5.1 / 6.1) running launch/dpgo_demo.launch on sphere2500 / 5 robots from the odometry guess in one process,
     once on libdpgo_b200.so and once on the CPU oracle: wall-clock seconds between the first UPDATE command and TERMINATE.
@@ -133,7 +133,7 @@ def reference_wrapper_e2e(timeout_s=40):
 
     out = {"workload": "launch/dpgo_demo.launch through the unmodified PGOAgentROS: sphere2500.g2o / 5 robots / RTR 3x50 / "
                        "Odometry guess / RoundRobin (kappa = 10000, tau = 100 on the message path)"}
-    for arm in ("b200", "oracle"):
+    for arm in arms:
         exe = os.path.join(ROOT, "oracle", "_ref", "dpgo_ros_inproc_" + arm)
         if not os.path.exists(exe):
             out[arm] = {"unavailable": "oracle/_ref is not built (needs the reference sources at build time)"}
@@ -279,6 +279,8 @@ def run_reference_arm(args):
                          "iterate_true_median_us": r.get("iterate_true_median_us")},
         "e2e": {"value": r["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_cost_2f": r["cost"], "wall_s": time.time() - t0,
+        # the reference's own wrapper (unmodified sources, oracle/_ref) on the CPU oracle back end -- no CUDA on this arm
+        "reference_wrapper": reference_wrapper_e2e(arms=("oracle",)),
     }
     print(json.dumps(line))
     return 0
