@@ -99,6 +99,7 @@ def lib():
     L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
     L.orc_initialize_chordal.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_iteration_number.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.orc_set_robot_active.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.orc_get_local_trajectory.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.orc_run_parallel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcRunResult)]
     L.orc_agent_iterate.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -199,6 +200,10 @@ class OracleTeam:
 
     def set_iteration_number(self, rid, it):
         _chk(self.L.orc_set_iteration_number(self.h, rid, int(it)), "set_iteration_number")
+
+    def set_robot_active(self, rid, robot, active):
+        """setRobotActive on agent `rid` (src/PGOAgentROS.cpp:382 ... :1582)."""
+        _chk(self.L.orc_set_robot_active(self.h, rid, int(robot), 1 if active else 0), "set_robot_active")
 
     def initialize_chordal(self, rid):
         """Chordal local initialisation (Agent::initializeChordal); returns the local trajectory [n, 3, 4]."""

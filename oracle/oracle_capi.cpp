@@ -147,6 +147,11 @@ int orc_set_iteration_number(void *t, int agent, int it) {
   ORC_CATCH
 }
 
+int orc_set_robot_active(void *t, int agent, int robot, int active) {
+  ORC_TRY((Team *)t)->agent(agent).setRobotActive(robot, active != 0);
+  ORC_CATCH
+}
+
 int orc_initialize_chordal(void *t, int agent) {
   ORC_TRY((Team *)t)->agent(agent).initializeChordal();
   ORC_CATCH

@@ -322,3 +322,36 @@ def test_chordal_initialization_starts_near_the_optimum(small_problem):
     ra, rb = a.run(500, stop_on_terminate=True), b.run(500, stop_on_terminate=True)
     assert rb.terminated and rb.iterations <= ra.iterations
     assert abs(b.global_cost() - 1025.398) < 5.0   # terminated by the relative-change test, a little above the optimum
+
+
+def test_deactivated_neighbour_equals_removed_edges():
+    """setRobotActive(k, false) (src/PGOAgentROS.cpp:382 ... :1582; upstream's default useInactiveNeighbors(false)): the
+    shared loop closures with robot k leave Q, G and the preconditioner.  Property: robot 1 of sphere2500 / 4 with robot 2
+    deactivated iterates exactly like robot 1 of the same problem with the 1-2 loop closures deleted."""
+    import dataclasses
+    pb = datasets.load_g2o_problem("sphere2500", 4)
+    m = pb.meas
+    keep = [e for e in range(len(m)) if {int(m.r1[e]), int(m.r2[e])} != {1, 2}]
+    pb_cut = dataclasses.replace(pb, meas=m.take(keep))
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2)
+    a, b = orc.OracleTeam(pb, **kw), orc.OracleTeam(pb_cut, **kw)
+    a.set_robot_active(1, 2, False)
+    for _ in range(3):
+        a.iterate(1, True)
+        b.iterate(1, True)
+    Xa, Xb = a.get_x(1), b.get_x(1)
+    assert np.linalg.norm(Xa - Xb) <= 1e-12 * np.linalg.norm(Xb)
+    assert a.opt_result(1).tcg_iters == b.opt_result(1).tcg_iters
+    # and it is not a no-op: with robot 2 active the iterate differs
+    c = orc.OracleTeam(pb, **kw)
+    for _ in range(3):
+        c.iterate(1, True)
+    assert np.linalg.norm(c.get_x(1) - Xb) > 1e-6 * np.linalg.norm(Xb)
+    # re-activation restores the full problem
+    a.set_robot_active(1, 2, True)
+    d = orc.OracleTeam(pb, **kw)
+    d.set_robot_active(1, 2, False)
+    d.set_robot_active(1, 2, True)
+    for _ in range(3):
+        d.iterate(1, True)
+    assert np.linalg.norm(d.get_x(1) - c.get_x(1)) <= 1e-12 * np.linalg.norm(Xb)

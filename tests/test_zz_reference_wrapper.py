@@ -331,3 +331,31 @@ def test_wrapper_on_b200_reproduces_the_golden_iteration_counts(ref_build, tmp_p
     res = _run_golden(BIN_B200, tmp_path, run)
     assert "sm_100a" in res["backend"] and res["kernel_launches"] > 0
     assert res["round_iterations"] == [run["iterations"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first GPU run pending (DESIGN.md 9)")
+def test_deactivated_neighbour_equals_removed_edges_on_b200():
+    """GPU twin of tests/test_oracle.py::test_deactivated_neighbour_equals_removed_edges: robot 1 of sphere2500 / 4 with
+    robot 2 deactivated (dpgo_b200_set_robot_active) against the oracle on the problem with the 1-2 loop closures deleted."""
+    import dataclasses
+
+    from dpgo_ros_b200 import agent as gpu
+    from oracle import binding as orc
+
+    pb = datasets.load_g2o_problem("sphere2500", 4)
+    m = pb.meas
+    keep = [e for e in range(len(m)) if {int(m.r1[e]), int(m.r2[e])} != {1, 2}]
+    pb_cut = dataclasses.replace(pb, meas=m.take(keep))
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2)
+    _, agents = gpu.make_team(pb, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=False)
+    agents[1].setRobotActive(2, False)
+    ref = orc.OracleTeam(pb_cut, **kw)
+    for _ in range(3):
+        agents[1].iterate(True)
+        ref.iterate(1, True)
+    X, Xo = agents[1].getX(), ref.get_x(1)
+    for a in agents:
+        a.close()
+    assert np.linalg.norm(X - Xo) <= 1e-7 * np.linalg.norm(Xo)
