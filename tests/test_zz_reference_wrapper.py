@@ -359,3 +359,56 @@ def test_deactivated_neighbour_equals_removed_edges_on_b200():
     for a in agents:
         a.close()
     assert np.linalg.norm(X - Xo) <= 1e-7 * np.linalg.norm(Xo)
+
+
+PENDING = pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first GPU run pending (DESIGN.md 9)")
+
+
+@pytest.mark.gpu
+@PENDING
+def test_wrapper_second_round_on_b200(ref_build, tmp_path):
+    """Two rounds on the GPU back end: the device agent is rebuilt from the host mirror after reset()."""
+    g = run_wrapper(BIN_B200, tmp_path, "g2", 2, "dpgo_demo", g2o="smallGrid3D.g2o", rounds=2, timeout=120)
+    assert not g["timed_out"] and g["round_iterations"] == [3, 3] and g["kernel_launches"] > 0
+
+
+@pytest.mark.gpu
+@PENDING
+def test_wrapper_recovers_from_a_lost_robot_on_b200(ref_build, tmp_path):
+    """The RECOVER scenario of the CPU test on the GPU back end: same iteration count and trajectories as on the oracle."""
+    kw = dict(g2o="sphere2500.g2o", params=["local_initialization_method=Odometry", "enable_recovery=true"],
+              extra=["--disconnect", "3@36.2"], timeout=120)
+    g = run_wrapper(BIN_B200, tmp_path, "gd", 5, "dpgo_demo", **kw)
+    c = run_wrapper(BIN_ORACLE, tmp_path, "cd", 5, "dpgo_demo", **kw)
+    assert g["commands"].get("6", 0) == 1 and g["round_iterations"] == c["round_iterations"]
+    Rg, tg = trajectories(g)
+    Rc, tc = trajectories(c)
+    for rid in (0, 1, 2, 4):
+        assert np.linalg.norm(tg[rid] - tc[rid]) <= 1e-6 * np.linalg.norm(tc[rid]), rid
+
+
+@pytest.mark.gpu
+@PENDING
+def test_robust_local_initialization_on_b200(ref_build, tmp_path):
+    """tests/cpp/robust_init_check.cpp linked against libdpgo_b200.so: same verdict as on the oracle back end."""
+    exe = os.path.join(str(tmp_path), "robust_init_check")
+    lib = os.path.join(ROOT, "dpgo_ros_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "robust_init_check.cpp"), "-L", lib, "-ldpgo_b200",
+                    "-Wl,-rpath," + lib, "-o", exe, "-pthread"], check=True)
+    out = subprocess.run([exe, os.path.join(DATA, "smallGrid3D.g2o")], stdout=subprocess.PIPE, text=True, check=True, timeout=120).stdout
+    corrupted, chordal_err, robust_err = out.split()
+    assert int(corrupted) == 8 and float(robust_err) < 0.5 and float(chordal_err) > 4 * float(robust_err), out
+
+
+@pytest.mark.gpu
+@PENDING
+def test_wrapper_asynchronous_demo_on_b200(ref_build, tmp_path):
+    """launch/asapp_demo.launch on the GPU back end: every robot's optimisation thread makes progress and the cost of the
+    published trajectories goes down."""
+    res = run_wrapper(BIN_B200, tmp_path, "ga", 5, "asapp_demo", g2o="sphere2500.g2o",
+                      extra=["--realtime", "10", "--run-sim-seconds", "60"], timeout=120)
+    assert not res["timed_out"] and all(rb["max_iteration"] > 50 for rb in res["robots"])
+    pb = ros_message_path_problem("sphere2500", 5)
+    first = trajectory_cost(pb, dict(res, robots=[dict(rb, trajectory=rb["first_trajectory"]) for rb in res["robots"]]))
+    assert trajectory_cost(pb, res) < 0.8 * first
