@@ -315,6 +315,7 @@ int main(int argc, char **argv) {
 
   // ---- one thread per node, each running the reference's own main()
   std::vector<std::thread> threads;
+  static bool node_failed = false;   // only ever touched by the thread that holds the processor
   auto run = [](ros::sim::Node *n, int (*entry)(int, char **)) {
     ros::sim::enter(n);
     char name[] = "node";
@@ -324,10 +325,12 @@ int main(int argc, char **argv) {
       rc = entry(1, av);
     } catch (const std::exception &e) {
       std::fprintf(stderr, "[%s/%s] uncaught exception: %s\n", n->ns.c_str(), n->name.c_str(), e.what());
+      node_failed = true;
       ros::shutdown();
     }
     if (rc != 0 && ros::ok()) {
       std::fprintf(stderr, "[%s/%s] main returned %d\n", n->ns.c_str(), n->name.c_str(), rc);
+      node_failed = true;
       ros::shutdown();
     }
     ros::sim::leave();
@@ -378,5 +381,6 @@ int main(int argc, char **argv) {
   }
   ros::sim::leave();
   for (auto &t : threads) t.join();
+  if (node_failed) return 3;
   return timed_out ? 1 : 0;
 }
