@@ -16,7 +16,13 @@
 // al. RA-L 2020; RTR-tCG: Absil et al. 2007) and is anchored on the wrapper's
 // call sites, cited per function as src/PGOAgentROS.cpp:<line>.  It is
 // cross-checked by an independent numpy restatement (oracle/np_oracle.py),
-// finite differences and known optima (tests/test_oracle*.py).
+// finite differences and SE-Sync's published optima (tests/test_oracle.py,
+// tests/test_known_optima.py).  What IS pinned against the reference itself is
+// the SCHEDULE (Team::run, the GNC stages, termination): the reference's wrapper
+// sources compile unmodified against the DPGO:: shim (oracle/Makefile.ref ->
+// oracle/_ref/) and their real control flow reproduces Team::run's iteration
+// counts and final cost exactly (tests/test_zz_reference_wrapper.py).  The
+// ARITHMETIC stays unpinned.
 // =============================================================================
 #pragma once
 #include <cstdint>
