@@ -333,8 +333,14 @@ class PGOAgent {
                        status.readyToTerminate ? 1 : 0, status.relativeChange};
     dpgo_b200_set_neighbor_status(h_, &s);
   }
-  bool hasNeighborStatus(unsigned id) const { return mTeamStatus.count(id) != 0; }          // :1116
-  PGOAgentStatus getNeighborStatus(unsigned id) const { return mTeamStatus.at(id); }        // :1121
+  bool hasNeighborStatus(unsigned id) const {                                              // :1116
+    DPGO_SHIM_LOCK;
+    return mTeamStatus.count(id) != 0;
+  }
+  PGOAgentStatus getNeighborStatus(unsigned id) const {                                    // :1121
+    DPGO_SHIM_LOCK;
+    return mTeamStatus.at(id);
+  }
   void setRobotActive(unsigned id, bool active) {                                          // :382 ... :1582
     if (id < mTeamRobotActive.size()) mTeamRobotActive[id] = active;
     mPoseGraph->setNeighborActive(id, active);
@@ -342,6 +348,7 @@ class PGOAgent {
   }
   bool isRobotActive(unsigned id) const { return id < mTeamRobotActive.size() && mTeamRobotActive[id]; }   // :195
   bool isRobotInitialized(unsigned id) const {                                             // :451, :468, :1144
+    DPGO_SHIM_LOCK;
     if (id == mID) return mState == PGOAgentState::INITIALIZED;
     auto it = mTeamStatus.find(id);
     return it != mTeamStatus.end() && it->second.state == PGOAgentState::INITIALIZED;
@@ -391,12 +398,14 @@ class PGOAgent {
   std::shared_ptr<PoseGraph> mPoseGraph;            // reassigned by the wrapper at :237
   ROPTResult mLocalOptResult;                       // :169-172
   unsigned mInstanceNumber = 0;
-  unsigned mIterationNumber = 0;                    // written by the RECOVER handler, :1196
+  // written by the RECOVER handler (:1196) and, in asynchronous mode, by the optimisation thread inside iterate() while
+  // the wrapper reads it through iteration_number(): atomic, assignable and readable like the plain unsigned upstream has
+  std::atomic<unsigned> mIterationNumber{0};
   unsigned mWeightUpdateCount = 0;                  // :193
   unsigned mRobustOptInnerIter = 0;                 // :193, :545
   std::map<unsigned, PGOAgentStatus> mTeamStatus;   // :196-199
   RobustCost mRobustCost;                           // :1050
-  bool mPublishPublicPosesRequested = false;        // :109, :112
+  std::atomic<bool> mPublishPublicPosesRequested{false};    // :109, :112 (raised inside iterate(), possibly by the optimisation thread)
   std::atomic<bool> mPublishAsynchronousRequested{false};   // :120, :125 (raised by the optimisation thread)
   std::optional<Matrix> YLift;                      // :1408, :1419, :1459
   std::optional<LiftedPose> globalAnchor;           // :426-429
@@ -440,8 +449,16 @@ class PGOAgent {
     check(dpgo_b200_agent_create((int)mID, &q, mParams.device, &h_), "PGOAgent");
     mBoundGraph = mPoseGraph.get();
     dpgo_b200_agent_t h = h_;
-    mPoseGraph->bindClear([h] { dpgo_b200_clear_data_matrices(h); });
-    mRobustCost.bind([h](double res) { return dpgo_b200_robust_weight(h, res); });
+    // both are reached from the wrapper WITHOUT passing through a PGOAgent method (mPoseGraph->clearDataMatrices(),
+    // :1351; mRobustCost.weight(), :1050) -- possibly while the optimisation thread is inside iterate()
+    mPoseGraph->bindClear([this, h] {
+      std::lock_guard<std::recursive_mutex> lock(mMutex);
+      dpgo_b200_clear_data_matrices(h);
+    });
+    mRobustCost.bind([this, h](double res) {
+      std::lock_guard<std::recursive_mutex> lock(mMutex);
+      return dpgo_b200_robust_weight(h, res);
+    });
   }
   void recreateHandle() {
     if (h_) dpgo_b200_agent_destroy(h_);
@@ -639,7 +656,7 @@ class PGOAgent {
   dpgo_b200_agent_t h_ = nullptr;
   const PoseGraph *mBoundGraph = nullptr;
   unsigned mLastIterationSeen = 0;
-  std::recursive_mutex mMutex;
+  mutable std::recursive_mutex mMutex;
   std::unique_ptr<std::thread> mOptimizationThread;
   std::atomic<bool> mEndLoopRequested{false};
 };
