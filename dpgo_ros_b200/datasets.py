@@ -411,8 +411,43 @@ class Problem:
         return measurements_of_robot(self.meas, rid)
 
 
+def spanning_tree_init(meas: Measurements, num_poses: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Initial guess for graphs whose odometry chain is broken (cubicle.g2o, rim.g2o: SURVEY App. C): compose the
+    measurements along a breadth-first spanning tree rooted at pose 0, edges taken in file order, either direction."""
+    from collections import deque
+
+    adj: List[List[Tuple[int, int, bool]]] = [[] for _ in range(num_poses)]
+    for e in range(len(meas)):
+        i, j = int(meas.p1[e]), int(meas.p2[e])
+        adj[i].append((j, e, True))
+        adj[j].append((i, e, False))
+    R = np.tile(np.eye(3), (num_poses, 1, 1))
+    t = np.zeros((num_poses, 3))
+    seen = np.zeros(num_poses, dtype=bool)
+    seen[0] = True
+    queue = deque([0])
+    while queue:
+        i = queue.popleft()
+        for j, e, forward in adj[i]:
+            if seen[j]:
+                continue
+            if forward:
+                R[j], t[j] = se3_compose(R[i], t[i], meas.R[e], meas.t[e])
+            else:
+                Rinv, tinv = se3_inverse(meas.R[e], meas.t[e])
+                R[j], t[j] = se3_compose(R[i], t[i], Rinv, tinv)
+            seen[j] = True
+            queue.append(j)
+    if not seen.all():
+        raise ValueError(f"pose graph is disconnected: {int((~seen).sum())} poses unreachable from pose 0")
+    return R, t
+
+
 def _global_odometry_init(meas: Measurements, num_poses: int) -> Tuple[np.ndarray, np.ndarray]:
-    return odometry_chain(meas, 0, num_poses)
+    try:
+        return odometry_chain(meas, 0, num_poses)
+    except ValueError:
+        return spanning_tree_init(meas, num_poses)
 
 
 def load_g2o_problem(name: str, num_robots: int, path: str | None = None) -> Problem:
