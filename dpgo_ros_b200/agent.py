@@ -106,8 +106,14 @@ class PGOAgent:
         check(self.L.dpgo_b200_reset(self.h), "reset")
 
     # ---- hot path ------------------------------------------------------------------------
-    def iterate(self, doOptimization: bool = True) -> None:
-        check(self.L.dpgo_b200_iterate(self.h, int(doOptimization)), "iterate")
+    def iterate(self, doOptimization: bool = True) -> bool:
+        """PGOAgent::iterate: True when the local solve ran (or none was asked for); False when iterate(true) had to
+        skip it because a neighbour's poses have not arrived (the iteration is counted all the same)."""
+        rc = self.L.dpgo_b200_iterate(self.h, int(doOptimization))
+        if rc == -4:  # DPGO_B200_ERR_MISSING
+            return False
+        check(rc, "iterate")
+        return True
 
     def setIterationNumber(self, iteration: int) -> None:
         """What the RECOVER handler does to mIterationNumber (src/PGOAgentROS.cpp:1196)."""
@@ -239,6 +245,14 @@ class PGOAgent:
         return self.L.dpgo_b200_weight_update_count(self.h)
 
     # ---- parity hooks -----------------------------------------------------------------------------
+    def denseQ(self):
+        """Q as the device kernel assembled it: (from the block-CSR copy, from the ELL + overflow copy), 4n x 4n."""
+        n4 = 4 * self.num_poses()
+        a = np.zeros((n4, n4), order="F")
+        b = np.zeros((n4, n4), order="F")
+        check(self.L.dpgo_b200_debug_dense_q(self.h, _dp(a), _dp(b)), "denseQ")
+        return a, b
+
     def eval(self, X: np.ndarray):
         X = np.asfortranarray(X, dtype=np.float64)
         f = C.c_double()

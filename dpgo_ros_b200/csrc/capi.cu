@@ -153,7 +153,12 @@ int dpgo_b200_initialize_in_global_frame(dpgo_b200_agent_t h, const double *Tw) 
 
 int dpgo_b200_iterate(dpgo_b200_agent_t h, int do_opt) {
   API_BEGIN
-  A(h)->iterate(do_opt != 0);
+  Agent *a = A(h);
+  const bool optimized = a->iterate(do_opt != 0);
+  // upstream returns the success of the local solve (the wrapper logs "iteration not successful", :160-175): an
+  // iterate(true) that had to be skipped because a neighbour's poses have not arrived yet advances the iteration
+  // counter like any other and reports DPGO_B200_ERR_MISSING
+  if (do_opt && !optimized && a->state == 2) fail(DPGO_B200_ERR_MISSING, "iterate: neighbour poses missing, local solve skipped");
   API_END
 }
 int dpgo_b200_get_opt_result(dpgo_b200_agent_t h, dpgo_b200_opt_result *out) {
@@ -248,6 +253,7 @@ int dpgo_b200_set_x(dpgo_b200_agent_t h, const double *X) {
   a->materialize_lookahead();
   a->drop_lookahead();
   const size_t bytes = sizeof(double) * a->r * 4 * a->n;
+  a->resid_valid = false;
   cuda_check(cudaMemcpy(a->dX.p, X, bytes, cudaMemcpyHostToDevice), "H2D X");
   if (a->P.acceleration) {
     cuda_check(cudaMemcpy(a->dV.p, X, bytes, cudaMemcpyHostToDevice), "H2D V");
@@ -323,16 +329,21 @@ int dpgo_b200_set_measurement_weight(dpgo_b200_agent_t h, int r1, int p1, int r2
   Agent *a = A(h);
   Meas *m = a->find_measurement(r1, p1, r2, p2);
   if (!m) fail(DPGO_B200_ERR_MISSING, "setMeasurementWeight: no such measurement");
+  const bool fixed_changed = m->fixed != (fixed != 0);
+  if (m->weight == w && !fixed_changed) return DPGO_B200_OK;
   m->weight = w;
   m->fixed = fixed != 0;
+  // the weight sits in Q, G, the preconditioner and the device-side loop-closure arrays; `fixed` decides whether
+  // the edge is in the re-weighting list at all
+  a->values_dirty = a->precon_dirty = a->weights_host_dirty = true;
+  if (fixed_changed) a->lc_dirty = true;
+  if (a->team) a->team->team_dirty = true;
   API_END
 }
 int dpgo_b200_compute_measurement_residual(dpgo_b200_agent_t h, int r1, int p1, int r2, int p2, double *res) {
   API_BEGIN
   Agent *a = A(h);
-  Meas *m = a->find_measurement(r1, p1, r2, p2);
-  if (!m) fail(DPGO_B200_ERR_MISSING, "computeMeasurementResidual: no such measurement");
-  if (!a->compute_residual(*m, res)) fail(DPGO_B200_ERR_MISSING, "computeMeasurementResidual: pose unavailable");
+  if (!a->compute_residual(r1, p1, r2, p2, res)) fail(DPGO_B200_ERR_MISSING, "computeMeasurementResidual: pose unavailable");
   API_END
 }
 double dpgo_b200_robust_weight(dpgo_b200_agent_t h, double residual) {
@@ -633,6 +644,45 @@ int dpgo_b200_debug_barrier_bench(int device, int grid, int iters, int mode, flo
   cudaEventElapsedTime(ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  API_END
+}
+// the data matrices as the device assembled them (k_assemble_values): Q dense 4n x 4n column-major from the block-CSR
+// copy AND, separately, from the ELL + overflow copy the hot phases read; G_lin = the r x 4n linear term for the
+// current inbox.  A read-out for the parity test against PoseGraph::denseQ() of the oracle; nothing is computed here.
+int dpgo_b200_debug_dense_q(dpgo_b200_agent_t h, double *Q_csr, double *Q_ell) {
+  API_BEGIN
+  Agent *a = A(h);
+  cuda_check(cudaSetDevice(a->device), "cudaSetDevice");
+  a->team->prepare();
+  const int n = a->n;
+  const size_t N = (size_t)4 * n;
+  auto put = [&](double *Q, int out_pose, int col_pose, const double *blk) {
+    // out_j += X_col * blk  =>  Q(4 col + p, 4 out + q) = blk(p, q)
+    for (int q = 0; q < 4; ++q)
+      for (int p = 0; p < 4; ++p) Q[((size_t)4 * out_pose + q) * N + (size_t)4 * col_pose + p] += blk[q * 4 + p];
+  };
+  if (Q_csr) {
+    std::memset(Q_csr, 0, sizeof(double) * N * N);
+    std::vector<double> val(a->h_q_col.size() * 16);
+    cuda_check(cudaMemcpy(val.data(), a->d_q_val.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H Q");
+    for (int j = 0; j < n; ++j)
+      for (int e = a->h_q_rowptr[j]; e < a->h_q_rowptr[j + 1]; ++e) put(Q_csr, j, a->h_q_col[e], &val[(size_t)e * 16]);
+  }
+  if (Q_ell) {
+    std::memset(Q_ell, 0, sizeof(double) * N * N);
+    std::vector<int> ec((size_t)n * 8), orp(n + 1), oc(a->d_qo_col.n);
+    std::vector<double> ev((size_t)n * 8 * 16), ov(a->d_qo_val.n);
+    cuda_check(cudaMemcpy(ec.data(), a->d_qe_col.p, ec.size() * sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+    cuda_check(cudaMemcpy(ev.data(), a->d_qe_val.p, ev.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H");
+    cuda_check(cudaMemcpy(orp.data(), a->d_qo_rowptr.p, orp.size() * sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+    cuda_check(cudaMemcpy(oc.data(), a->d_qo_col.p, oc.size() * sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+    cuda_check(cudaMemcpy(ov.data(), a->d_qo_val.p, ov.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H");
+    for (int j = 0; j < n; ++j) {
+      for (int k = 0; k < 8; ++k)
+        if (ec[(size_t)j * 8 + k] >= 0) put(Q_ell, j, ec[(size_t)j * 8 + k], &ev[((size_t)j * 8 + k) * 16]);
+      for (int e = orp[j]; e < orp[j + 1]; ++e) put(Q_ell, j, oc[e], &ov[(size_t)e * 16]);
+    }
+  }
   API_END
 }
 int dpgo_b200_debug_host_profile(dpgo_b200_agent_t h, double *out3, int reset) {

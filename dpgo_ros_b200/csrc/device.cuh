@@ -27,6 +27,9 @@ struct AgentStat {
 
 struct AgentDev {
   int id, n, r, n_in;
+  // readyToTerminate gate under robust costs: the share of loop closures whose weight has settled at 0 or 1 is at
+  // least robustOptMinConvergenceRatio (src/PGOAgentROSNode.cpp:214); recomputed on the host at every weight change
+  int conv_ok;
   // state
   double *X, *Y, *V, *Xinit;
   // Q as block-CSR by OUTPUT pose j: out_j += X_{col} * val (4x4 col-major)

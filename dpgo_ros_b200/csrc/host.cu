@@ -28,17 +28,6 @@ static inline cudaError_t use_device(int device) {
   return cudaSetDevice(device);
 }
 
-// T~ = [R t; 0 1], Omega = w diag(kappa, kappa, kappa, tau)
-static void edge_blocks(const Meas &m, double *T, double *Om) {
-  std::memset(T, 0, 16 * sizeof(double));
-  for (int j = 0; j < 3; ++j)
-    for (int i = 0; i < 3; ++i) T[j * 4 + i] = m.R[j * 3 + i];
-  for (int i = 0; i < 3; ++i) T[12 + i] = m.t[i];
-  T[15] = 1.0;
-  Om[0] = Om[1] = Om[2] = m.weight * m.kappa;
-  Om[3] = m.weight * m.tau;
-}
-
 // ============================================================================
 // Agent
 // ============================================================================
@@ -78,14 +67,17 @@ void Agent::add_measurement(const Meas &m) {
   if (have.count(key)) return;  // hasMeasurement, :276
   if (m.r1 < 0 || m.r2 < 0 || m.r1 >= P.num_robots || m.r2 >= P.num_robots || m.p1 < 0 || m.p2 < 0)
     fail(DPGO_B200_ERR_INVALID, "measurement index out of range");
-  have.insert(key);
   if (m.r1 == id && m.r2 == id) {
-    if (m.p1 + 1 == m.p2)
+    if (m.p1 + 1 == m.p2) {
+      have[key] = {0, (int)odom.size()};
       odom.push_back(m);
-    else
+    } else {
+      have[key] = {1, (int)plc.size()};
       plc.push_back(m);
+    }
     n = std::max(n, std::max(m.p1, m.p2) + 1);
   } else {
+    have[key] = {2, (int)slc.size()};
     slc.push_back(m);
     if (m.r1 == id) {
       n = std::max(n, m.p1 + 1);
@@ -97,16 +89,22 @@ void Agent::add_measurement(const Meas &m) {
   }
   if (la_used > 0 && !structure_dirty) materialize_lookahead();
   drop_lookahead();
-  structure_dirty = values_dirty = precon_dirty = wiring_dirty = true;
+  structure_dirty = values_dirty = precon_dirty = wiring_dirty = lc_dirty = weights_host_dirty = true;
+  resid_valid = false;
   pub_frames_cache.clear();
   if (team) team->team_dirty = true;
 }
 
 Meas *Agent::find_measurement(int r1, int p1, int r2, int p2) {
-  for (auto *vec : {&odom, &plc, &slc})
-    for (auto &m : *vec)
-      if (m.r1 == r1 && m.p1 == p1 && m.r2 == r2 && m.p2 == p2) return &m;
-  return nullptr;
+  auto it = have.find({{r1, p1}, {r2, p2}});
+  if (it == have.end()) return nullptr;
+  return &(it->second.first == 0 ? odom : (it->second.first == 1 ? plc : slc))[it->second.second];
+}
+int Agent::measurement_index(int r1, int p1, int r2, int p2) const {
+  auto it = have.find({{r1, p1}, {r2, p2}});
+  if (it == have.end()) return -1;
+  const int base = it->second.first == 0 ? 0 : (it->second.first == 1 ? (int)odom.size() : (int)(odom.size() + plc.size()));
+  return base + it->second.second;
 }
 
 const std::vector<int> &Agent::my_public_frames(int nbr) const {
@@ -294,6 +292,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
       }
   }
   drop_lookahead();
+  resid_valid = false;
   dX.upload(X);
   dXinit.upload(X);
   dY.upload(X);
@@ -308,6 +307,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
 
 void Agent::reset() {
   drop_lookahead();
+  resid_valid = false;
   instance++;
   iter = 0;
   state = 0;
@@ -403,12 +403,125 @@ void Agent::build_structure() {
     outbox_range[b] = {outbox_total, cnt};
     outbox_total += cnt;
   }
-  // loop closures subject to reweighting
-  lc_list.clear();
-  for (auto &m : plc)
-    if (!m.fixed) lc_list.push_back(&m);
-  for (auto &m : slc)
-    if (!m.fixed) lc_list.push_back(&m);
+  // ---- the measurements on the device: [odom | plc | slc]
+  {
+    const int M = num_meas();
+    std::vector<double> R((size_t)M * 9), t((size_t)M * 3), ka(M), ta(M);
+    std::vector<int> src(M), dst(M);
+    std::vector<unsigned char> fl(M);
+    for (int e = 0; e < M; ++e) {
+      const Meas &m = meas_at(e);
+      const bool sr = m.r1 != id, dr = m.r2 != id;
+      fl[e] = (unsigned char)((sr ? 1 : 0) | (dr ? 2 : 0));
+      src[e] = sr ? slot_of[{m.r1, m.p1}] : m.p1;
+      dst[e] = dr ? slot_of[{m.r2, m.p2}] : m.p2;
+      std::memcpy(&R[(size_t)e * 9], m.R, 9 * sizeof(double));
+      std::memcpy(&t[(size_t)e * 3], m.t, 3 * sizeof(double));
+      ka[e] = m.kappa;
+      ta[e] = m.tau;
+    }
+    d_m_R.upload(R);
+    d_m_t.upload(t);
+    d_m_kappa.upload(ka);
+    d_m_tau.upload(ta);
+    d_m_src.upload(src);
+    d_m_dst.upload(dst);
+    d_m_flags.upload(fl);
+    d_m_w.alloc(M);
+    d_m_skip.alloc(M);
+    d_m_resid.alloc(M);
+    weights_host_dirty = true;
+    resid_valid = false;
+  }
+  // ---- which (measurement, role) pairs land in which Q slot, in measurement order (k_assemble_values)
+  {
+    const size_t nq = h_q_col.size();
+    std::vector<std::vector<int>> items(nq);
+    auto slot = [&](int col, int row) {  // block multiplying X_col in output pose `row`
+      auto b = h_q_col.begin() + h_q_rowptr[row], e = h_q_col.begin() + h_q_rowptr[row + 1];
+      return (size_t)(std::lower_bound(b, e, col) - h_q_col.begin());
+    };
+    const int no = (int)odom.size(), np = (int)plc.size();
+    for (int e = 0; e < no + np; ++e) {
+      const Meas &m = meas_at(e);
+      items[slot(m.p1, m.p1)].push_back(e * 4 + 0);
+      items[slot(m.p2, m.p2)].push_back(e * 4 + 1);
+      items[slot(m.p1, m.p2)].push_back(e * 4 + 2);
+      items[slot(m.p2, m.p1)].push_back(e * 4 + 3);
+    }
+    for (int k = 0; k < (int)slc.size(); ++k) {
+      const Meas &m = slc[k];
+      const int e = no + np + k;
+      if (m.r1 == id)
+        items[slot(m.p1, m.p1)].push_back(e * 4 + 0);
+      else
+        items[slot(m.p2, m.p2)].push_back(e * 4 + 1);
+    }
+    std::vector<int> ptr(nq + 1, 0), flat;
+    for (size_t q = 0; q < nq; ++q) {
+      flat.insert(flat.end(), items[q].begin(), items[q].end());
+      ptr[q + 1] = (int)flat.size();
+    }
+    if (flat.empty()) flat.push_back(0);
+    d_qc_ptr.upload(ptr);
+    d_qc_item.upload(flat);
+    // ELL(8) layout of Q + overflow: columns here, values by the kernel
+    constexpr int W = 8;
+    std::vector<int> ec((size_t)n * W, -1), orp(n + 1, 0), oc, qdst(std::max<size_t>(nq, 1), 0);
+    for (int j = 0; j < n; ++j) {
+      int k = 0;
+      for (int e = h_q_rowptr[j]; e < h_q_rowptr[j + 1]; ++e, ++k) {
+        if (k < W) {
+          ec[(size_t)j * W + k] = h_q_col[e];
+          qdst[e] = j * W + k;
+        } else {
+          qdst[e] = -(1 + (int)oc.size());
+          oc.push_back(h_q_col[e]);
+        }
+      }
+      orp[j + 1] = (int)oc.size();
+    }
+    d_q_dst.upload(qdst);
+    d_qe_col.upload(ec);
+    d_qe_val.alloc((size_t)n * W * 16);
+    d_qo_rowptr.upload(orp);
+    d_qo_val.alloc(std::max<size_t>(oc.size(), 1) * 16);
+    if (oc.empty()) oc.push_back(0);
+    d_qo_col.upload(oc);
+    d_q_val.alloc(std::max<size_t>(nq, 1) * 16);
+  }
+  // ---- linear-term blocks: one per shared edge, in the order of h_s_slot (per pose, slc order)
+  {
+    const int base = (int)(odom.size() + plc.size());
+    const size_t ns = s_edge.size();
+    std::vector<int> item(std::max<size_t>(ns, 1), 0), sdst(std::max<size_t>(ns, 1), 0);
+    for (size_t k = 0; k < ns; ++k) item[k] = (base + s_edge[k]) * 2 + (slc[s_edge[k]].r1 == id ? 0 : 1);
+    constexpr int W = 4;
+    std::vector<int> ec((size_t)n * W, -1), orp(n + 1, 0), oc;
+    for (int j = 0; j < n; ++j) {
+      int k = 0;
+      for (int e = h_s_rowptr[j]; e < h_s_rowptr[j + 1]; ++e, ++k) {
+        if (k < W) {
+          ec[(size_t)j * W + k] = h_s_slot[e];
+          sdst[e] = j * W + k;
+        } else {
+          sdst[e] = -(1 + (int)oc.size());
+          oc.push_back(h_s_slot[e]);
+        }
+      }
+      orp[j + 1] = (int)oc.size();
+    }
+    d_s_item.upload(item);
+    d_s_dst.upload(sdst);
+    d_se_slot.upload(ec);
+    d_se_val.alloc((size_t)n * W * 16);
+    d_so_rowptr.upload(orp);
+    d_so_val.alloc(std::max<size_t>(oc.size(), 1) * 16);
+    if (oc.empty()) oc.push_back(0);
+    d_so_slot.upload(oc);
+    d_s_val.alloc(std::max<size_t>(ns, 1) * 16);
+  }
+  lc_dirty = true;
 
   d_q_rowptr.upload(h_q_rowptr);
   d_q_col.upload(h_q_col);
@@ -440,163 +553,78 @@ void Agent::build_structure() {
   wiring_dirty = true;
 }
 
-void Agent::build_values() {
-  std::vector<double> qv((size_t)h_q_col.size() * 16, 0.0);
-  auto entry = [&](int i, int j) -> double * {
-    auto b = h_q_col.begin() + h_q_rowptr[j], e = h_q_col.begin() + h_q_rowptr[j + 1];
-    auto it = std::lower_bound(b, e, i);
-    return &qv[(size_t)(it - h_q_col.begin()) * 16];
-  };
-  double T[16], Om[4], TOm[16], TOmTt[16];
-  auto prep = [&](const Meas &m) {
-    edge_blocks(m, T, Om);
-    for (int j = 0; j < 4; ++j)
-      for (int i = 0; i < 4; ++i) TOm[j * 4 + i] = T[j * 4 + i] * Om[j];
-    for (int j = 0; j < 4; ++j)
-      for (int i = 0; i < 4; ++i) {
-        double s = 0;
-        for (int k = 0; k < 4; ++k) s += TOm[k * 4 + i] * T[k * 4 + j];
-        TOmTt[j * 4 + i] = s;
-      }
-  };
-  for (auto *vec : {&odom, &plc})
-    for (const auto &m : *vec) {
-      prep(m);
-      double *ii = entry(m.p1, m.p1), *jj = entry(m.p2, m.p2), *ij = entry(m.p1, m.p2), *ji = entry(m.p2, m.p1);
-      for (int q = 0; q < 16; ++q) ii[q] += TOmTt[q];
-      for (int c = 0; c < 4; ++c) jj[c * 4 + c] += Om[c];
-      for (int q = 0; q < 16; ++q) ij[q] -= TOm[q];                       // Q_ij = -T Om
-      for (int j = 0; j < 4; ++j)
-        for (int i = 0; i < 4; ++i) ji[j * 4 + i] -= TOm[i * 4 + j];      // Q_ji = -(T Om)^T
+// loop closures subject to re-weighting: every non-fixed private / shared loop closure; the lower-ID robot owns a
+// shared edge's weight (src/PGOAgentROS.cpp:732, 1340)
+void Agent::build_lc_list() {
+  lc_meas.clear();
+  lc_mask.clear();
+  const int no = (int)odom.size(), np = (int)plc.size();
+  for (int k = 0; k < np; ++k)
+    if (!plc[k].fixed) {
+      lc_meas.push_back(no + k);
+      lc_mask.push_back(1);
     }
-  for (const auto &m : slc) {
+  for (int k = 0; k < (int)slc.size(); ++k)
+    if (!slc[k].fixed) {
+      const int other = slc[k].r1 == id ? slc[k].r2 : slc[k].r1;
+      lc_meas.push_back(no + np + k);
+      lc_mask.push_back(other >= id ? 1 : 0);
+    }
+  std::vector<int> lm = lc_meas;
+  std::vector<unsigned char> mk = lc_mask;
+  if (lm.empty()) {
+    lm.push_back(0);
+    mk.push_back(0);
+  }
+  d_lc_meas.upload(lm);
+  d_lc_mask.upload(mk);
+  d_lc_residual.alloc(lm.size());
+  lc_dirty = false;
+}
+
+void Agent::upload_weights() {
+  const int M = num_meas();
+  std::vector<double> w(M);
+  for (int e = 0; e < M; ++e) w[e] = meas_at(e).weight;
+  d_m_w.upload(w);
+  weights_host_dirty = false;
+}
+
+MeasDev Agent::meas_view() const {
+  return MeasDev{num_meas(), d_m_R.p, d_m_t.p, d_m_kappa.p, d_m_tau.p, d_m_w.p, d_m_skip.p, d_m_src.p, d_m_dst.p,
+                 d_m_flags.p};
+}
+AssembleDev Agent::assemble_view() const {
+  AssembleDev A{};
+  A.nq = (int)h_q_col.size();
+  A.ns = (int)h_s_slot.size();
+  A.qc_ptr = d_qc_ptr.p; A.qc_item = d_qc_item.p; A.q_dst = d_q_dst.p;
+  A.s_item = d_s_item.p; A.s_dst = d_s_dst.p;
+  A.q_val = d_q_val.p; A.qe_val = d_qe_val.p; A.qo_val = d_qo_val.p;
+  A.s_val = d_s_val.p; A.se_val = d_se_val.p; A.so_val = d_so_val.p;
+  return A;
+}
+
+// Q and the linear-term blocks from the measurements, on the device (assemble.cu).  What crosses from the host is at
+// most the weight vector (when the host changed a weight: setMeasurementWeight, a neighbour's weights) and the
+// per-measurement "neighbour deactivated" flags -- never a matrix.
+void Agent::build_values() {
+  if (lc_dirty) build_lc_list();
+  if (weights_host_dirty) upload_weights();
+  {
     // shared loop closures with a deactivated neighbour leave the problem (upstream's default; the alternative,
     // useInactiveNeighbors(true), is commented out in the wrapper: src/PGOAgentROS.cpp:151-156)
-    if (inactive_robots.count(m.r1 == id ? m.r2 : m.r1)) continue;
-    prep(m);
-    if (m.r1 == id) {
-      double *ii = entry(m.p1, m.p1);
-      for (int q = 0; q < 16; ++q) ii[q] += TOmTt[q];
-    } else {
-      double *jj = entry(m.p2, m.p2);
-      for (int c = 0; c < 4; ++c) jj[c * 4 + c] += Om[c];
-    }
+    const int M = num_meas(), base = (int)(odom.size() + plc.size());
+    std::vector<unsigned char> skip(M, 0);
+    if (!inactive_robots.empty())
+      for (int k = 0; k < (int)slc.size(); ++k)
+        if (inactive_robots.count(slc[k].r1 == id ? slc[k].r2 : slc[k].r1)) skip[base + k] = 1;
+    d_m_skip.upload(skip);
   }
-  d_q_val.upload(qv);
-  {
-    // ELL(8) copy of Q + overflow
-    constexpr int W = 8;
-    std::vector<int> ec((size_t)n * W, -1), orp(n + 1, 0), oc;
-    std::vector<double> ev((size_t)n * W * 16, 0.0), ov;
-    for (int j = 0; j < n; ++j) {
-      int k = 0;
-      for (int e = h_q_rowptr[j]; e < h_q_rowptr[j + 1]; ++e, ++k) {
-        if (k < W) {
-          ec[(size_t)j * W + k] = h_q_col[e];
-          std::memcpy(&ev[((size_t)j * W + k) * 16], &qv[(size_t)e * 16], 16 * sizeof(double));
-        } else {
-          oc.push_back(h_q_col[e]);
-          ov.insert(ov.end(), qv.begin() + (size_t)e * 16, qv.begin() + (size_t)e * 16 + 16);
-        }
-      }
-      orp[j + 1] = (int)oc.size();
-    }
-    if (oc.empty()) {
-      oc.push_back(0);
-      ov.assign(16, 0.0);
-    }
-    d_qe_col.upload(ec);
-    d_qe_val.upload(ev);
-    d_qo_rowptr.upload(orp);
-    d_qo_col.upload(oc);
-    d_qo_val.upload(ov);
-  }
-  // G blocks in the order of h_s_slot (per pose, slc order)
-  std::vector<double> sv((size_t)h_s_slot.size() * 16, 0.0);
-  {
-    std::vector<std::vector<int>> sl(n);
-    for (size_t e = 0; e < slc.size(); ++e) sl[slc[e].r1 == id ? slc[e].p1 : slc[e].p2].push_back((int)e);
-    size_t k = 0;
-    for (int j = 0; j < n; ++j)
-      for (int e : sl[j]) {
-        const auto &m = slc[e];
-        edge_blocks(m, T, Om);
-        double *M = &sv[k * 16];
-        if (inactive_robots.count(m.r1 == id ? m.r2 : m.r1)) {   // block stays zero: no pull towards a lost neighbour
-          ++k;
-          continue;
-        }
-        if (m.r1 == id) {  // outgoing: G_i -= X_j Om T^T
-          for (int jj = 0; jj < 4; ++jj)
-            for (int ii = 0; ii < 4; ++ii) M[jj * 4 + ii] = -Om[ii] * T[ii * 4 + jj];
-        } else {  // incoming: G_j -= X_i T Om
-          for (int jj = 0; jj < 4; ++jj)
-            for (int ii = 0; ii < 4; ++ii) M[jj * 4 + ii] = -T[jj * 4 + ii] * Om[jj];
-        }
-        ++k;
-      }
-  }
-  d_s_val.upload(sv);
-  {
-    // ELL(4) copy of the neighbour term + overflow
-    constexpr int W = 4;
-    std::vector<int> ec((size_t)n * W, -1), orp(n + 1, 0), oc;
-    std::vector<double> ev((size_t)n * W * 16, 0.0), ov;
-    for (int j = 0; j < n; ++j) {
-      int k = 0;
-      for (int e = h_s_rowptr[j]; e < h_s_rowptr[j + 1]; ++e, ++k) {
-        if (k < W) {
-          ec[(size_t)j * W + k] = h_s_slot[e];
-          std::memcpy(&ev[((size_t)j * W + k) * 16], &sv[(size_t)e * 16], 16 * sizeof(double));
-        } else {
-          oc.push_back(h_s_slot[e]);
-          ov.insert(ov.end(), sv.begin() + (size_t)e * 16, sv.begin() + (size_t)e * 16 + 16);
-        }
-      }
-      orp[j + 1] = (int)oc.size();
-    }
-    if (oc.empty()) {
-      oc.push_back(0);
-      ov.assign(16, 0.0);
-    }
-    d_se_slot.upload(ec);
-    d_se_val.upload(ev);
-    d_so_rowptr.upload(orp);
-    d_so_slot.upload(oc);
-    d_so_val.upload(ov);
-  }
-  // loop-closure arrays
-  const size_t L = lc_list.size();
-  std::vector<int> src(L), dst(L);
-  std::vector<unsigned char> sr(L), dr(L), mask(L);
-  std::vector<double> R(L * 9), t(L * 3), ka(L), ta(L), w(L);
-  for (size_t e = 0; e < L; ++e) {
-    const Meas &m = *lc_list[e];
-    sr[e] = m.r1 != id;
-    dr[e] = m.r2 != id;
-    src[e] = sr[e] ? slot_of[{m.r1, m.p1}] : m.p1;
-    dst[e] = dr[e] ? slot_of[{m.r2, m.p2}] : m.p2;
-    const int other = sr[e] ? m.r1 : (dr[e] ? m.r2 : id);
-    mask[e] = (other >= id);  // lower ID owns a shared edge's weight (src/PGOAgentROS.cpp:732,1340)
-    std::memcpy(&R[e * 9], m.R, 9 * sizeof(double));
-    std::memcpy(&t[e * 3], m.t, 3 * sizeof(double));
-    ka[e] = m.kappa;
-    ta[e] = m.tau;
-    w[e] = m.weight;
-  }
-  d_lc_src.upload(src);
-  d_lc_dst.upload(dst);
-  d_lc_src_remote.upload(sr);
-  d_lc_dst_remote.upload(dr);
-  d_lc_mask.upload(mask);
-  d_lc_R.upload(R);
-  d_lc_t.upload(t);
-  d_lc_kappa.upload(ka);
-  d_lc_tau.upload(ta);
-  d_lc_weight.upload(w);
-  d_lc_residual.alloc(L);
+  cuda_check(launch_assemble_values(meas_view(), assemble_view(), 0), "k_assemble_values");
   values_dirty = false;
   precon_dirty = true;
+  resid_valid = false;
 }
 
 void Agent::build_preconditioner() {
@@ -625,12 +653,14 @@ void Agent::ensure_device() {
   cuda_check(use_device(device), "cudaSetDevice");
   if (structure_dirty) build_structure();
   if (values_dirty) build_values();
+  if (lc_dirty) build_lc_list();
   if (precon_dirty) build_preconditioner();
 }
 
 AgentDev Agent::dev_view() const {
   AgentDev A{};
   A.id = id; A.n = n; A.r = r; A.n_in = (int)slot_key.size();
+  A.conv_ok = weights_converged() ? 1 : 0;
   A.X = dX.p; A.Y = dY.p; A.V = dV.p; A.Xinit = dXinit.p;
   A.q_rowptr = d_q_rowptr.p; A.q_col = d_q_col.p; A.q_val = d_q_val.p;
   A.s_rowptr = d_s_rowptr.p; A.s_slot = d_s_slot.p; A.s_val = d_s_val.p;
@@ -651,16 +681,33 @@ AgentDev Agent::dev_view() const {
   return A;
 }
 
+// (accepted + rejected) / total loop closures >= robustOptMinConvergenceRatio; counted like PoseGraph::statistics()
+// (src/PGOAgentROS.cpp:1058-1067): weight exactly 1 = accepted, exactly 0 = rejected
+bool Agent::weights_converged() const {
+  if (!(P.robust_opt_min_convergence_ratio > 0.0)) return true;
+  size_t total = 0, settled = 0;
+  for (auto *vec : {&plc, &slc})
+    for (const auto &m : *vec) {
+      ++total;
+      if (m.weight == 1.0 || m.weight == 0.0) ++settled;
+    }
+  return total == 0 || (double)settled >= P.robust_opt_min_convergence_ratio * (double)total;
+}
+
 bool Agent::all_inbox_valid(bool aux) const {
+  // Slots of a DEACTIVATED neighbour never fill (it sends nothing, src/PGOAgentROS.cpp:377-400) and are not read:
+  // its shared loop closures have zero blocks in Q and G (build_values), as in the oracle (Agent::iterate skips
+  // inactive neighbours before the pose look-up).
   const auto &v = aux ? inbox_valid_aux : inbox_valid_reg;
-  for (char c : v)
-    if (!c) return false;
+  for (size_t s = 0; s < v.size(); ++s)
+    if (!v[s] && !inactive_robots.count(slot_key[s].first)) return false;
   return true;
 }
 
 // ---- iterate (standalone path: a team of one, neighbours fed through the inbox)
 bool Agent::iterate(bool do_opt) {
   cuda_check(use_device(device), "cudaSetDevice");
+  resid_valid = false;
   Team *tm = team;
   if (state != 2) {
     iter++;
@@ -742,6 +789,7 @@ int Agent::get_shared_pose_dict(int nbr, bool aux, int *frames, double *poses, i
 void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const double *poses, int count) {
   cuda_check(use_device(device), "cudaSetDevice");
   if (structure_dirty) build_structure();
+  resid_valid = false;
   // stage in pinned host memory; the next launch uploads the inbox with one async copy
   double *inbox = h_inbox + (aux ? (size_t)slot_key.size() * 4 * r : 0);
   auto &valid = aux ? inbox_valid_aux : inbox_valid_reg;
@@ -852,45 +900,40 @@ void Agent::update_measurement_weights() {
   team->gnc_update_all();
 }
 
-bool Agent::compute_residual(const Meas &m, double *res) {
-  if (state != 2) return false;
+// computeMeasurementResidual (src/PGOAgentROS.cpp:1049).  The TERMINATE handler asks for every active loop closure in
+// turn (:1044-1057; ~1000 per robot on the tunnels dataset): the first call runs ONE launch over all measurements and
+// the rest are served from the cached array until X, the inbox or the graph change.
+void Agent::refresh_residuals() {
   cuda_check(use_device(device), "cudaSetDevice");
-  team->prepare();
-  // single-measurement residual through the same kernel as the weight update
-  DevBuf<int> src, dst;
-  DevBuf<unsigned char> sr, dr, mask;
-  DevBuf<double> R, t, ka, ta, w, rs;
-  const bool s_rem = m.r1 != id, d_rem = m.r2 != id;
-  int si, di;
-  if (s_rem) {
+  team->prepare();  // materialises a consumed lookahead, flushes the staged inbox
+  const int M = num_meas();
+  h_resid.assign(M, 0.0);
+  if (M > 0) {
+    ResidualJob J{M, nullptr, nullptr, d_m_resid.p, 0.0, 0.0, 0};
+    cuda_check(launch_measurement_residuals(meas_view(), J, r, dX.p, d_inbox_reg(), team->stream), "k_measurement_residuals");
+    cuda_check(cudaMemcpyAsync(h_resid.data(), d_m_resid.p, sizeof(double) * M, cudaMemcpyDeviceToHost, team->stream),
+               "D2H residuals");
+    cuda_check(cudaStreamSynchronize(team->stream), "k_measurement_residuals");
+  }
+  resid_valid = true;
+}
+
+bool Agent::compute_residual(int r1, int p1, int r2, int p2, double *res) {
+  if (state != 2) return false;
+  const int idx = measurement_index(r1, p1, r2, p2);
+  if (idx < 0) fail(DPGO_B200_ERR_MISSING, "computeMeasurementResidual: no such measurement");
+  if (structure_dirty) resid_valid = false;
+  if (!resid_valid) refresh_residuals();
+  const Meas &m = meas_at(idx);
+  if (m.r1 != id) {
     auto it = slot_of.find({m.r1, m.p1});
     if (it == slot_of.end() || !inbox_valid_reg[it->second]) return false;
-    si = it->second;
-  } else {
-    si = m.p1;
   }
-  if (d_rem) {
+  if (m.r2 != id) {
     auto it = slot_of.find({m.r2, m.p2});
     if (it == slot_of.end() || !inbox_valid_reg[it->second]) return false;
-    di = it->second;
-  } else {
-    di = m.p2;
   }
-  src.upload({si});
-  dst.upload({di});
-  sr.upload({(unsigned char)s_rem});
-  dr.upload({(unsigned char)d_rem});
-  mask.upload({(unsigned char)0});
-  R.upload(std::vector<double>(m.R, m.R + 9));
-  t.upload(std::vector<double>(m.t, m.t + 3));
-  ka.upload({m.kappa});
-  ta.upload({m.tau});
-  w.upload({m.weight});
-  rs.alloc(1);
-  LcDev L{1, src.p, dst.p, sr.p, dr.p, mask.p, R.p, t.p, ka.p, ta.p, w.p, rs.p};
-  cuda_check(launch_gnc_weights(L, r, dX.p, d_inbox_reg(), P.gnc_barc * P.gnc_barc, mu, P.cost_type, 0),
-             "gnc_weights");
-  cuda_check(cudaMemcpy(res, rs.p, sizeof(double), cudaMemcpyDeviceToHost), "D2H residual");
+  *res = h_resid[idx];
   return true;
 }
 
@@ -1327,6 +1370,7 @@ void Team::read_back() {
 void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, float *ms) {
   RunArgs args = args_in;
   args.seq = ++seq;
+  for (Agent *a : agents) a->resid_valid = false;
   // Nesterov sequences (a7): gamma_k = (1 + sqrt(1 + 4 N^2 gamma_{k-1}^2)) / 2N, alpha_k = 1 / (gamma_k N),
   // reset on restart iterations ((iter + 1) % restartInterval == 0)
   const dpgo_b200_params &P = agents[0]->P;
@@ -1566,16 +1610,20 @@ void Team::gnc_compute_weights() {
   prepare();
   for (Agent *a : agents) {
     if (a->state != 2) continue;
-    const size_t L = a->lc_list.size();
+    const size_t L = a->lc_meas.size();
     if (L) {
-      LcDev Ld{(int)L, a->d_lc_src.p, a->d_lc_dst.p, a->d_lc_src_remote.p, a->d_lc_dst_remote.p, a->d_lc_mask.p,
-               a->d_lc_R.p, a->d_lc_t.p, a->d_lc_kappa.p, a->d_lc_tau.p, a->d_lc_weight.p, a->d_lc_residual.p};
-      cuda_check(launch_gnc_weights(Ld, a->r, a->dX.p, a->d_inbox_reg(), a->P.gnc_barc * a->P.gnc_barc, a->mu,
-                                    a->P.cost_type, 0),
-                 "gnc_weights");
-      std::vector<double> w(L);
-      cuda_check(cudaMemcpy(w.data(), a->d_lc_weight.p, L * sizeof(double), cudaMemcpyDeviceToHost), "D2H weights");
-      for (size_t e = 0; e < L; ++e) a->lc_list[e]->weight = w[e];
+      // residual + GNC-TLS weight on the device; the weights this agent owns are rewritten in MeasDev::w, which is
+      // what k_assemble_values reads when gnc_finish_update marks the data matrices stale
+      ResidualJob J{(int)L, a->d_lc_meas.p, a->d_lc_mask.p, a->d_lc_residual.p, a->P.gnc_barc * a->P.gnc_barc, a->mu,
+                    a->P.cost_type};
+      cuda_check(launch_measurement_residuals(a->meas_view(), J, a->r, a->dX.p, a->d_inbox_reg(), stream), "gnc_weights");
+      // host mirror (get_lc_weights, the owner -> neighbour weight messages): owned entries only
+      std::vector<double> w(a->num_meas());
+      cuda_check(cudaMemcpyAsync(w.data(), a->d_m_w.p, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream),
+                 "D2H weights");
+      cuda_check(cudaStreamSynchronize(stream), "gnc_weights");
+      for (size_t e = 0; e < L; ++e)
+        if (a->lc_mask[e]) a->meas_at(a->lc_meas[e]).weight = w[a->lc_meas[e]];
     }
   }
   // publishMeasurementWeights (:721-754) -> measurementWeightsCallback (:1315-1353)
@@ -1587,8 +1635,10 @@ void Team::gnc_compute_weights() {
           if (o->id == other) {
             Meas *mm = o->find_measurement(m.r1, m.p1, m.r2, m.p2);
             if (mm) {
+              if (mm->fixed != m.fixed) o->lc_dirty = true;
               mm->weight = m.weight;
               mm->fixed = m.fixed;
+              o->weights_host_dirty = true;
             }
           }
     }
@@ -1601,6 +1651,7 @@ void Team::gnc_finish_update() {
     a->weight_update_count++;
     a->robust_inner_iter = 0;
     a->values_dirty = a->precon_dirty = true;
+    a->resid_valid = false;
     const size_t bytes = (size_t)a->r * 4 * a->n * sizeof(double);
     if (a->weight_update_count <= a->P.robust_opt_num_resets)
       cuda_check(cudaMemcpy(a->dX.p, a->dXinit.p, bytes, cudaMemcpyDeviceToDevice), "reset X");

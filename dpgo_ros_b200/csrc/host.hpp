@@ -70,6 +70,7 @@ class Agent {
   // ---- pose graph
   void add_measurement(const Meas &m);
   Meas *find_measurement(int r1, int p1, int r2, int p2);
+  int measurement_index(int r1, int p1, int r2, int p2) const;  // position in [odom | plc | slc], -1 if unknown
   std::vector<int> neighbors() const { return std::vector<int>(nbrs.begin(), nbrs.end()); }
   const std::vector<int> &my_public_frames(int nbr) const;  // sorted; cached until the pose graph changes
 
@@ -90,7 +91,8 @@ class Agent {
   bool should_terminate() const;
   bool should_update_weights() const;
   void update_measurement_weights();  // standalone (team of one) path
-  bool compute_residual(const Meas &m, double *res);
+  bool compute_residual(int r1, int p1, int r2, int p2, double *res);
+  void refresh_residuals();  // one launch over every measurement, cached until X / the inbox / the graph change
   double robust_weight(double residual) const;
 
   // ---- device structures
@@ -101,6 +103,7 @@ class Agent {
   bool need_preconditioner() const { return P.method == 0 || P.rgd_use_preconditioner; }
   AgentDev dev_view() const;
   bool all_inbox_valid(bool aux) const;
+  bool weights_converged() const;
 
   // identity / params
   int id;
@@ -114,7 +117,8 @@ class Agent {
   // pose graph (host)
   int n = 0;
   std::vector<Meas> odom, plc, slc;
-  std::set<std::pair<std::pair<int, int>, std::pair<int, int>>> have;
+  // (r1, p1, r2, p2) -> (0 odom / 1 plc / 2 slc, position in that vector)
+  std::map<std::pair<std::pair<int, int>, std::pair<int, int>>, std::pair<int, int>> have;
   std::set<int> nbrs;
   mutable std::map<int, std::vector<int>> pub_frames_cache;
   // per neighbour: the contiguous inbox slot range that holds its poses and their (sorted) frame ids
@@ -148,6 +152,8 @@ class Agent {
 
   // dirtiness
   bool structure_dirty = true, values_dirty = true, precon_dirty = true, wiring_dirty = true;
+  bool lc_dirty = true;        // the set of re-weightable loop closures changed (fixedWeight flipped)
+  bool weights_host_dirty = true;  // host weights newer than MeasDev::w (set by every host-side weight write)
 
   // device buffers
   DevBuf<double> dX, dY, dV, dXinit;
@@ -191,11 +197,30 @@ class Agent {
   DevBuf<double *> d_pub_dst_reg, d_pub_dst_aux;
   DevBuf<double> dPinv;
   DevBuf<double> dG, dRg, dRgT, dZ, dEta, dDlt0, dDlt1, dHd, dRv, dRvT, dX2, dX3, dRg2, dRg2T, dZeta, dS, dS2;
-  // loop-closure arrays for the GNC kernel
-  DevBuf<int> d_lc_src, d_lc_dst;
-  DevBuf<unsigned char> d_lc_src_remote, d_lc_dst_remote, d_lc_mask;
-  DevBuf<double> d_lc_R, d_lc_t, d_lc_kappa, d_lc_tau, d_lc_weight, d_lc_residual;
-  std::vector<Meas *> lc_list;  // the measurements behind the LC arrays
+  // the measurements on the device, [odom | plc | slc] (assemble.cu: MeasDev), and the slot lists of the
+  // weight-dependent blocks (AssembleDev)
+  DevBuf<double> d_m_R, d_m_t, d_m_kappa, d_m_tau, d_m_w, d_m_resid;
+  DevBuf<int> d_m_src, d_m_dst, d_qc_ptr, d_qc_item, d_q_dst, d_s_item, d_s_dst;
+  DevBuf<unsigned char> d_m_flags, d_m_skip;
+  MeasDev meas_view() const;
+  AssembleDev assemble_view() const;
+  int num_meas() const { return (int)(odom.size() + plc.size() + slc.size()); }
+  Meas &meas_at(int idx) {
+    return idx < (int)odom.size() ? odom[idx]
+                                  : (idx < (int)(odom.size() + plc.size()) ? plc[idx - odom.size()]
+                                                                           : slc[idx - odom.size() - plc.size()]);
+  }
+  // loop closures subject to re-weighting (non-fixed): measurement index + "this agent owns the weight"
+  DevBuf<int> d_lc_meas;
+  DevBuf<unsigned char> d_lc_mask;
+  DevBuf<double> d_lc_residual;
+  std::vector<int> lc_meas;
+  std::vector<unsigned char> lc_mask;
+  void build_lc_list();
+  void upload_weights();
+  // cached residuals of every measurement (TERMINATE handler, src/PGOAgentROS.cpp:1044-1057)
+  std::vector<double> h_resid;
+  bool resid_valid = false;
   // host copies of structure used for wiring
   std::vector<int> h_pub_rowptr;
   std::vector<std::pair<int, int>> h_pub_entries;  // (neighbour, my frame) per publication entry

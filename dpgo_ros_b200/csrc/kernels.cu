@@ -233,43 +233,6 @@ __global__ void __launch_bounds__(kThreads) k_publish_all(const __grid_constant_
   }
 }
 
-// GNC-TLS (a8): residual and weight of every non-fixed loop closure.
-// computeMeasurementResidual (src/PGOAgentROS.cpp:1049) + RobustCost::weight (:1050).
-__global__ void k_gnc_weights(LcDev L, int r, const double *X, const double *inbox, double barc_sq, double mu,
-                              int cost_type) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= L.count) return;
-  const double *Xi = (L.src_remote[e] ? inbox : X) + (size_t)L.src[e] * 4 * r;
-  const double *Xj = (L.dst_remote[e] ? inbox : X) + (size_t)L.dst[e] * 4 * r;
-  const double *Rm = L.R + (size_t)e * 9;  // column-major
-  const double *tm = L.t + (size_t)e * 3;
-  double rot = 0, tr = 0;
-  for (int a = 0; a < r; ++a) {
-    const double y0 = Xi[a], y1 = Xi[r + a], y2 = Xi[2 * r + a];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const double s = y0 * Rm[c * 3] + y1 * Rm[c * 3 + 1] + y2 * Rm[c * 3 + 2] - Xj[c * r + a];
-      rot += s * s;
-    }
-    const double s = Xj[3 * r + a] - Xi[3 * r + a] - (y0 * tm[0] + y1 * tm[1] + y2 * tm[2]);
-    tr += s * s;
-  }
-  const double rsq = L.kappa[e] * rot + L.tau[e] * tr;
-  L.residual[e] = sqrt(rsq);
-  double w = 1.0;
-  if (cost_type == 5) {
-    const double upper = (mu + 1.0) / mu * barc_sq;
-    const double lower = mu / (mu + 1.0) * barc_sq;
-    if (rsq >= upper)
-      w = 0.0;
-    else if (rsq <= lower)
-      w = 1.0;
-    else
-      w = sqrt(barc_sq * mu * (mu + 1.0) / rsq) - mu;
-  }
-  if (L.update_mask[e]) L.weight[e] = w;
-}
-
 // ---------------------------------------------------------------------------
 // host-side launch wrappers
 // ---------------------------------------------------------------------------
@@ -402,12 +365,4 @@ cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s) {
   k_publish_all<<<grid, kThreads, 0, s>>>(T);
   return cudaGetLastError();
 }
-cudaError_t launch_gnc_weights(const LcDev &L, int r, const double *X, const double *inbox, double barc_sq,
-                               double mu, int cost_type, cudaStream_t s) {
-  if (L.count == 0) return cudaSuccess;
-  ++g_launches;
-  k_gnc_weights<<<(L.count + 127) / 128, 128, 0, s>>>(L, r, X, inbox, barc_sq, mu, cost_type);
-  return cudaGetLastError();
-}
-
 }  // namespace dpgo

@@ -33,14 +33,35 @@ struct RunArgs {
   int skip_stats;  // 1: leave fOpt / gradNormOpt of the last step to Agent::finish_opt_stats (AgentStat::optimized = 2)
 };
 
-// non-fixed loop closures of one agent, for the GNC-TLS residual + weight kernel
-struct LcDev {
+// The agent's measurements as a structure of arrays, order [odometry | private loop closures | shared loop closures]
+// (assemble.cu).  src / dst: local pose index, or inbox slot when that end belongs to a neighbour (flags bit 0 / 1).
+struct MeasDev {
   int count;
-  const int *src, *dst;                      // local pose index, or inbox slot when remote
-  const unsigned char *src_remote, *dst_remote;
-  const unsigned char *update_mask;          // 1: this agent owns the weight
-  const double *R, *t, *kappa, *tau;         // R column-major 3x3
-  double *weight, *residual;
+  const double *R, *t, *kappa, *tau;   // R column-major 3x3
+  double *w;                           // measurement weight (GNC-TLS rewrites it on the device)
+  const unsigned char *skip;           // 1: shared edge with a deactivated neighbour -- contributes nothing
+  const int *src, *dst;
+  const unsigned char *flags;
+};
+// destination slots of the weight-dependent blocks: Q (block-CSR by output pose, nq slots, contributions
+// qc_item = measurement * 4 + role listed per slot) and the linear term (ns blocks, s_item = measurement * 2 +
+// incoming).  *_dst >= 0: ELL position (pose * W + k); < 0: -(1 + overflow index).
+struct AssembleDev {
+  int nq, ns;
+  const int *qc_ptr, *qc_item, *q_dst;
+  const int *s_item, *s_dst;
+  double *q_val, *qe_val, *qo_val;
+  double *s_val, *se_val, *so_val;
+};
+// residuals of `count` measurements (meas == nullptr: all, in order); update_mask != nullptr: entries with 1 also
+// get their GNC-TLS weight written into MeasDev::w
+struct ResidualJob {
+  int count;
+  const int *meas;
+  const unsigned char *update_mask;
+  double *residual;
+  double barc_sq, mu;
+  int cost_type;
 };
 
 long long kernel_launch_count();
@@ -64,8 +85,9 @@ cudaError_t launch_publish_all(const TeamDev &T, int grid, cudaStream_t s);
 // Z = B * P, P symmetric n4 x n4 (ld), B / Z column-major with rows <= 8 rows
 cudaError_t launch_rows_times_sym(const double *B, const double *P, size_t ld, int rows, int n4, double *Z,
                                   cudaStream_t s);
-cudaError_t launch_gnc_weights(const LcDev &L, int r, const double *X, const double *inbox, double barc_sq,
-                               double mu, int cost_type, cudaStream_t s);
+cudaError_t launch_assemble_values(const MeasDev &M, const AssembleDev &A, cudaStream_t s);
+cudaError_t launch_measurement_residuals(const MeasDev &M, const ResidualJob &J, int r, const double *X,
+                                         const double *inbox, cudaStream_t s);
 
 // dense_inverse.cu: P <- (blocks scattered) ; P <- P^-1 (SPD), N multiple of 32
 cudaError_t launch_scatter_blocks(double *P, size_t ld, const int *rowptr, const int *col, const double *val,

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         grid_reduce<1>(gs, bs, v, sm_red);
         const double relchange = sqrt(v[0] / A.n);
-        const bool ready = !(relchange > P.rel_change_tol);
+        const bool ready = !(relchange > P.rel_change_tol) && A.conv_ok;
         if (ready)
           c.ready_mask |= (1ull << sel_robot);
         else
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (rel_due & (1u << ai)) {
               const double relchange = sqrt(sm_rel[ai] / T.ag[ai].n);
               const int rid = T.ag[ai].id;
-              if (!(relchange > P.rel_change_tol))
+              if (!(relchange > P.rel_change_tol) && T.ag[ai].conv_ok)
                 c.ready_mask |= (1ull << rid);
               else
                 c.ready_mask &= ~(1ull << rid);
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const double relchange = sqrt(t[4] / T.ag[ai].n);
           st->f_init = t[0]; st->gn_init = sqrt(t[1]); st->f_opt = t[2]; st->gn_opt = sqrt(t[3]);
           st->relchange = relchange;
-          st->ready = !(relchange > P.rel_change_tol);
+          st->ready = !(relchange > P.rel_change_tol) && T.ag[ai].conv_ok;
           st->optimized = 1;
           st->tcg_iters = 0; st->rtr_outer = 0; st->rtr_rej = 0;
         }
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (rel_due & (1u << ai)) {
         const double relchange = sqrt(sm_rel[ai] / T.ag[ai].n);
         const int rid = T.ag[ai].id;
-        if (!(relchange > P.rel_change_tol))
+        if (!(relchange > P.rel_change_tol) && T.ag[ai].conv_ok)
           c.ready_mask |= (1ull << rid);
         else
           c.ready_mask &= ~(1ull << rid);

@@ -244,7 +244,10 @@ class PGOAgent {
     if (mIterationNumber != mLastIterationSeen)   // the wrapper rewound mIterationNumber (RECOVER, :1196)
       dpgo_b200_set_iteration_number(h_, (int)mIterationNumber);
     const int rc = dpgo_b200_iterate(h_, doOptimization ? 1 : 0);
-    if (rc != 0) return false;
+    // DPGO_B200_ERR_MISSING: the iteration was counted but the local solve had to be skipped (a neighbour's poses have
+    // not arrived); upstream returns the success of the solve and the wrapper logs it (:160-175)
+    if (rc != 0 && rc != DPGO_B200_ERR_MISSING) return false;
+    const bool solved = rc == 0;
     dpgo_b200_status s;
     dpgo_b200_get_status(h_, &s);
     mIterationNumber = mLastIterationSeen = (unsigned)s.iteration_number;
@@ -256,7 +259,7 @@ class PGOAgent {
     mTeamStatus[mID] = mStatus;
     if (mParams.robustCostParams.costType != RobustCostParameters::Type::L2) mRobustOptInnerIter++;
     if (mState == PGOAgentState::INITIALIZED) {
-      if (doOptimization) {
+      if (doOptimization && solved) {
         dpgo_b200_opt_result o;
         // fOpt / gradNormOpt cost a second gradient pass on the GPU: only fetched when somebody prints them (:169-172)
         (mParams.verbose ? dpgo_b200_get_opt_result : dpgo_b200_get_opt_result_lazy)(h_, &o);
@@ -269,7 +272,7 @@ class PGOAgent {
       }
       mPublishPublicPosesRequested = mParams.acceleration || doOptimization;   // :109
     }
-    return true;
+    return solved;
   }
 
   // ---- public poses (a9)
@@ -342,6 +345,7 @@ class PGOAgent {
     return mTeamStatus.at(id);
   }
   void setRobotActive(unsigned id, bool active) {                                          // :382 ... :1582
+    DPGO_SHIM_LOCK;
     if (id < mTeamRobotActive.size()) mTeamRobotActive[id] = active;
     mPoseGraph->setNeighborActive(id, active);
     if (h_ && id < mParams.numRobots) dpgo_b200_set_robot_active(h_, (int)id, active ? 1 : 0);
@@ -365,7 +369,10 @@ class PGOAgent {
   }
 
   // ---- GNC (a8)
-  bool shouldUpdateMeasurementWeights() { return dpgo_b200_should_update_measurement_weights(h_) == 1; }   // :210
+  bool shouldUpdateMeasurementWeights() {                                                  // :210
+    DPGO_SHIM_LOCK;
+    return dpgo_b200_should_update_measurement_weights(h_) == 1;
+  }
   void updateMeasurementWeights() {                                                        // :1218
     DPGO_SHIM_LOCK;
     check(dpgo_b200_update_measurement_weights(h_), "updateMeasurementWeights");

@@ -51,7 +51,7 @@ typedef struct {
   int cost_type;                              /* 0 L2 ... 5 GNC_TLS (:178-188) */
   double gnc_barc, gnc_mu_step, gnc_init_mu;  /* :202-211 */
   int robust_opt_num_weight_updates, robust_opt_num_resets, robust_opt_inner_iters; /* :212-217 */
-  double robust_opt_min_convergence_ratio;    /* :214 */
+  double robust_opt_min_convergence_ratio;    /* :214 -- readyToTerminate needs this share of loop-closure weights settled at 0 or 1 */
   int max_num_iters;                          /* :226-231 */
   double rel_change_tol;                      /* :145 */
   double precond_lambda;                      /* Q + lambda I regularisation of the preconditioner */
@@ -252,6 +252,12 @@ size_t dpgo_b200_sync_driver_shm_bytes(int num_robots, int max_shared_poses);
 int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const int *robot_ids, int num_local, int num_robots,
                                   void *shm, int max_shared_poses, int steps, int accelerated, int start_iter,
                                   double *seconds, int *terminated_at);
+
+/* ---- diagnostics ---------------------------------------------------------------------
+ * Q as the DEVICE assembled it (per-edge accumulation kernel, dpgo_ros_b200/csrc/assemble.cu; the reference
+ * assembles it in PoseGraph::quadraticMatrix after addMeasurement :277 / clearDataMatrices :1351): dense 4n x 4n
+ * column-major, once from the block-CSR copy and once from the ELL + overflow copy.  Either pointer may be NULL. */
+int dpgo_b200_debug_dense_q(dpgo_b200_agent_t a, double *Q_from_csr, double *Q_from_ell);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,8 @@ def lib():
     L.orc_hess.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     L.orc_precond.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     L.orc_dense_q.argtypes = [C.c_void_p, C.c_int, dp, dp]
+    L.orc_set_measurement_weight.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.c_int]
+    L.orc_compute_measurement_residual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [dp]
     L.orc_manifold_project.argtypes = [C.c_int, C.c_int, dp, dp]
     L.orc_tangent_project.argtypes = [C.c_int, C.c_int, dp, dp, dp]
     L.orc_retract.argtypes = [C.c_int, C.c_int, dp, dp, dp]
@@ -281,6 +283,16 @@ class OracleTeam:
         out = np.zeros_like(X, order="F")
         _chk(self.L.orc_precond(self.h, rid, _dp(X), _dp(V), _dp(out)), "precond")
         return out
+
+    def set_measurement_weight(self, rid, r1, p1, r2, p2, w, fixed=False):
+        """setMeasurementWeight (src/PGOAgentROS.cpp:1341) followed by clearDataMatrices (:1351)."""
+        _chk(self.L.orc_set_measurement_weight(self.h, rid, r1, p1, r2, p2, float(w), int(fixed)), "set_measurement_weight")
+
+    def compute_measurement_residual(self, rid, r1, p1, r2, p2):
+        """computeMeasurementResidual (src/PGOAgentROS.cpp:1049); None when a pose is unavailable."""
+        res = C.c_double()
+        rc = self.L.orc_compute_measurement_residual(self.h, rid, r1, p1, r2, p2, C.byref(res))
+        return res.value if rc == 0 else None
 
     def dense_q(self, rid: int):
         n = self.n[rid]

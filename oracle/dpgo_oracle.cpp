@@ -1030,6 +1030,18 @@ bool Agent::iterate(bool doOptimization) {
       status_.relativeChange = std::sqrt(squaredNorm(D) / pg_->n());
       bool ready = success;
       if (status_.relativeChange > params_.relChangeTol) ready = false;
+      // robustOptMinConvergenceRatio (src/PGOAgentROSNode.cpp:214; launch default 0, launch/PGOAgent.launch:34): not
+      // ready while too few loop-closure weights have settled at 0 or 1 [UPSTREAM-RECALL; counted like the
+      // statistics the TERMINATE handler prints, src/PGOAgentROS.cpp:1058-1067]
+      if (params_.robustOptMinConvergenceRatio > 0.0) {
+        size_t total = 0, settled = 0;
+        for (auto *vec : {&pg_->privateLoopClosures(), &pg_->sharedLoopClosures()})
+          for (const auto &m : *vec) {
+            ++total;
+            if (m.weight == 1.0 || m.weight == 0.0) ++settled;
+          }
+        if (total > 0 && (double)settled < params_.robustOptMinConvergenceRatio * (double)total) ready = false;
+      }
       status_.readyToTerminate = ready;
     }
   }

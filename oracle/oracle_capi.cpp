@@ -326,6 +326,20 @@ int orc_dense_q(void *t, int agent, double *Q /* 4n x 4n col-major */, double *G
   ORC_CATCH
 }
 
+int orc_set_measurement_weight(void *t, int agent, int r1, int p1, int r2, int p2, double w, int fixed) {
+  ORC_TRY
+  Agent &a = ((Team *)t)->agent(agent);
+  if (!a.setMeasurementWeight(r1, p1, r2, p2, w, fixed != 0)) return -4;
+  a.poseGraph().clearDataMatrices();
+  ORC_CATCH
+}
+int orc_compute_measurement_residual(void *t, int agent, int r1, int p1, int r2, int p2, double *res) {
+  ORC_TRY Agent &a = ((Team *)t)->agent(agent);
+  Measurement *m = a.poseGraph().findMeasurement(r1, p1, r2, p2);
+  if (!m || !a.computeMeasurementResidual(*m, res)) return -4;
+  ORC_CATCH
+}
+
 // manifold ops on raw r x 4n arrays
 int orc_manifold_project(int r, int n, const double *M, double *out) {
   ORC_TRY Mat A(r, 4 * n), B;

@@ -67,7 +67,7 @@ ParamMap agentDefaults() {
                   {"update_rule", std::string("Uniform")}, {"multirobot_initialization", true}, {"acceleration", false},
                   {"restart_interval", 50}, {"robust_cost_type", std::string("L2")}, {"GNC_use_probability", true},
                   {"GNC_quantile", 0.9}, {"GNC_barc", 5.0}, {"GNC_mu_step", 2.0}, {"GNC_init_mu", 1e-5},
-                  {"robust_opt_num_weight_updates", 4}, {"robust_opt_num_resets", 0}, {"robust_opt_min_convergence_ratio", 0.8},
+                  {"robust_opt_num_weight_updates", 4}, {"robust_opt_num_resets", 0}, {"robust_opt_min_convergence_ratio", 0.0},
                   {"robust_opt_inner_iters_per_robot", 10}, {"robust_init_min_inliers", 2}, {"max_iteration_number", 1000},
                   {"relative_change_tolerance", 0.1}, {"publish_iterate", false}, {"visualize_loop_closures", false},
                   {"complete_reset", false}, {"enable_recovery", false}, {"synchronize_measurements", true},

@@ -152,3 +152,108 @@ def test_recover_rewinds_the_iteration_number():
     for a in agents:
         assert a.iteration_number() == 13
         assert rel(a.getX(), oteam.get_x(a.id)) < 1e-9, a.id
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# data matrices assembled on the device (dpgo_ros_b200/csrc/assemble.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,robots", [("tinyGrid3D", 1), ("smallGrid3D", 2), ("sphere2500", 8), ("tunnels", 8)])
+def test_device_assembled_q_matches_oracle(name, robots):
+    """Per-edge accumulation kernel (k_assemble_values) against PoseGraph::denseQ() of the oracle, both copies the
+    kernel writes (block-CSR for the dense inverse, ELL + overflow for the hot phases): <= 1e-13 relative."""
+    pb = datasets.load_tunnels_problem() if name == "tunnels" else datasets.load_g2o_problem(name, robots)
+    kw = dict(r=5, method=0)
+    oteam = orc.OracleTeam(pb, **kw)
+    _, agents = gpu.make_team(pb, colocate=False, **kw)
+    for a in agents:
+        Qo, _ = oteam.dense_q(a.id)
+        Qc, Qe = a.denseQ()
+        assert rel(Qc, Qo) < 1e-13 and rel(Qe, Qo) < 1e-13, (a.id, rel(Qc, Qo), rel(Qe, Qo))
+        assert np.array_equal(Qc, Qe)
+    for a in agents:
+        a.close()
+
+
+def test_weight_change_reassembles_on_the_device():
+    """setMeasurementWeight + clearDataMatrices (src/PGOAgentROS.cpp:1341-1351) and a plain setMeasurementWeight (C-ABI
+    user, no clearDataMatrices): Q, the gradient and the preconditioner follow the new weight."""
+    pb = datasets.load_g2o_problem("smallGrid3D", 2)
+    kw = dict(r=5, method=0)
+    oteam = orc.OracleTeam(pb, **kw)
+    _, agents = gpu.make_team(pb, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=False)
+    a = agents[0]
+    r1, p1, r2, p2, w, fx = a.sharedLoopClosures()
+    e = 3
+    key = (int(r1[e]), int(p1[e]), int(r2[e]), int(p2[e]))
+    assert a.setMeasurementWeight(*key, 0.25, False)          # no clearDataMatrices on purpose
+    oteam.set_measurement_weight(0, *key, 0.25, False)
+    X = a.getX()
+    f, eg, rg = a.eval(X)
+    fo, ego, rgo = oteam.eval(0, X)
+    assert abs(f - fo) <= 1e-12 * abs(fo) and rel(eg, ego) < 1e-12
+    Qo, _ = oteam.dense_q(0)
+    assert rel(a.denseQ()[0], Qo) < 1e-13
+    V = np.asfortranarray(np.random.default_rng(0).standard_normal(X.shape))
+    assert rel(a.precond(X, V), oteam.precond(0, X, V)) < 1e-8
+    for a in agents:
+        a.close()
+
+
+def test_residuals_are_batched_and_cached():
+    """computeMeasurementResidual for every loop closure (the TERMINATE handler, src/PGOAgentROS.cpp:1044-1057): ONE
+    kernel launch serves them all; values match the oracle; a pose update invalidates the cache."""
+    from dpgo_ros_b200 import capi
+    pb = datasets.load_tunnels_problem()
+    kw = dict(r=5, method=0, cost_type=5, gnc_barc=3.0)
+    oteam = orc.OracleTeam(pb, **kw)
+    _, agents = gpu.make_team(pb, colocate=False, **kw)
+    gpu.exchange_host(agents, accel=False)
+    oteam.exchange_all()
+    a = agents[7]
+    r1, p1, r2, p2, w, fx = a.sharedLoopClosures()
+    L = capi.lib()
+    a.computeMeasurementResidual(int(r1[0]), int(p1[0]), int(r2[0]), int(p2[0]))   # everything built, cache filled
+    before = L.dpgo_b200_kernel_launch_count()
+    for e in range(len(w)):
+        key = (int(r1[e]), int(p1[e]), int(r2[e]), int(p2[e]))
+        got, want = a.computeMeasurementResidual(*key), oteam.compute_measurement_residual(7, *key)
+        assert got is not None and abs(got - want) <= 1e-10 * max(1.0, abs(want)), (e, got, want)
+    assert L.dpgo_b200_kernel_launch_count() == before, "cached residuals must not launch"
+    a.iterate(True)
+    oteam.iterate(7, True)
+    key = (int(r1[5]), int(p1[5]), int(r2[5]), int(p2[5]))
+    got, want = a.computeMeasurementResidual(*key), oteam.compute_measurement_residual(7, *key)
+    assert abs(got - want) <= 1e-7 * max(1.0, abs(want))
+    for a in agents:
+        a.close()
+
+
+def test_neighbour_inactive_from_the_start():
+    """A robot that is inactive from INITIALIZE onwards (SET_ACTIVE_ROBOTS with a subset, src/PGOAgentROS.cpp:377-400)
+    never sends its poses: its inbox slots stay empty, and iterate(true) must still optimise -- against the oracle, which
+    skips inactive neighbours before the pose look-up."""
+    pb = datasets.load_g2o_problem("sphere2500", 4)
+    kw = dict(r=5, method=0, gradnorm_tol=0.5, rel_change_tol=0.2)
+    _, agents = gpu.make_team(pb, colocate=False, **kw)
+    oteam = orc.OracleTeam(pb, **kw)
+    live = [a for a in agents if a.id != 2]
+    for a in live:
+        a.setRobotActive(2, False)
+        oteam.set_robot_active(a.id, 2, False)
+    gpu.exchange_host(live, accel=False)          # robot 2 publishes nothing
+    oteam.exchange_all()
+    for it in range(6):
+        sel = live[it % 3]
+        assert sel.iterate(True) is True
+        oteam.iterate(sel.id, True)
+        gpu.exchange_host(live, accel=False, only=[sel.id])
+        oteam.exchange_all()
+    for a in live:
+        assert rel(a.getX(), oteam.get_x(a.id)) < 1e-7, a.id
+    # and without the deactivation the same call reports that the solve was skipped
+    _, fresh = gpu.make_team(pb, colocate=False, **kw)
+    gpu.exchange_host([b for b in fresh if b.id != 2], accel=False)
+    assert fresh[1].iterate(True) is False and fresh[1].iteration_number() == 1
+    for a in agents + fresh:
+        a.close()
