@@ -1,7 +1,10 @@
 // extern "C" surface declared in include/dpgo_b200.h.  Every entry point
 // converts exceptions into negative error codes; nothing here computes on the
 // CPU -- a missing / unusable CUDA device surfaces as DPGO_B200_ERR_CUDA.
+#include <chrono>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "host.hpp"
@@ -17,7 +20,35 @@ struct dpgo_b200_team_s {
 
 static thread_local std::string g_last_error;
 
-#define API_BEGIN try {
+// seconds spent inside each entry point (dpgo_b200_debug_api_profile): lets a caller split its wall clock into
+// "inside the library" and "its own host code" (the reference wrapper's message handling)
+namespace {
+struct ApiClock {
+  std::mutex mu;
+  std::map<std::string, std::pair<double, long long>> acc;
+};
+ApiClock &api_clock() {
+  static ApiClock c;
+  return c;
+}
+struct ApiTimer {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  explicit ApiTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~ApiTimer() {
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ApiClock &c = api_clock();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto &e = c.acc[name];
+    e.first += dt;
+    e.second += 1;
+  }
+};
+}  // namespace
+
+#define API_BEGIN   \
+  ApiTimer api_timer_(__func__); \
+  try {
 #define API_END                                    \
   }                                                \
   catch (const Error &e) {                         \
@@ -684,6 +715,25 @@ int dpgo_b200_debug_dense_q(dpgo_b200_agent_t h, double *Q_csr, double *Q_ell) {
     }
   }
   API_END
+}
+// "name seconds calls\n" per entry point that was called since load (or since the last reset); returns the number of
+// bytes the full report needs
+int dpgo_b200_debug_api_profile(char *buf, int cap, int reset) {
+  ApiClock &c = api_clock();
+  std::lock_guard<std::mutex> lock(c.mu);
+  std::string out;
+  for (const auto &kv : c.acc) {
+    char line[160];
+    snprintf(line, sizeof line, "%s %.9f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t k = std::min(out.size(), (size_t)cap - 1);
+    std::memcpy(buf, out.data(), k);
+    buf[k] = 0;
+  }
+  if (reset) c.acc.clear();
+  return (int)out.size() + 1;
 }
 int dpgo_b200_debug_host_profile(dpgo_b200_agent_t h, double *out3, int reset) {
   API_BEGIN

@@ -63,7 +63,7 @@ struct AgentDev {
   // dense preconditioner (Q + lambda I)^-1, 4n x 4n, symmetric
   const double *Pinv;
   // work vectors (r x 4n) and their row-major "T" copies ([r][4n]) for the dense phase
-  double *G, *Rg, *RgT, *Z, *eta, *dlt0, *dlt1, *Hd, *rv, *rvT, *X2, *X3, *Rg2, *Rg2T, *zeta;
+  double *G, *Rg, *RgT, *Z, *eta, *dlt0, *dlt1, *Hd, *HdT, *rv, *rvT, *rw, *rwT, *X2, *X3, *Rg2, *Rg2T, *zeta;
   double *S, *S2;  // per pose sym(Y^T egrad_Y): 6 doubles
   AgentStat *stat;
 };

@@ -536,7 +536,8 @@ void Agent::build_structure() {
   std::memset(h_inbox, 0, d_inbox.n * sizeof(double));
   inbox_dirty = false;
   outbox_mirror_valid = false;
-  for (auto *b : {&dG, &dRg, &dRgT, &dZ, &dEta, &dDlt0, &dDlt1, &dHd, &dRv, &dRvT, &dX2, &dX3, &dRg2, &dRg2T, &dZeta})
+  for (auto *b : {&dG, &dRg, &dRgT, &dZ, &dEta, &dDlt0, &dDlt1, &dHd, &dHdT, &dRv, &dRvT, &dRw, &dRwT, &dX2, &dX3, &dRg2, &dRg2T,
+                  &dZeta})
     b->alloc(vec);
   dS.alloc((size_t)6 * n);
   dS2.alloc((size_t)6 * n);
@@ -676,7 +677,7 @@ AgentDev Agent::dev_view() const {
   A.pub_rowptr = d_pub_rowptr.p; A.pub_dst_reg = d_pub_dst_reg.p; A.pub_dst_aux = d_pub_dst_aux.p;
   A.Pinv = dPinv.p;
   A.G = dG.p; A.Rg = dRg.p; A.RgT = dRgT.p; A.Z = dZ.p; A.eta = dEta.p; A.dlt0 = dDlt0.p; A.dlt1 = dDlt1.p;
-  A.Hd = dHd.p; A.rv = dRv.p; A.rvT = dRvT.p; A.X2 = dX2.p; A.X3 = dX3.p; A.Rg2 = dRg2.p; A.Rg2T = dRg2T.p;
+  A.Hd = dHd.p; A.HdT = dHdT.p; A.rv = dRv.p; A.rvT = dRvT.p; A.rw = dRw.p; A.rwT = dRwT.p; A.X2 = dX2.p; A.X3 = dX3.p; A.Rg2 = dRg2.p; A.Rg2T = dRg2T.p;
   A.zeta = dZeta.p; A.S = dS.p; A.S2 = dS2.p; A.stat = d_stat;
   return A;
 }

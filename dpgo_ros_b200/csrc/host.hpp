@@ -196,7 +196,7 @@ class Agent {
   void free_pinned();
   DevBuf<double *> d_pub_dst_reg, d_pub_dst_aux;
   DevBuf<double> dPinv;
-  DevBuf<double> dG, dRg, dRgT, dZ, dEta, dDlt0, dDlt1, dHd, dRv, dRvT, dX2, dX3, dRg2, dRg2T, dZeta, dS, dS2;
+  DevBuf<double> dG, dRg, dRgT, dZ, dEta, dDlt0, dDlt1, dHd, dHdT, dRv, dRvT, dRw, dRwT, dX2, dX3, dRg2, dRg2T, dZeta, dS, dS2;
   // the measurements on the device, [odom | plc | slc] (assemble.cu: MeasDev), and the slot lists of the
   // weight-dependent blocks (AssembleDev)
   DevBuf<double> d_m_R, d_m_t, d_m_kappa, d_m_tau, d_m_w, d_m_resid;

@@ -494,9 +494,12 @@ struct DensePassCols {
 // acc over one pass of <= DensePassCols/4 poses whose columns start at `cols`
 // (shared memory or global, column stride ld); result to zs[pose][c][8].
 // STREAM: `cols` is global memory read once (agents whose slab does not fit shared memory)
-template <int R, bool STREAM = false>
+// AXPY: the left operand is VT + alpha * HT, formed while it is loaded (tCG: r+ = r + alpha H[delta] without a pass
+// of its own and the grid barrier that would have to follow it)
+template <int R, bool STREAM = false, bool AXPY = false>
 __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const double *VT, int r, int n4, int npass,
-                                           double *zs, double *red /* [8 warps][16 cols][8] */) {
+                                           double *zs, double *red /* [8 warps][16 cols][8] */,
+                                           const double *HT = nullptr, double alpha = 0.0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncols = npass * 4;
   constexpr int NC = DensePassCols<R>::value;  // columns held per thread (register budget)
@@ -515,6 +518,13 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
       const int q = q0 + kThreads * i;
 #pragma unroll
       for (int a = 0; a < R; ++a) vr[i][a] = (a < r && q < n4) ? VT[(size_t)a * n4 + q] : 0.0;
+      if constexpr (AXPY) {
+        double hr[R];
+#pragma unroll
+        for (int a = 0; a < R; ++a) hr[a] = (a < r && q < n4) ? HT[(size_t)a * n4 + q] : 0.0;
+#pragma unroll
+        for (int a = 0; a < R; ++a) vr[i][a] = fma(alpha, hr[a], vr[i][a]);
+      }
     }
     if constexpr (STREAM) {
       // columns streamed from HBM: request the whole chunk (QC x NC independent loads per thread) before the first
@@ -620,10 +630,10 @@ __device__ __forceinline__ void dense_pass(const double *cols, size_t ld, const 
 // Z slab of this CTA's chunk [p0, p0+np) into zs[pose_local][c][8].
 // BIG: instantiated for teams with an agent whose slab does not fit shared memory; only those kernels carry the
 // register-hungry streaming pass (it costs the small-agent kernels 4 us per iteration in spills otherwise)
-template <int R, bool BIG = false>
+template <int R, bool BIG = false, bool AXPY = false>
 __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const double *VT, int p0, int np,
                                            SlabState &ss, uint64_t *mbar, double *slab, size_t slab_cap_bytes,
-                                           double *zs, double *red) {
+                                           double *zs, double *red, const double *HT = nullptr, double alpha = 0.0) {
   const int r = rdim<R>(A), n4 = 4 * A.n;
   const size_t ldp = agent_ldp(A);
   const int pps = slab_poses(A, np, slab_cap_bytes);
@@ -636,8 +646,8 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
     // and 2.3 TB/s: the ring's per-tile barriers cost more than the registers it frees.)
     constexpr int NPP = DensePassCols<R>::value / 4;
     for (int sub = 0; sub < np; sub += NPP)
-      dense_pass<R, BIG>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(NPP, np - sub), zs + sub * 32,
-                         red);
+      dense_pass<R, BIG, AXPY>(A.Pinv + (size_t)4 * (p0 + sub) * ldp, ldp, VT, r, n4, min(NPP, np - sub), zs + sub * 32,
+                               red, HT, alpha);
     __syncthreads();
     return;
   }
@@ -665,7 +675,8 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
     DBG(16);
     constexpr int NPP = DensePassCols<R>::value / 4;
     for (int sub = 0; sub < cnt; sub += NPP)
-      dense_pass<R>(slab + (size_t)4 * sub * ldp, ldp, VT, r, n4, min(NPP, cnt - sub), zs + (s0 + sub) * 32, red);
+      dense_pass<R, false, AXPY>(slab + (size_t)4 * sub * ldp, ldp, VT, r, n4, min(NPP, cnt - sub),
+                                 zs + (s0 + sub) * 32, red, HT, alpha);
   }
   if (np > pps) ss.agent = -1;  // the buffer no longer holds sub-chunk 0
   __syncthreads();
@@ -830,6 +841,177 @@ __device__ __forceinline__ void phase_precond(const AgentDev &A, int ai, const d
       if (neg_out) {
         double nz[4] = {-z[0], -z[1], -z[2], -z[3]};
         st4(neg_out + off, r, a, act, nz);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tCG with TWO grid-wide synchronisations per inner iteration (team_run.cuh, rtr_solve).
+//
+// The textbook loop needs four: <delta, H delta> after the Hessian-vector product, |r+|^2 after the residual update,
+// <z+, r+> after the preconditioner, and a barrier after the new direction.  Here
+//   * the Hessian-vector phase forms delta+ = -z + beta delta ON THE FLY for the pose it owns and for every pose it
+//     gathers (z and the previous delta are both complete by then), so the direction never needs a pass and a
+//     barrier of its own;
+//   * the preconditioner phase reads r+ = r + alpha H[delta] on the fly (dense_pass<.., AXPY>), and its epilogue
+//     -- chunk-owned poses -- stores r+, advances eta and accumulates |r+|^2 and <z+, r+> for ONE joint reduction.
+// The arithmetic of every vector is the one of the four-barrier loop, operation for operation (the preconditioner
+// application of the iteration that turns out to be the last is speculative and discarded).
+// ---------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void ell_gather_dir(const int *ell_col, const double *ell_val, const int *ovf_rowptr,
+                                               const int *ovf_col, const double *ovf_val, const double *Zsrc,
+                                               const double *Dprev, double beta, int j, bool valid, int r, int a,
+                                               bool act, double *stage, double (&acc)[4]) {
+  const int mycol = (valid && a < W) ? ell_col[(size_t)j * W + a] : -1;
+  int o0 = 0, o1 = 0;
+  if (valid) {
+    o0 = ovf_rowptr[j];
+    o1 = ovf_rowptr[j + 1];
+  }
+  double2 bq[W];
+  const double2 *bsrc = reinterpret_cast<const double2 *>(ell_val + (size_t)(valid ? j : 0) * W * 16);
+#pragma unroll
+  for (int k = 0; k < W; ++k) bq[k] = valid ? bsrc[k * 8 + a] : make_double2(0.0, 0.0);
+  double2 *st2 = reinterpret_cast<double2 *>(stage);
+#pragma unroll
+  for (int k = 0; k < W; ++k) st2[k * 8 + a] = bq[k];
+  int cols[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) cols[k] = gshfl(mycol, k);
+  __syncwarp();
+  // two half-width batches: 2 x 4 x 4 loads in flight per lane (z and the previous direction of four poses)
+#pragma unroll
+  for (int h = 0; h < W; h += 4) {
+    double zi[4][4], di[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool on = act && cols[h + k] >= 0;
+      const size_t off = (size_t)(cols[h + k] >= 0 ? cols[h + k] : 0) * 4 * r;
+      ld4(Zsrc + off, r, a, on, zi[k]);
+      ld4(Dprev + off, r, a, on, di[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (cols[h + k] >= 0) {
+        double xi[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xi[c] = -zi[k][c] + beta * di[k][c];
+        row_times_block(xi, stage + (h + k) * 16, acc);
+      }
+  }
+  __syncwarp();
+  for (int e = o0; e < o1; ++e) {
+    double zo[4], dp[4], xo[4];
+    const size_t off = (size_t)ovf_col[e] * 4 * r;
+    ld4(Zsrc + off, r, a, act, zo);
+    ld4(Dprev + off, r, a, act, dp);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xo[c] = -zo[c] + beta * dp[c];
+    row_times_block(xo, ovf_val + (size_t)e * 16, acc);
+  }
+}
+
+// H[delta] with delta given (first inner iteration: Dcur already holds -z0) or formed on the fly as
+// -Z + beta Dprev (and then stored to Dcur for the pose this group owns).  Writes Hd and its row-major copy HdT;
+// pvh accumulates <delta, H delta>.
+template <int RC>
+__device__ __forceinline__ void phase_hess_dir(const AgentDev &A, const double *Xbase, const double *S, bool first,
+                                               const double *Zsrc, const double *Dprev, double beta, double *Dcur,
+                                               double *Hout, double *HoutT, double *stage_all, double &pvh) {
+  PoseIter it;
+  const int n = A.n, r = rdim<RC>(A);
+  const size_t n4 = (size_t)4 * n;
+  double *stage = stage_all + (size_t)it.lg * kStageStride;
+  int j;
+  while (it.next(n, j)) {
+    const bool valid = j < n;
+    const bool act = valid && it.a < r;
+    const size_t off = (size_t)(valid ? j : 0) * 4 * r;
+    double x[4], v[4], h[4] = {0, 0, 0, 0};
+    ld4(Xbase + off, r, it.a, act, x);
+    Sym3 Sj = {0, 0, 0, 0, 0, 0};
+    if (valid) {
+      const double *s = S + (size_t)j * 6;
+      Sj.a00 = s[0]; Sj.a01 = s[1]; Sj.a02 = s[2]; Sj.a11 = s[3]; Sj.a12 = s[4]; Sj.a22 = s[5];
+    }
+    if (first) {
+      ld4(Dcur + off, r, it.a, act, v);
+      ell_gather<8>(A.qe_col, A.qe_val, A.qo_rowptr, A.qo_col, A.qo_val, Dcur, j, valid, r, it.a, act, stage, h);
+    } else {
+      double z[4], d[4];
+      ld4(Zsrc + off, r, it.a, act, z);
+      ld4(Dprev + off, r, it.a, act, d);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = -z[c] + beta * d[c];
+      if (valid) st4(Dcur + off, r, it.a, act, v);
+      ell_gather_dir<8>(A.qe_col, A.qe_val, A.qo_rowptr, A.qo_col, A.qo_val, Zsrc, Dprev, beta, j, valid, r, it.a,
+                        act, stage, h);
+    }
+    sub_y_sym(v, Sj, h);
+    tangent_project_row(x, h);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pvh += v[c] * h[c];
+    if (valid) {
+      st4(Hout + off, r, it.a, act, h);
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) HoutT[(size_t)it.a * n4 + 4 * j + c] = h[c];
+      }
+    }
+  }
+}
+
+// z+ = Proj_Xbase( (r + alpha Hd) Pinv ) for the whole agent, and for the poses of this CTA's chunk:
+//   r+ = r + alpha Hd  (stored column- and row-major),  eta (+)= alpha delta,
+//   prr += |r+|^2,  pzr += <z+, r+>.
+template <int R>
+__device__ __forceinline__ void phase_precond_cg(const AgentDev &A, int ai, const double *Xbase, const double *Rin,
+                                                 const double *RinT, const double *Hd, const double *HdT,
+                                                 double alpha, const double *Dcur, bool eta_zero, double *eta,
+                                                 double *Rout, double *RoutT, double *Zout, SlabState &ss,
+                                                 uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
+                                                 double *red, double &prr, double &pzr) {
+  const int n = A.n, r = rdim<R>(A);
+  const size_t n4 = (size_t)4 * n;
+  const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
+  int p0, np;
+  cta_pose_chunk(n, p0, np);
+  dense_slab<R, false, true>(A, ai, RinT, p0, np, ss, mbar, slab, slab_cap, zs, red, HdT, alpha);
+  for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
+    const int k = k0 + lg;
+    const bool valid = k < np;
+    const int j = p0 + (valid ? k : 0);
+    const bool act = valid && a < r;
+    const size_t off = (size_t)j * 4 * r;
+    double y[4], z[4], rr[4], hd[4], d[4], e[4];
+    ld4(Xbase + off, r, a, act, y);
+    ld4(Rin + off, r, a, act, rr);
+    ld4(Hd + off, r, a, act, hd);
+    ld4(Dcur + off, r, a, act, d);
+    if (eta_zero) {
+      e[0] = e[1] = e[2] = e[3] = 0.0;
+    } else {
+      ld4(eta + off, r, a, act, e);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) z[c] = act ? zs[((valid ? k : 0) * 4 + c) * 8 + a] : 0.0;
+    tangent_project_row(y, z);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      rr[c] = fma(alpha, hd[c], rr[c]);   // the same operation dense_pass<.., AXPY> applied to its operand
+      e[c] += alpha * d[c];
+      prr += rr[c] * rr[c];
+      pzr += z[c] * rr[c];
+    }
+    if (valid) {
+      st4(Zout + off, r, a, act, z);
+      st4(Rout + off, r, a, act, rr);
+      st4(eta + off, r, a, act, e);
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) RoutT[(size_t)a * n4 + 4 * j + c] = rr[c];
       }
     }
   }

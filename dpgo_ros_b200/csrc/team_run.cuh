@@ -23,41 +23,6 @@ struct SmemLayout {
 // ---------------------------------------------------------------------------
 // pose-local vector phases used by tCG
 // ---------------------------------------------------------------------------
-// eta (+)= alpha * dlt ;  r = rsrc + alpha * Hd (also row-major copy) ; partial |r|^2
-template <int RC>
-__device__ __forceinline__ void phase_tcg_update(const AgentDev &A, double alpha, bool eta_zero, const double *dlt,
-                                                 const double *Hd, const double *rsrc, double *eta, double *rv,
-                                                 double *rvT, double &prr) {
-  PoseIter it;
-  const int n = A.n, r = rdim<RC>(A);
-  const size_t n4 = (size_t)4 * n;
-  int j;
-  while (it.next(n, j)) {
-    const bool valid = j < n;
-    const bool act = valid && it.a < r;
-    if (!act) continue;
-    const size_t off = (size_t)j * 4 * r;
-    double d[4], h[4], rs[4], e[4];
-    ld4(dlt + off, r, it.a, act, d);
-    ld4(Hd + off, r, it.a, act, h);
-    ld4(rsrc + off, r, it.a, act, rs);
-    if (eta_zero) {
-      e[0] = e[1] = e[2] = e[3] = 0.0;
-    } else {
-      ld4(eta + off, r, it.a, act, e);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      e[c] += alpha * d[c];
-      rs[c] += alpha * h[c];
-      prr += rs[c] * rs[c];
-      rvT[(size_t)it.a * n4 + 4 * j + c] = rs[c];
-    }
-    st4(eta + off, r, it.a, act, e);
-    st4(rv + off, r, it.a, act, rs);
-  }
-}
-
 // eta (+)= tau * dlt  (trust-region boundary / negative curvature exit)
 template <int RC>
 __device__ __forceinline__ void phase_axpy_eta(const AgentDev &A, double tau, bool eta_zero, const double *dlt,
@@ -79,25 +44,6 @@ __device__ __forceinline__ void phase_axpy_eta(const AgentDev &A, double tau, bo
 #pragma unroll
     for (int c = 0; c < 4; ++c) e[c] += tau * d[c];
     st4(eta + off, r, it.a, act, e);
-  }
-}
-
-// dlt = -z + beta * dlt
-template <int RC>
-__device__ __forceinline__ void phase_direction(const AgentDev &A, double beta, const double *Z, double *dlt) {
-  PoseIter it;
-  const int n = A.n, r = rdim<RC>(A);
-  int j;
-  while (it.next(n, j)) {
-    const bool act = j < n && it.a < r;
-    if (!act) continue;
-    const size_t off = (size_t)j * 4 * r;
-    double z[4], d[4];
-    ld4(Z + off, r, it.a, act, z);
-    ld4(dlt + off, r, it.a, act, d);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) d[c] = -z[c] + beta * d[c];
-    st4(dlt + off, r, it.a, act, d);
   }
 }
 
@@ -208,41 +154,48 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
     bool eta_zero = true;
     int status = 4;  // 0 negcurv, 1 exceeded, 2 lcon, 3 scon, 4 maxiter
     int j = 0;
+    // two grid-wide synchronisations per inner iteration (phases.cuh: phase_hess_dir / phase_precond_cg)
+    double beta = 0.0;
+    double *dcur = A.dlt0, *dprev = A.dlt1;   // delta_j (materialised by the Hessian-vector phase) / delta_{j-1}
+    double *rnext = A.rv, *rnextT = A.rvT;    // ping-pong target of r+ (never the buffer other CTAs still read)
     for (j = 0; j < P.rtr_tcg_iterations; ++j) {
       v[0] = 0;
-      phase_hess<R>(A, x1, S1, A.dlt0, A.Hd, L.stage, v[0]);
+      phase_hess_dir<R>(A, x1, S1, j == 0, A.Z, dprev, beta, dcur, A.Hd, A.HdT, L.stage, v[0]);
       grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
       const double d_Hd = v[0];
       const double alpha = z_r / d_Hd;
       const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
       if (d_Hd <= 0 || e_Pe_new >= Delta * Delta) {
         const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
-        phase_axpy_eta<R>(A, tau, eta_zero, A.dlt0, A.eta);
+        phase_axpy_eta<R>(A, tau, eta_zero, dcur, A.eta);
         eta_zero = false;
         status = (d_Hd <= 0) ? 0 : 1;
         break;
       }
       e_Pe = e_Pe_new;
-      v[0] = 0;
-      phase_tcg_update<R>(A, alpha, eta_zero, A.dlt0, A.Hd, rsrc, A.eta, A.rv, A.rvT, v[0]);
+      v[0] = v[1] = 0;
+      phase_precond_cg<R>(A, ai, x1, rsrc, rsrcT, A.Hd, A.HdT, alpha, dcur, eta_zero, A.eta, rnext, rnextT, A.Z, ss,
+                          mbar, L.slab, L.slab_cap, L.zs, red, v[0], v[1]);
       eta_zero = false;
-      grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
-      rsrc = A.rv;
-      rsrcT = A.rvT;
+      grid_reduce<2>(gs, bs, reinterpret_cast<double(&)[2]>(v), sm);
+      rsrc = rnext;
+      rsrcT = rnextT;
+      rnext = (rnext == A.rv) ? A.rw : A.rv;
+      rnextT = (rnextT == A.rvT) ? A.rwT : A.rvT;
       const double norm_r = sqrt(v[0]);
       const double tempnum = pow(norm_r0, theta);
       if (norm_r <= norm_r0 * fmin(tempnum, kappa)) {
         status = (kappa < tempnum) ? 2 : 3;
         break;
       }
-      v[0] = 0;
-      phase_precond<R>(A, ai, x1, rsrc, rsrcT, A.Z, nullptr, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
-      grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
       const double zold_rold = z_r;
-      z_r = v[0];
-      const double beta = z_r / zold_rold;
-      phase_direction<R>(A, beta, A.Z, A.dlt0);
-      grid_barrier(gs, bs);
+      z_r = v[1];
+      beta = z_r / zold_rold;
+      {  // the next Hessian-vector phase forms delta_{j+1} = -z + beta delta_j while it gathers
+        double *t = dcur;
+        dcur = dprev;
+        dprev = t;
+      }
       e_Pd = beta * (e_Pd + alpha * d_Pd);
       d_Pd = z_r + beta * beta * d_Pd;
     }

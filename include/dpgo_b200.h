@@ -258,6 +258,10 @@ int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const int *robot_id
  * assembles it in PoseGraph::quadraticMatrix after addMeasurement :277 / clearDataMatrices :1351): dense 4n x 4n
  * column-major, once from the block-CSR copy and once from the ELL + overflow copy.  Either pointer may be NULL. */
 int dpgo_b200_debug_dense_q(dpgo_b200_agent_t a, double *Q_from_csr, double *Q_from_ell);
+/* wall-clock seconds spent inside each entry point of this library since load (or the last reset), one
+ * "name seconds calls" line per entry point; returns the bytes the full report needs.  Lets a caller (the
+ * reference's wrapper in oracle/_ref) split its run time into library time and its own host code. */
+int dpgo_b200_debug_api_profile(char *buf, int cap, int reset);
 
 #ifdef __cplusplus
 }

@@ -11,8 +11,13 @@
 // It is linked ONLY into oracle/_ref/dpgo_ros_inproc_oracle.  libdpgo_b200.so, the shim and the Python
 // package never see it; the product has no CPU path.
 // =============================================================================
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <exception>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -28,7 +33,52 @@ struct dpgo_b200_agent_s {
 
 static thread_local std::string g_err;
 
-#define TRY_ try {
+// same per-entry-point clock as the CUDA library's (dpgo_b200_debug_api_profile), so that the wrapper's run time
+// splits into "library" and "wrapper host code" the same way on both back ends
+namespace {
+struct ApiClock {
+  std::mutex mu;
+  std::map<std::string, std::pair<double, long long>> acc;
+};
+ApiClock &api_clock() {
+  static ApiClock c;
+  return c;
+}
+struct ApiTimer {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  explicit ApiTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~ApiTimer() {
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ApiClock &c = api_clock();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto &e = c.acc[name];
+    e.first += dt;
+    e.second += 1;
+  }
+};
+}  // namespace
+extern "C" int dpgo_b200_debug_api_profile(char *buf, int cap, int reset) {
+  ApiClock &c = api_clock();
+  std::lock_guard<std::mutex> lock(c.mu);
+  std::string out;
+  for (const auto &kv : c.acc) {
+    char line[160];
+    snprintf(line, sizeof line, "%s %.9f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t k = std::min(out.size(), (size_t)cap - 1);
+    std::memcpy(buf, out.data(), k);
+    buf[k] = 0;
+  }
+  if (reset) c.acc.clear();
+  return (int)out.size() + 1;
+}
+
+#define TRY_                     \
+  ApiTimer api_timer_(__func__); \
+  try {
 #define CATCH_                         \
   }                                    \
   catch (const std::exception &e) {    \

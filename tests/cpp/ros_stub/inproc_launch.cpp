@@ -37,6 +37,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -162,9 +163,16 @@ class Monitor {
       subs_.push_back(nh.subscribe<dpgo_ros::Command>(prefix + "command", 100, [this](const dpgo_ros::CommandConstPtr &m) {
         commands_[m->command]++;
         if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration > last_update_iteration_) last_update_iteration_ = m->executing_iteration;
-        if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration == 1) round_start_ = ros::sim::world().delivering_published_at;
-        if (m->command == dpgo_ros::Command::TERMINATE)
+        if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration == 1) {
+          round_start_ = ros::sim::world().delivering_published_at;
+          dpgo_b200_debug_api_profile(nullptr, 0, 1);   // library clock: this round only
+        }
+        if (m->command == dpgo_ros::Command::TERMINATE) {
           round_wall_seconds_.push_back(std::chrono::duration<double>(ros::sim::world().delivering_published_at - round_start_).count());
+          std::string prof((size_t)dpgo_b200_debug_api_profile(nullptr, 0, 0), '\0');
+          dpgo_b200_debug_api_profile(&prof[0], (int)prof.size(), 0);
+          round_library_profile_.push_back(prof.c_str());
+        }
         if (m->command == dpgo_ros::Command::TERMINATE) {
           terminate_time_ = ros::sim::world().now;
           round_iterations_.push_back(last_update_iteration_);
@@ -193,6 +201,32 @@ class Monitor {
     // costs nothing, so this is the compute + host protocol time of the optimisation itself
     f << "],\n  \"round_wall_seconds\": [";
     for (size_t k = 0; k < round_wall_seconds_.size(); ++k) f << (k ? ", " : "") << round_wall_seconds_[k];
+    // seconds inside the DPGO library (every dpgo_b200_* entry point) between the same two events, total and per entry
+    // point: round_wall_seconds minus this is the wrapper's own host code + the ROS stand-in
+    f << "],\n  \"round_library_seconds\": [";
+    for (size_t k = 0; k < round_library_profile_.size(); ++k) {
+      double total = 0;
+      std::istringstream is(round_library_profile_[k]);
+      std::string name;
+      double sec;
+      long long calls;
+      while (is >> name >> sec >> calls) total += sec;
+      f << (k ? ", " : "") << total;
+    }
+    f << "],\n  \"round_library_profile\": [";
+    for (size_t k = 0; k < round_library_profile_.size(); ++k) {
+      f << (k ? ", {" : "{");
+      std::istringstream is(round_library_profile_[k]);
+      std::string name;
+      double sec;
+      long long calls;
+      bool firstp = true;
+      while (is >> name >> sec >> calls) {
+        f << (firstp ? "" : ", ") << "\"" << name << "\": [" << sec << ", " << calls << "]";
+        firstp = false;
+      }
+      f << "}";
+    }
     f << "],\n  \"commands\": {";
     bool first = true;
     for (const auto &kv : commands_) {
@@ -227,6 +261,7 @@ class Monitor {
   std::vector<ros::Subscriber> subs_;
   std::vector<unsigned> round_iterations_;   // iteration number of the last UPDATE command of every finished round
   std::vector<double> round_wall_seconds_;
+  std::vector<std::string> round_library_profile_;
   std::chrono::steady_clock::time_point round_start_ = std::chrono::steady_clock::now();
   std::map<int, unsigned long> commands_;
   unsigned last_update_iteration_ = 0;

@@ -77,6 +77,8 @@ def ros_message_path_problem(name, robots):
 def trajectories(result):
     R, t = {}, {}
     for rb in result["robots"]:
+        if not rb["trajectory"]:      # a robot that dropped out never published its final trajectory
+            continue
         a = np.array(rb["trajectory"]).reshape(-1, 7)
         t[rb["id"]] = a[:, :3]
         R[rb["id"]] = np.stack([datasets.quat_to_rot(q) for q in a[:, 3:7]])
