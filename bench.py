@@ -63,7 +63,7 @@ def async_cpu_reference(ticks=300, threads=None):
     return res.iterations / res.wall_seconds
 
 
-def hbm_regime_single_rank(device, iters=6):
+def hbm_regime_single_rank(device, iters=6, cpu_beside=True):
     """Secondary figure: one rank of BASELINE config 5 at the named size (synthetic 100k poses / 1M edges / 8 agents,
     robot 0: 12 500 poses) -- one iterate(true) streams the 20 GB dense preconditioner once, the regime in which the
     HBM roofline is the physical bound.  Same measurement as tools/bench_config5.py."""
@@ -86,22 +86,66 @@ def hbm_regime_single_rank(device, iters=6):
     for o, frames in need.items():
         fr = np.array(sorted(frames), dtype=np.int32)
         ag.updateNeighborPoses(o, fr, np.ascontiguousarray(np.einsum("ak,nkc->nca", yl, pb.T_init[o][fr])), False)
+    t_build = _t.perf_counter()
     ag.iterate(True)   # builds Q and the 50 016^2 dense inverse
+    t_build = _t.perf_counter() - t_build
     ts = []
     for _ in range(iters):
         t0 = _t.perf_counter()
         ag.iterate(True)
         ts.append(_t.perf_counter() - t0)
-    ag.close()
     n = pb.n[0]
+    # the Riemannian-gradient kernel of this regime on its own (k_edge_grad), cold L2 like inside a step, device time
+    # between the first CTA's start and the last CTA's end: the "per-iteration Riemannian-gradient kernel" of the north star
+    shared = m.r1 != m.r2
+    nbr_pub = sum(len(v) for v in need.values())
+    b_grad = len(m) * 128 + 2 * n * P.r * 4 * 8 + nbr_pub * P.r * 4 * 8
+    grad = {}
+    try:
+        kns, ens = [], []
+        for _ in range(9):
+            _, _, k, e = ag.edgeGrad(None, flush_l2=True)
+            kns.append(k)
+            ens.append(e)
+        peak, _ = load_peaks()
+        us = float(np.median(kns)) * 1e-3
+        grad = {"kernel": "k_edge_grad<5> (dpgo_ros_b200/csrc/edge_grad.cu)", "us": us, "us_cuda_events": float(np.median(ens)) * 1e-3,
+                "b_grad_bytes": b_grad, "achieved_GBps": b_grad / (us * 1e-6) / 1e9, "peak_GBps": peak,
+                "frac": b_grad / (us * 1e-6) / 1e9 / peak,
+                "how": "median of 9 launches, each after rewriting 512 MB (cold L2, as inside a step where the 20 GB "
+                       "preconditioner has just streamed through); device time = last CTA end - first CTA start "
+                       "(globaltimer); bytes = SURVEY 8(d) B_grad of this agent"}
+    except Exception as e:  # noqa: BLE001
+        grad = {"error": str(e)[:200]}
+    ag.close()
     npad = (4 * n + 31) // 32 * 32
     nbytes = npad * npad * 8 + 2 * n * P.r * 4 * 8 + len(m) * 128 + 2 * n * P.r * 4 * 8
     ms = float(np.median(ts)) * 1e3
     peak, _ = load_peaks()
-    return {"workload": "config 5 at the named size, one of its 8 ranks: robot 0 of the synthetic 100k-pose / 1M-edge graph "
-                        f"(n={n}, {len(m)} edges), RGD 0.2 + dense preconditioner, per-robot C ABI iterate(true)",
-            "ms_per_iterate": ms, "algorithmic_bytes": nbytes, "achieved_GBps": nbytes / (ms * 1e-3) / 1e9,
-            "peak_GBps": peak, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+    out = {"workload": "config 5 at the named size, one of its 8 ranks: robot 0 of the synthetic 100k-pose / 1M-edge graph "
+                       f"(n={n}, {len(m)} edges; lattice generator datasets.make_synthetic_problem -- the SURVEY 8(d) random-walk "
+                       "generator is datasets.make_random_walk_problem), RGD 0.2 + dense preconditioner, per-robot C ABI iterate(true)",
+           "ms_per_iterate": ms, "preconditioner_build_s": t_build, "algorithmic_bytes": nbytes,
+           "achieved_GBps": nbytes / (ms * 1e-3) / 1e9, "peak_GBps": peak, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+           "frac_note": "implementation bytes (the 20 GB dense inverse streamed once per step), NOT SURVEY 8(d) bytes",
+           "riemannian_gradient_kernel": grad}
+    if cpu_beside:
+        try:   # the same robot's iterate(true) on the CPU oracle (sparse Cholesky preconditioner), one core
+            from oracle import binding as orc
+            oteam = orc.OracleTeam(pb, **ASYNC_CONFIG)
+            t0 = _t.perf_counter()
+            oteam.iterate(0, True)
+            t_fact = _t.perf_counter() - t0
+            cs = []
+            for _ in range(5):
+                t0 = _t.perf_counter()
+                oteam.iterate(0, True)
+                cs.append(_t.perf_counter() - t0)
+            out["cpu_beside"] = {"ms_per_iterate": float(np.median(cs)) * 1e3, "first_iterate_s": t_fact, "cores": 1,
+                                 "kind": "port", "speedup": float(np.median(cs)) * 1e3 / ms}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_beside"] = {"error": str(e)[:200]}
+    return out
 
 
 def async_mode_single_gpu(pb, device, ticks=2000):
@@ -122,37 +166,65 @@ def async_mode_single_gpu(pb, device, ticks=2000):
             "final_cost_2f": cost}
 
 
-def reference_wrapper_e2e(timeout_s=40, arms=("b200", "oracle")):
-    """Secondary figure: the reference's OWN wrapper (unmodified sources built by oracle/Makefile.ref into oracle/_ref,
-    DESIGN.md 5.1 / 6.1) running launch/dpgo_demo.launch on sphere2500 / 5 robots from the odometry guess in one process,
-    once on libdpgo_b200.so and once on the CPU oracle: wall-clock seconds between the first UPDATE command and TERMINATE.
-    RTR 3x50 (what the ROS node forces in synchronous mode), so this is NOT the headline workload; it is the only number
-    that runs the reference's real host code.  Never fails the bench line."""
+WRAPPER_RUNS = (
+    # (key, BASELINE config, command-line of oracle/_ref/dpgo_ros_inproc_*, what it is)
+    ("sphere2500_5_odometry", None,
+     ["--robots", "5", "--g2o", "data/sphere2500.g2o", "--preset", "dpgo_demo", "--param", "local_initialization_method=Odometry"],
+     "launch/dpgo_demo.launch, README.md:32 command: sphere2500.g2o / 5 robots / RTR 3x50 / Odometry guess"),
+    ("config3_torus3D_4_r6", 3,
+     ["--robots", "4", "--g2o", "data/torus3D.g2o", "--preset", "dpgo_demo", "--param", "relaxation_rank=6"],
+     "BASELINE config 3: launch/dpgo_demo.launch on torus3D.g2o / 4 robots / r = 6 / RTR 3x50 / Chordal guess"),
+    ("config4_tunnels_8_gnc", 4,
+     ["--robots", "8", "--measurements", "data/tunnels", "--preset", "gnc_demo"],
+     "BASELINE config 4: launch/dpgo_gnc_demo.launch on the tunnels dataset / 8 robots / GNC_TLS, 3 weight updates"),
+)
+
+
+def reference_wrapper_e2e(timeout_s=60, arms=("b200", "oracle"), repeats=2):
+    """Secondary figures: the reference's OWN wrapper (unmodified sources built by oracle/Makefile.ref into oracle/_ref,
+    DESIGN.md 5.1 / 6.1) running its demo launch files in one process, once on libdpgo_b200.so and once on the CPU
+    oracle -- the only numbers that run the reference's real host code, and the driver-run numbers of BASELINE configs 3
+    and 4 (RTR 3x50 is what the ROS node forces in synchronous mode, src/PGOAgentROSNode.cpp:82-87).  Per run:
+    wall-clock seconds between the first UPDATE command and TERMINATE (best of `repeats`), and the part of it spent
+    inside the library (every dpgo_b200_* entry point; the rest is the wrapper's message handling + the ROS stand-in,
+    identical on both arms).  Never fails the bench line."""
     import subprocess
     import tempfile
 
-    out = {"workload": "launch/dpgo_demo.launch through the unmodified PGOAgentROS: sphere2500.g2o / 5 robots / RTR 3x50 / "
-                       "Odometry guess / RoundRobin (kappa = 10000, tau = 100 on the message path)"}
-    for arm in arms:
-        exe = os.path.join(ROOT, "oracle", "_ref", "dpgo_ros_inproc_" + arm)
-        if not os.path.exists(exe):
-            out[arm] = {"unavailable": "oracle/_ref is not built (needs the reference sources at build time)"}
-            continue
-        try:
-            with tempfile.TemporaryDirectory() as tmp:
-                res = os.path.join(tmp, "r.json")
-                cmd = [exe, "--robots", "5", "--g2o", os.path.join(ROOT, "data", "sphere2500.g2o"), "--preset", "dpgo_demo",
-                       "--param", "local_initialization_method=Odometry", "--out", res, "--log", "0"]
-                p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=timeout_s)
-                if p.returncode != 0:
-                    out[arm] = {"error": (p.stderr or "")[-200:]}
-                    continue
-                d = json.load(open(res))
-            it, wall = d["round_iterations"][0], d["round_wall_seconds"][0]
-            out[arm] = {"backend": d["backend"], "iterations": it, "wall_seconds": wall, "iters_per_s": it / wall,
-                        "gpu_kernel_launches": d["kernel_launches"]}
-        except Exception as e:  # noqa: BLE001
-            out[arm] = {"error": str(e)[:200]}
+    out = {"what": "the unmodified PGOAgentROS on both back ends (kappa = 10000, tau = 100 on the message path); "
+                   "wall_seconds: first UPDATE -> TERMINATE; library_seconds: inside dpgo_b200_* calls during that window"}
+    for key, _cfg, argv, what in WRAPPER_RUNS:
+        entry = {"workload": what}
+        for arm in arms:
+            exe = os.path.join(ROOT, "oracle", "_ref", "dpgo_ros_inproc_" + arm)
+            if not os.path.exists(exe):
+                entry[arm] = {"unavailable": "oracle/_ref is not built (needs the reference sources at build time)"}
+                continue
+            best = None
+            try:
+                for _ in range(repeats):
+                    with tempfile.TemporaryDirectory() as tmp:
+                        res = os.path.join(tmp, "r.json")
+                        cmd = [exe] + [os.path.join(ROOT, a) if a.startswith("data/") else a for a in argv] + ["--out", res, "--log", "0"]
+                        p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=timeout_s)
+                        if p.returncode != 0:
+                            entry[arm] = {"error": (p.stderr or "")[-200:]}
+                            break
+                        d = json.load(open(res))
+                    it, wall = d["round_iterations"][0], d["round_wall_seconds"][0]
+                    lib = (d.get("round_library_seconds") or [None])[0]
+                    if best is None or wall < best["wall_seconds"]:
+                        best = {"backend": d["backend"], "iterations": it, "wall_seconds": wall, "library_seconds": lib,
+                                "iters_per_s": it / wall, "gpu_kernel_launches": d["kernel_launches"]}
+                if best is not None:
+                    entry[arm] = best
+            except Exception as e:  # noqa: BLE001
+                entry[arm] = {"error": str(e)[:200]}
+        if all(isinstance(entry.get(a), dict) and "wall_seconds" in entry[a] for a in ("b200", "oracle") if a in arms) and len(arms) == 2:
+            entry["speedup_wall"] = entry["oracle"]["wall_seconds"] / entry["b200"]["wall_seconds"]
+            if entry["b200"].get("library_seconds") and entry["oracle"].get("library_seconds"):
+                entry["speedup_library"] = entry["oracle"]["library_seconds"] / entry["b200"]["library_seconds"]
+        out[key] = entry
     return out
 
 
@@ -237,15 +309,19 @@ def cpu_reference(steps, warmup, threads=None, sample_note=True):
     """The CPU arm: oracle/ (a port -- the reference's own arithmetic is not vendored) on the host cores."""
     from dpgo_ros_b200 import datasets
     from oracle import binding as orc
+    native = orc.use_native()   # -O3 -march=native on this very machine, like the reference's CMakeLists.txt:9
     cores = os.cpu_count() or 1
     threads = threads or min(8, cores)
     pb = datasets.load_g2o_problem("sphere2500", 8)
     team = orc.OracleTeam(pb, **CONFIG2)
-    if warmup:
-        team.run(warmup, threads=threads, stop_on_terminate=False)
+    # the CPU arm is timed warm: thread pool up, factorisations done, caches hot (round 1's 20 cold steps read 730 it/s
+    # where the steady state is ~900)
+    warmup = max(warmup, 300)
+    team.run(warmup, threads=threads, stop_on_terminate=False)
     res = team.run(steps, threads=threads, stop_on_terminate=False)
     out = dict(value=res.iterations / res.wall_seconds, seconds=res.wall_seconds, steps=res.iterations,
-               threads=threads, cores=cores, cost=team.global_cost())
+               threads=threads, cores=cores, cost=team.global_cost(),
+               build="-O3 -march=native, built on this machine" if native else "-O3 -march=x86-64-v3 (prebuilt; native build unavailable)")
     # SURVEY 8d: "also report per-iterate(true) median us" -- one robot's local solve on one core, neighbours' poses fresh
     try:
         samples = []
@@ -274,8 +350,8 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "sphere2500.g2o",
         "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": r["value"], "unit": "iters/s", "cores": r["threads"], "kind": "port",
-                         "sample": f"{r['steps']} steps of the same workload, one OS thread per agent "
-                                   f"({r['threads']} threads on {r['cores']} host cores)",
+                         "sample": f"{r['steps']} steps of the same workload after 300 warm-up steps, one OS thread per "
+                                   f"agent ({r['threads']} threads on {r['cores']} host cores); {r['build']}",
                          "iterate_true_median_us": r.get("iterate_true_median_us")},
         "e2e": {"value": r["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_cost_2f": r["cost"], "wall_s": time.time() - t0,
@@ -301,6 +377,11 @@ def e2e_host_exchange(problem, steps, warmup, device):
     return steps / sec, float(payload), float(payload), X
 
 
+def e2e_step_count(args):
+    """Steps the e2e arm is timed over -- the same rule at every N (round 1 used 4000 at N = 1 and 20 at N > 1)."""
+    return max(args.steps, args.e2e_steps)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,7 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3000, help="bounded CPU-baseline sample (steps)")
-    ap.add_argument("--e2e-steps", type=int, default=4000)
+    ap.add_argument("--e2e-steps", type=int, default=2000, help="lower bound of the steps the e2e arm is timed over")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -365,15 +446,22 @@ def main():
     for a in agents:
         a.close()
 
-    e2e_val, h2d, d2h, _ = e2e_host_exchange(pb, args.e2e_steps, max(3, min(args.warmup, 20)), local_rank)
+    e2e_val, h2d, d2h, _ = e2e_host_exchange(pb, e2e_step_count(args), max(3, min(args.warmup, 20)), local_rank)
 
     peak, peak_src = load_peaks()
     step_bytes, grad_bytes = algorithmic_bytes(pb, CONFIG2["r"])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if os.path.exists(tpath):  # dram__bytes_read+write of one `ncu --set full` capture, per step
-        traffic = json.load(open(tpath))["traffic_bytes_per_step"] * args.steps
-    achieved = step_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
+    # achieved = B_grad x Riemannian-gradient evaluations / kernel time.  One step evaluates the gradient of
+    # the selected agent twice (the step's own gradient at Y, and f / |grad| at X+ for mLocalOptResult).
+    grad_evals_per_step = 2
+    achieved = grad_evals_per_step * grad_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    for tname in ("traffic_r2.json", "traffic_r1.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):  # dram__bytes_read+write of one `ncu --set full` capture of this kernel, per step
+            traffic = json.load(open(tpath))["traffic_bytes_per_step"] * args.steps
+            traffic_src = f"profiles/{tname} (ncu --set full capture of this kernel, bytes per step x steps; not measured in this run)"
+            break
+    model_achieved = step_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
     cpu = cpu_reference(args.cpu_steps, 50)
     async_mode = async_mode_single_gpu(pb, local_rank)
     async_mode["cpu_ticks_per_s"] = async_cpu_reference()
@@ -397,14 +485,26 @@ def main():
         "e2e": {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "per-robot C ABI (iterate / getSharedPoseDict / updateNeighborPoses), host buffers, 8 agents"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_team_run<5> (persistent: all phases of all K steps)",
-                     "algorithmic_bytes_per_step": step_bytes, "b_grad_per_agent": grad_bytes,
-                     "note": "latency-bound by construction: the working set of a step is ~13 MB and L2-resident "
-                             "(SURVEY §8d caveat); frac is the effective algorithmic bandwidth"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "k_team_run<5,1> (persistent: all phases of all K steps in one launch)",
+                     "accounting": "SURVEY 8(d): B_grad = edges*128 + 2*n*r*4*8 + n_nbr_pub*r*4*8 per Riemannian-gradient "
+                                   "evaluation, 2 evaluations per step, / CUDA-event time of the launch",
+                     "b_grad_per_agent": grad_bytes, "grad_evals_per_step": grad_evals_per_step,
+                     "note": "config 2 is latency-bound, not bandwidth-bound: one agent's gradient is ~200 KB and the "
+                             "whole step is L2-resident, so the HBM fraction of the 8(d) bytes is ~0.003-0.005 by "
+                             "construction (a step is a chain of ~10 dependent L2 round trips and 2 grid barriers). "
+                             "FP64 throughout: tcgen05 has no FP64 path and DMMA m8n8k4 measures the DFMA rate on "
+                             "B200 (profiles/microbench_r1.txt), so the dense (r x 4n)(4n x 4n) product stays on the "
+                             "FP64 pipe -- tensor cores declined with evidence. The HBM-bound regime of this path is "
+                             "config 5: see hbm_bound_regime.",
+                     "effective_step_model": {
+                         "what": "NOT the 8(d) figure: bytes the implementation's own step touches (2 B_grad + the "
+                                 "12.5 MB dense preconditioner of the selected agent + Nesterov bookkeeping of all "
+                                 "agents), kept for continuity with round 1",
+                         "bytes_per_step": step_bytes, "achieved": model_achieved, "frac": model_achieved / peak}},
         "cpu_baseline": {"value": cpu["value"], "unit": "iters/s", "cores": cpu["threads"], "kind": "port",
                          "sample": f"{cpu['steps']} steps of the same workload on the oracle, one OS thread per "
-                                   f"agent ({cpu['threads']} threads, {cpu['cores']} host cores)",
+                                   f"agent ({cpu['threads']} threads, {cpu['cores']} host cores); {cpu['build']}",
                          "iterate_true_median_us": cpu.get("iterate_true_median_us")},
         "async_mode": async_mode,
         "hbm_bound_regime": hbm_regime,

@@ -253,6 +253,19 @@ class PGOAgent:
         check(self.L.dpgo_b200_debug_dense_q(self.h, _dp(a), _dp(b)), "denseQ")
         return a, b
 
+    def edgeGrad(self, X: Optional[np.ndarray] = None, flush_l2: bool = False):
+        """k_edge_grad on its own (LARGE agents): (f, rgrad, kernel ns by globaltimer, ns by CUDA events)."""
+        n4 = 4 * self.num_poses()
+        rg = np.zeros((self.r, n4), order="F")
+        f, kns, ens = C.c_double(), C.c_double(), C.c_double()
+        Xp = None
+        if X is not None:
+            X = np.asfortranarray(X, dtype=np.float64)
+            Xp = _dp(X)
+        check(self.L.dpgo_b200_debug_edge_grad(self.h, Xp, int(flush_l2), C.byref(f), _dp(rg), C.byref(kns), C.byref(ens)),
+              "edgeGrad")
+        return f.value, rg, kns.value, ens.value
+
     def eval(self, X: np.ndarray):
         X = np.asfortranarray(X, dtype=np.float64)
         f = C.c_double()

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "host.hpp"
 
@@ -25,23 +26,28 @@ static thread_local std::string g_last_error;
 namespace {
 struct ApiClock {
   std::mutex mu;
-  std::map<std::string, std::pair<double, long long>> acc;
+  struct Ev {
+    const char *name;
+    double t0, t1;   // steady_clock seconds
+  };
+  std::vector<Ev> ev;
 };
 ApiClock &api_clock() {
   static ApiClock c;
   return c;
 }
+inline double api_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 struct ApiTimer {
   const char *name;
-  std::chrono::steady_clock::time_point t0;
-  explicit ApiTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  double t0;
+  explicit ApiTimer(const char *n) : name(n), t0(api_now()) {}
   ~ApiTimer() {
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double t1 = api_now();
     ApiClock &c = api_clock();
     std::lock_guard<std::mutex> lock(c.mu);
-    auto &e = c.acc[name];
-    e.first += dt;
-    e.second += 1;
+    if (c.ev.size() < (size_t)4 << 20) c.ev.push_back({name, t0, t1});
   }
 };
 }  // namespace
@@ -716,13 +722,21 @@ int dpgo_b200_debug_dense_q(dpgo_b200_agent_t h, double *Q_csr, double *Q_ell) {
   }
   API_END
 }
-// "name seconds calls\n" per entry point that was called since load (or since the last reset); returns the number of
-// bytes the full report needs
-int dpgo_b200_debug_api_profile(char *buf, int cap, int reset) {
+// "name seconds calls\n" per entry point, restricted to the part of every call that fell inside [t_begin, t_end]
+// (std::chrono::steady_clock seconds); returns the number of bytes the full report needs
+int dpgo_b200_debug_api_profile(double t_begin, double t_end, char *buf, int cap, int reset) {
   ApiClock &c = api_clock();
   std::lock_guard<std::mutex> lock(c.mu);
+  std::map<std::string, std::pair<double, long long>> acc;
+  for (const auto &e : c.ev) {
+    const double a = std::max(e.t0, t_begin), b = std::min(e.t1, t_end);
+    if (b <= a) continue;
+    auto &x = acc[e.name];
+    x.first += b - a;
+    x.second += 1;
+  }
   std::string out;
-  for (const auto &kv : c.acc) {
+  for (const auto &kv : acc) {
     char line[160];
     snprintf(line, sizeof line, "%s %.9f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
     out += line;
@@ -732,8 +746,74 @@ int dpgo_b200_debug_api_profile(char *buf, int cap, int reset) {
     std::memcpy(buf, out.data(), k);
     buf[k] = 0;
   }
-  if (reset) c.acc.clear();
+  if (reset) c.ev.clear();
   return (int)out.size() + 1;
+}
+// The LARGE-agent gradient kernel (k_edge_grad, edge_grad.cu) on its own: f, rgrad at X against the current inbox, and
+// the kernel's device time between the first CTA's start and the last CTA's end (globaltimer) -- the in-situ figure
+// the roofline of the HBM-bound regime is quoted on.  flush_l2 != 0 rewrites a 512 MB scratch buffer first, so the
+// records come from HBM as they do inside a step (where 10-20 GB of preconditioner have just streamed through L2).
+int dpgo_b200_debug_edge_grad(dpgo_b200_agent_t h, const double *X, int flush_l2, double *f, double *rgrad,
+                              double *kernel_ns, double *event_ns) {
+  API_BEGIN
+  Agent *a = A(h);
+  if (a->state != 2) fail(DPGO_B200_ERR_STATE, "edge_grad: agent not initialized");
+  a->team->prepare();
+  if (!a->has_edge_arrays()) fail(DPGO_B200_ERR_STATE, "edge_grad: the agent is below the edge-record threshold");
+  if (!a->all_inbox_valid(false)) fail(DPGO_B200_ERR_MISSING, "edge_grad: neighbour poses missing");
+  const size_t cnt = (size_t)a->r * 4 * a->n;
+  DevBuf<double> dX, dG, dR, dRT;
+  DevBuf<unsigned char> scratch;
+  if (X)
+    dX.upload(std::vector<double>(X, X + cnt));
+  dG.alloc(cnt);
+  dR.alloc(cnt);
+  dRT.alloc(cnt);
+  cudaStream_t st = a->team->stream;
+  if (flush_l2) {
+    scratch.alloc((size_t)512 << 20, false);
+    cuda_check(cudaMemsetAsync(scratch.p, 1, scratch.n, st), "flush L2");
+  }
+  EdgeGradArgs eg{};
+  eg.n = a->n;
+  eg.build_g = 1;
+  eg.rec = a->d_er_rec.p;
+  eg.inc_ptr = a->d_inc_ptr.p;
+  eg.inc_item = a->d_inc_item.p;
+  eg.Xin = X ? dX.p : a->dX.p;
+  eg.inbox = a->d_inbox_reg();
+  eg.G = dG.p;
+  eg.Rg = dR.p;
+  eg.RgT = dRT.p;
+  eg.partials = a->d_eg_partials.p;
+  eg.tmarks = a->d_eg_marks.p;
+  cuda_check(cudaMemsetAsync(a->d_eg_marks.p, 0xff, sizeof(unsigned long long), st), "marks");
+  cuda_check(cudaMemsetAsync(a->d_eg_marks.p + 1, 0, sizeof(unsigned long long), st), "marks");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  cuda_check(launch_edge_grad(eg, a->r, st), "k_edge_grad");
+  cudaEventRecord(e1, st);
+  cuda_check(cudaStreamSynchronize(st), "k_edge_grad");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  unsigned long long marks[2];
+  cuda_check(cudaMemcpy(marks, a->d_eg_marks.p, sizeof marks, cudaMemcpyDeviceToHost), "D2H marks");
+  if (kernel_ns) *kernel_ns = (double)(marks[1] - marks[0]);
+  if (event_ns) *event_ns = ms * 1e6;
+  const int grid = edge_grad_grid(a->n);
+  std::vector<double> part((size_t)grid * 2);
+  cuda_check(cudaMemcpy(part.data(), a->d_eg_partials.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H partials");
+  if (f) {
+    double s0 = 0;
+    for (int b = 0; b < grid; ++b) s0 += part[(size_t)b * 2];
+    *f = s0;
+  }
+  if (rgrad) cuda_check(cudaMemcpy(rgrad, dR.p, cnt * sizeof(double), cudaMemcpyDeviceToHost), "D2H rgrad");
+  API_END
 }
 int dpgo_b200_debug_host_profile(dpgo_b200_agent_t h, double *out3, int reset) {
   API_BEGIN

@@ -95,10 +95,14 @@ struct TeamCtl {
   unsigned pad;
   unsigned long long fab_seq;  // multi-GPU: sequence number of the last fabric barrier this rank arrived at
   unsigned long long la_seq;   // stand-alone path: the lookahead written by launch `la_seq` is complete
+  unsigned long long fab_step; // multi-GPU: global steps this rank has run over the fabric (base of the progress words)
 };
 constexpr size_t kCtlBytes = 128;   // result block: [TeamCtl (padded) | AgentStat x agents (128 B each) | outboxes]
 constexpr size_t kStatBytes = 128;
-static_assert(sizeof(TeamCtl) <= kCtlBytes, "TeamCtl must fit its slot of the result block");
+// two words behind TeamCtl in its slot of the (host-mapped) result block, for ARMED launches of the stand-alone path:
+// the host's doorbell (go = 2 seq + 1, abort = 2 seq) and the kernel's answer when it left without solving (2 seq)
+constexpr size_t kCtlDoorbellOff = 96, kCtlArmStateOff = 104;
+static_assert(sizeof(TeamCtl) <= kCtlDoorbellOff, "TeamCtl must leave room for the doorbell words in its slot");
 
 struct GridSync {
   unsigned long long *counter;  // monotonically increasing arrival counter
@@ -111,9 +115,19 @@ struct GridSync {
 // which for a remote neighbour is peer memory of another GPU (CUDA IPC mapping, NVLink), and
 // the ranks keep in step with flag words in each other's window -- the device-side replacement
 // of the PublicPoses topic and of the iteration gate (src/PGOAgentROS.cpp:662-690, 136-149).
-// Every rank's window starts with   flags[kMaxRanks] | payload[2][kMaxRanks]   (u64 each):
-// flags[s] = number of the last fabric barrier rank s arrived at (monotone), payload[q][s] =
-// the word rank s attached to its arrival at a barrier of parity q.
+// Every rank's window starts with   flags[kMaxRanks] | payload[2][kMaxRanks] | prog[kMaxRanks]   (u64 each):
+// flags[s] = number of the last ALL-RANK barrier rank s arrived at (monotone), payload[q][s] = the word rank s
+// attached to its arrival at a barrier of parity q -- used where every rank needs every rank (the leader's
+// termination test, entering / leaving a launch, the parallel schedule);
+// prog[s] = POINT-TO-POINT progress word of rank s, written only into the windows of the ranks that host a
+// neighbour of one of s's robots.  The synchronous schedules run on these alone (the wrapper's gate waits for
+// activeNeighborIDs() only, src/PGOAgentROS.cpp:136-149).  In global step k (1-based, monotone across launches):
+//     2k      "my Nesterov-phase publications of step k have landed in your inboxes"
+//     2k + 1  "my inbox of step k is consumed" -- posted at once by a rank that does not hold the selected robot;
+//             plain RBCD: "my step k, X+ publication included, is over"
+//   a rank waits for 2(k-1)+1 from its neighbour ranks before its first store of step k into their inboxes, and the
+//   selected robot's rank for 2k (plain RBCD: 2(k-1)+1) from that robot's neighbour ranks before it assembles G.
+//   Model-checked in tests/test_fabric_protocol_model.py (freshness, no write-after-read, no deadlock).
 // ---------------------------------------------------------------------------
 struct Fabric {
   int world, rank;  // world <= 1: single-GPU team, no fabric
@@ -121,11 +135,17 @@ struct Fabric {
   unsigned long long *payload;                   // my window, [2][kMaxRanks]
   unsigned long long *peer_flags[kMaxRanks];     // peers' windows (peer-mapped); [rank] unused
   unsigned long long *peer_payload[kMaxRanks];
+  unsigned long long *prog;                      // my window: progress words of the other ranks
+  unsigned long long *peer_prog[kMaxRanks];
+  unsigned nbr_ranks;                            // ranks (bit s) that host a neighbour of any local robot
+  unsigned agent_nbr_ranks[kMaxLocal];           // same, per local agent
+  unsigned long long step0;       // global steps completed before this launch
   unsigned long long seq0;        // barriers completed before this launch
   unsigned long long local_mask;  // robots that live on this rank
   unsigned long long timeout_ns;  // a peer that does not show up for this long aborts the launch
 };
-constexpr size_t kFabricHeaderBytes = 3 * kMaxRanks * sizeof(unsigned long long) + 64;  // 256
+constexpr size_t kFabricHeaderBytes = 512;  // 4 * kMaxRanks words + padding (the inboxes stay 256-byte aligned)
+static_assert(4 * kMaxRanks * sizeof(unsigned long long) <= kFabricHeaderBytes, "fabric header too small");
 
 struct TeamDev {
   int num_local, num_robots;
@@ -497,6 +517,49 @@ __device__ __forceinline__ bool fabric_wait(const Fabric &F, const GridSync &gs,
   bad = __syncthreads_or(bad);
   if (bad && threadIdx.x == 0 && !bs.dead) {
     red_release_add_u64(gs.counter, kBarPoison);  // release every local CTA that is (or will be) in a grid barrier
+    bs.dead = 1;
+  }
+  return !bad;
+}
+// point-to-point progress words.  post: right after a grid barrier that follows this rank's stores into peer memory
+// (same release chain as fabric_arrive); wait: lanes of every CTA poll the words of the ranks in `mask`.
+__device__ __forceinline__ void fabric_post(const Fabric &F, unsigned mask, unsigned long long value) {
+  if (blockIdx.x == 0 && (int)threadIdx.x < F.world && ((mask >> threadIdx.x) & 1u)) {
+    __threadfence_system();
+    st_release_sys_u64(F.peer_prog[threadIdx.x] + F.rank, value);
+  }
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// acquire = false: the wait only guards this rank's later STORES (write-after-read on a neighbour's inbox); the
+// branch on the polled value orders them, and skipping the system-scope acquire saves the ~3.5 us it takes to drain
+// this SM's outstanding peer stores first (2-GPU profile)
+__device__ __forceinline__ bool fabric_wait_prog(const Fabric &F, const GridSync &gs, BarState &bs, unsigned mask,
+                                                 unsigned long long value, bool acquire = true) {
+  int bad = (threadIdx.x == 0) ? bs.dead : 0;
+  if (!bad && (int)threadIdx.x < F.world && ((mask >> threadIdx.x) & 1u)) {
+    const unsigned long long *f = F.prog + threadIdx.x;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    // spin on relaxed loads (no ordering work per probe), acquire once the word is there
+    while (ld_relaxed_sys_u64(f) < value) {
+      if ((++spins & 0x3ff) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > F.timeout_ns || ld_acquire_u64(gs.counter) >= kBarPoison) {
+          bad = 1;
+          break;
+        }
+      }
+    }
+    if (acquire) (void)ld_acquire_sys_u64(f);
+  }
+  bad = __syncthreads_or(bad);
+  if (bad && threadIdx.x == 0 && !bs.dead) {
+    red_release_add_u64(gs.counter, kBarPoison);
     bs.dead = 1;
   }
   return !bad;

@@ -50,6 +50,12 @@ Agent::Agent(int id_, const dpgo_b200_params &p, int device_) : id(id_), P(p), d
 }
 
 Agent::~Agent() {
+  if (armed) {
+    try {
+      disarm();
+    } catch (...) {
+    }
+  }
   if (team && team != own.get()) team->remove(this);
   if (own) own->agents.clear();
   team = nullptr;
@@ -87,6 +93,7 @@ void Agent::add_measurement(const Meas &m) {
       nbrs.insert(m.r1);
     }
   }
+  if (armed) disarm();
   if (la_used > 0 && !structure_dirty) materialize_lookahead();
   drop_lookahead();
   structure_dirty = values_dirty = precon_dirty = wiring_dirty = lc_dirty = weights_host_dirty = true;
@@ -291,6 +298,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
         X[((size_t)i * 4 + c) * r + a] = s;
       }
   }
+  if (armed) disarm();
   drop_lookahead();
   resid_valid = false;
   dX.upload(X);
@@ -306,6 +314,7 @@ void Agent::initialize_in_global_frame(const double *Tw_rm) {
 }
 
 void Agent::reset() {
+  if (armed) disarm();
   drop_lookahead();
   resid_valid = false;
   instance++;
@@ -521,6 +530,36 @@ void Agent::build_structure() {
     d_so_slot.upload(oc);
     d_s_val.alloc(std::max<size_t>(ns, 1) * 16);
   }
+  // ---- LARGE agents: per-pose incidence lists of the edge-record gradient (edge_grad.cu)
+  if (n >= kEdgeGradMinPoses) {
+    const int M = num_meas();
+    std::vector<int> ptr(n + 1, 0);
+    auto mine = [&](const Meas &m, bool dst_end) { return dst_end ? (m.r2 == id) : (m.r1 == id); };
+    for (int e = 0; e < M; ++e) {
+      const Meas &m = meas_at(e);
+      if (mine(m, false)) ptr[m.p1 + 1]++;
+      if (mine(m, true)) ptr[m.p2 + 1]++;
+    }
+    for (int j = 0; j < n; ++j) ptr[j + 1] += ptr[j];
+    std::vector<int2> items(std::max(1, ptr[n]));
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int e = 0; e < M; ++e) {
+      const Meas &m = meas_at(e);
+      const int src = m.r1 == id ? m.p1 : -(slot_of[{m.r1, m.p1}] + 1);
+      const int dst = m.r2 == id ? m.p2 : -(slot_of[{m.r2, m.p2}] + 1);
+      if (m.r1 == id) items[fill[m.p1]++] = make_int2(e * 2 + 0, dst);   // this pose is the source: other end = dst
+      if (m.r2 == id) items[fill[m.p2]++] = make_int2(e * 2 + 1, src);
+    }
+    d_inc_ptr.upload(ptr);
+    d_inc_item.upload(items);
+    d_er_rec.alloc((size_t)std::max(1, M) * 16, false);
+    d_eg_partials.alloc((size_t)edge_grad_grid(n) * 2);
+    d_eg_marks.alloc(2);
+  } else {
+    d_inc_ptr.release();
+    d_inc_item.release();
+    d_er_rec.release();
+  }
   lc_dirty = true;
 
   d_q_rowptr.upload(h_q_rowptr);
@@ -623,6 +662,7 @@ void Agent::build_values() {
     d_m_skip.upload(skip);
   }
   cuda_check(launch_assemble_values(meas_view(), assemble_view(), 0), "k_assemble_values");
+  if (has_edge_arrays()) cuda_check(launch_pack_edge_records(meas_view(), d_er_rec.p, 0), "k_pack_edge_records");
   values_dirty = false;
   precon_dirty = true;
   resid_valid = false;
@@ -635,17 +675,19 @@ void Agent::build_preconditioner() {
   }
   const size_t npad = roundup32((size_t)4 * n);
   dPinv.alloc(npad * npad, false);
-  DevBuf<double> work, dinv;
-  DevBuf<int> info;
-  work.alloc(npad * npad, false);
-  dinv.alloc((npad / 32) * 1024, false);
-  info.alloc(1);
+  // the factorisation workspace stays allocated between rebuilds (a GNC weight update rebuilds the inverse of every
+  // robot: cudaMalloc / cudaFree of a few MB each time cost more than the kernels on the tunnels robots, and
+  // cudaFree synchronises the device) -- except for agents whose workspace is measured in GB
+  dPwork.alloc(npad * npad, false);
+  dPdinv.alloc((npad / 32) * 1024, false);
+  dPinfo.alloc(1);
   cuda_check(launch_scatter_blocks(dPinv.p, npad, d_q_rowptr.p, d_q_col.p, d_q_val.p, n, P.precond_lambda,
                                    (int)npad, 0),
              "scatter_blocks");
-  cuda_check(spd_inverse(dPinv.p, work.p, dinv.p, (int)npad, info.p, 0), "spd_inverse");
+  cuda_check(spd_inverse(dPinv.p, dPwork.p, dPdinv.p, (int)npad, dPinfo.p, 0), "spd_inverse");
   int h_info = 0;
-  cuda_check(cudaMemcpy(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
+  cuda_check(cudaMemcpy(&h_info, dPinfo.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
+  if (npad * npad * sizeof(double) > ((size_t)1 << 30)) dPwork.release();
   if (h_info != 0) fail(DPGO_B200_ERR_NUMERIC, "preconditioner: Q + lambda I is not positive definite");
   precon_dirty = false;
 }
@@ -741,12 +783,51 @@ bool Agent::iterate(bool do_opt) {
   const bool restart = accel && ((iter + 2) % P.restart_interval == 0);
   bool can_opt = do_opt;
   if (do_opt && !all_inbox_valid(accel && !restart)) can_opt = false;  // data matrices cannot be built
+  if (armed) {
+    if (can_opt) {
+      // the solve kernel of this very call has been on the GPU since the last neighbour poses arrived (Agent::arm):
+      // ring the doorbell -- the kernel pulls the staged inbox itself -- and wait for its result
+      inbox_dirty = false;
+      std::atomic_thread_fence(std::memory_order_release);
+      *tm->doorbell() = tm->pending.args.seq * 2ull + 1ull;
+      const unsigned long long seq = tm->pending.args.seq;
+      volatile TeamCtl *c = reinterpret_cast<volatile TeamCtl *>(tm->h_result);
+      bool expired = false;
+      for (unsigned spins = 0; c->seq != seq; ++spins) {
+        if (*tm->arm_state() == seq * 2ull) {
+          expired = true;
+          break;
+        }
+        if ((spins & 0xffff) == 0xffff) {
+          const cudaError_t q = cudaStreamQuery(tm->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) cuda_check(q, "armed k_team_run");
+        }
+      }
+      armed = false;
+      if (!expired) {
+        float ms = 0;
+        tm->launch_finish(tm->pending, &ms);
+        stats_pending = true;
+        opt.f_opt = opt.gradnorm_opt = std::nan("");
+        publish_requested = true;
+        return true;
+      }
+      // the kernel gave up before it saw the doorbell: it has committed the consumed lookahead and left
+      std::atomic_thread_fence(std::memory_order_acquire);
+      drop_lookahead();
+      outbox_stale = true;
+      arm_backoff = 64;
+    } else {
+      disarm();
+    }
+  }
   if (!accel && !can_opt) {
     iter++;
     tm->ctl.iter = iter;
     if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
     return false;
   }
+  if (do_opt && arm_backoff > 0) --arm_backoff;
   tm->run_forced(can_opt ? local_index : -1);
   publish_requested = accel || can_opt;  // mPublishPublicPosesRequested, src/PGOAgentROS.cpp:109
   return can_opt;
@@ -802,6 +883,7 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
     std::memcpy(inbox + (size_t)ns->second.first * 4 * r, poses, pb * count);
     std::memset(valid.data() + ns->second.first, 1, count);
     inbox_dirty = true;
+    maybe_arm();
     return;
   }
   for (int k = 0; k < count; ++k) {
@@ -813,11 +895,60 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
   }
 }
 
+// Arm the next iterate(true).  Called when neighbour poses arrive (updateNeighborPoses): if this accelerated
+// stand-alone RGD agent has answered all the iterate(false) calls its last launch speculated (N - 1 of them in the
+// RoundRobin schedule), the next call the wrapper makes is iterate(true) -- so its solve kernel is launched NOW, with
+// everything it can do without the neighbours' latest poses in front (lookahead commit, Nesterov phase, TMA prefetch
+// of the preconditioner slab), and waits for the doorbell.  Nothing else may want this GPU in between: any other
+// device-touching call disarms first, and a kernel nobody rings within the time-out leaves by itself.
+void Agent::maybe_arm() {
+  static const bool disabled = getenv("DPGO_B200_NO_ARM") != nullptr;
+  if (disabled || armed || !lookahead_usable() || P.method != 1 || P.cost_type != 0) return;
+  if (la_valid <= 0 || la_used != la_valid) return;
+  if (structure_dirty || values_dirty || precon_dirty || wiring_dirty || lc_dirty || team->team_dirty) return;
+  if (arm_backoff > 0) return;
+  Team *tm = team;
+  cuda_check(use_device(device), "cudaSetDevice");
+  RunArgs args{};
+  args.max_iters = 1;
+  args.force_selected = local_index;
+  args.pull_mask = 1u << local_index;
+  args.skip_stats = 1;
+  args.armed = 1;
+  static const double timeout_us = getenv("DPGO_B200_ARM_TIMEOUT_US") ? atof(getenv("DPGO_B200_ARM_TIMEOUT_US")) : 300.0;
+  args.arm_timeout_ns = (unsigned long long)(timeout_us * 1e3);
+  args.arm_decision = reinterpret_cast<int *>(tm->dBar.p + 3);
+  *tm->doorbell() = 0;
+  *tm->arm_state() = 0;
+  std::atomic_thread_fence(std::memory_order_release);
+  tm->launch_begin(args, tm->grid, false, tm->pending);
+  armed = true;
+}
+
+void Agent::disarm() {
+  if (!armed) return;
+  Team *tm = team;
+  const unsigned long long seq = tm->pending.args.seq;
+  *tm->doorbell() = seq * 2ull;
+  for (unsigned spins = 0; *tm->arm_state() != seq * 2ull; ++spins)
+    if ((spins & 0xffff) == 0xffff) {
+      const cudaError_t q = cudaStreamQuery(tm->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) cuda_check(q, "armed k_team_run (abort)");
+      if (q == cudaSuccess && *tm->arm_state() != seq * 2ull) break;   // (the kernel left some other way)
+    }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  armed = false;
+  drop_lookahead();      // the kernel committed the consumed steps before it waited
+  outbox_stale = true;
+  arm_backoff = 8;
+}
+
 bool Agent::lookahead_usable() const {
   return P.acceleration && state == 2 && team == own.get() && h_la_out != nullptr && !team->window;
 }
 
 void Agent::materialize_lookahead() {
+  if (armed) disarm();
   if (la_used == 0) return;
   cuda_check(use_device(device), "cudaSetDevice");
   RunArgs args{};
@@ -833,6 +964,7 @@ void Agent::materialize_lookahead() {
 // gradient pass at X+ against the G of the solve (still cached: G is rebuilt by the next solve only)
 void Agent::finish_opt_stats() {
   if (!stats_pending) return;
+  if (armed) disarm();
   cuda_check(use_device(device), "cudaSetDevice");
   team->prepare(false, true);  // needs X+ (X2) and G only
   const int grid = team->grid;
@@ -1014,8 +1146,10 @@ void Team::prepare(bool need_inbox, bool keep_lookahead) {
   cuda_check(use_device(device), "cudaSetDevice");
   if (agents.empty()) fail(DPGO_B200_ERR_STATE, "team has no agents");
   if (!keep_lookahead)
-    for (Agent *a : agents)
+    for (Agent *a : agents) {
+      if (a->armed) a->disarm();
       if (a->la_used > 0) a->materialize_lookahead();  // whoever comes next reads X / Y / V directly
+    }
   bool rewire = team_dirty;
   for (Agent *a : agents) {
     if (a->structure_dirty || a->values_dirty || a->precon_dirty) rewire = true;
@@ -1095,8 +1229,14 @@ void Team::prepare(bool need_inbox, bool keep_lookahead) {
   T.p.robust_inner_iters = P.robust_opt_inner_iters;
   T.p.max_num_iters = P.max_num_iters;
   T.p.rel_change_tol = P.rel_change_tol;
-  if (grid <= 0) grid = max_coop_grid(device);
-  dBar.alloc(3);  // [0]: full-grid launches, [1]: small-grid launches, [2]: last-block-done counter
+  if (grid <= 0) {
+    grid = max_coop_grid(device);
+    if (const char *g = getenv("DPGO_B200_GRID")) {   // diagnostics: CTAs of the persistent kernel
+      const int v = atoi(g);
+      if (v > 0 && v < grid) grid = v;
+    }
+  }
+  dBar.alloc(4);  // [0]: full-grid launches, [1]: small-grid launches, [2]: last-block-done counter, [3]: armed-launch decision
   {
     int total = 0;
     for (Agent *a : agents) total += a->n;
@@ -1118,10 +1258,23 @@ void Team::prepare(bool need_inbox, bool keep_lookahead) {
     Fb.rank = fab_rank;
     Fb.flags = reinterpret_cast<unsigned long long *>(window);
     Fb.payload = Fb.flags + kMaxRanks;
+    Fb.prog = Fb.flags + 3 * kMaxRanks;
     for (int s = 0; s < fab_world; ++s) {
       unsigned long long *pf = reinterpret_cast<unsigned long long *>(peer_base[s]);
       Fb.peer_flags[s] = pf;
       Fb.peer_payload[s] = pf ? pf + kMaxRanks : nullptr;
+      Fb.peer_prog[s] = pf ? pf + 3 * kMaxRanks : nullptr;
+    }
+    // ranks that host a neighbour of a local robot: the only ones the point-to-point protocol talks to
+    Fb.nbr_ranks = 0;
+    for (size_t i = 0; i < agents.size(); ++i) {
+      unsigned m = 0;
+      for (int b : agents[i]->nbrs) {
+        auto rt = routes.find({agents[i]->id, b});
+        if (rt != routes.end()) m |= 1u << rt->second.peer;
+      }
+      Fb.agent_nbr_ranks[i] = m;
+      Fb.nbr_ranks |= m;
     }
     Fb.local_mask = 0;
     for (Agent *a : agents) Fb.local_mask |= 1ull << a->id;
@@ -1159,6 +1312,7 @@ void Team::fabric_init(int world, int rank) {
   fab_world = world;
   fab_rank = rank;
   fab_seq = 0;
+  fab_step = 0;
   peer_base[rank] = window;
   team_dirty = true;
 }
@@ -1254,10 +1408,92 @@ dpgo_b200_run_result Team::fabric_run(int max_iters, bool stop_on_terminate) {
   args.stop_on_terminate = stop_on_terminate ? 1 : 0;
   args.fabric = 1;
   args.parallel = parallel_schedule_checked();
+  if (const char *fv = getenv("DPGO_B200_FAB_VARIANT")) args.fab_variant = atoi(fv);
+  if (edge_grad_loop(grid)) {
+    // LARGE agents: one tick per launch (the gradient runs in k_edge_grad in front of it); every rank takes the same
+    // decision, so the ranks still meet launch by launch
+    dpgo_b200_run_result acc{};
+    for (int it = 0; it < max_iters; ++it) {
+      RunArgs a1 = args;
+      a1.max_iters = 1;
+      a1.skip_stats = it + 1 < max_iters ? 1 : 0;
+      cuda_check(launch_fabric_rendezvous(T.fab, fab_seq + 1, stream), "k_fabric_rendezvous");
+      fab_seq += 1;
+      T.fab.seq0 = fab_seq;
+      T.fab.step0 = fab_step;
+      float ms1 = 0;
+      const int l0 = launches;
+      launch_and_read(a1, grid, true, &ms1);
+      fab_seq = ctl.fab_seq;
+      fab_step = ctl.fab_step;
+      acc.device_ms += ms1;
+      acc.kernel_launches += launches - l0;
+      acc.iterations += ctl.iters_done;
+      acc.stop_reason = ctl.stop_reason;
+      if (ctl.stop_reason == -1) {
+        cuda_check(cudaMemset(dBar.p, 0, dBar.n * sizeof(unsigned long long)), "reset barrier");
+        fail(DPGO_B200_ERR_CUDA, "fabric_run: timed out waiting for a peer GPU");
+      }
+      if (ctl.stop_reason == 1) acc.terminated = 1;
+      if ((ctl.stop_reason == 1 && stop_on_terminate) || ctl.stop_reason == 2 || ctl.iters_done == 0) break;
+    }
+    return acc;
+  }
+  // start together: a one-warp kernel in front of the timed launch meets the other ranks (all-rank barrier in the
+  // windows), so the CUDA events around the persistent kernel do not count the skew between the processes' launch
+  // calls -- with K = 20 steps of 20 us that skew used to be most of the measurement
+  cuda_check(launch_fabric_rendezvous(T.fab, fab_seq + 1, stream), "k_fabric_rendezvous");
+  fab_seq += 1;
   T.fab.seq0 = fab_seq;
+  T.fab.step0 = fab_step;
+  // diagnostics: DPGO_B200_FAB_PROF=<cta> records clock64() marks of that CTA for the first 64 steps of every launch
+  static const char *fab_prof = getenv("DPGO_B200_FAB_PROF");
+  if (fab_prof) {
+    if (dProf.n < 4096 + 64) dProf.alloc((size_t)4096 + 64);
+    cuda_check(cudaMemsetAsync(dProf.p, 0, dProf.n * sizeof(long long), stream), "clear prof");
+    T.prof = dProf.p;
+    T.prof_iters = std::min(64, args.max_iters);
+    T.prof_cta = atoi(fab_prof);
+  }
   float ms = 0;
   launch_and_read(args, grid, true, &ms);
   fab_seq = ctl.fab_seq;
+  fab_step = ctl.fab_step;
+  if (fab_prof && ctl.iters_done >= 64) {
+    std::vector<long long> h(64 * 16);
+    cuda_check(cudaMemcpy(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost), "D2H prof");
+    // marks: 0 step start, 7 after the write-after-read wait, 1 Nesterov done, 2 barrier + post, 8 after the gate,
+    // 3 gradient done, 4 barrier + post, 5 step done, 6 end
+    const int order[] = {0, 7, 1, 2, 8, 3, 4, 5, 6};
+    const char *nm[] = {"war_wait", "nesterov", "barrier_post", "gate", "gradient", "barrier_post2", "step", "tail"};
+    double acc_sel[9] = {0}, acc_non[9] = {0};
+    int nsel = 0, nnon = 0;
+    for (int it = 8; it < 63; ++it) {
+      const long long *m = &h[(size_t)it * 16];
+      const bool sel = m[3] != 0;
+      long long prev = m[0];
+      double seg[9];
+      for (int k = 1; k < 9; ++k) {
+        long long cur = m[order[k]];
+        if (cur == 0 || cur < prev) cur = prev;   // mark not hit in this step
+        seg[k - 1] = (double)(cur - prev);
+        prev = cur;
+      }
+      seg[8] = (double)(h[(size_t)(it + 1) * 16] - m[0]);   // whole step
+      for (int k = 0; k < 9; ++k) (sel ? acc_sel : acc_non)[k] += seg[k];
+      (sel ? nsel : nnon)++;
+    }
+    char path[256];
+    snprintf(path, sizeof path, "gpurun_out/fabprof_rank%d.txt", fab_rank);
+    if (FILE *fp = fopen(path, "a")) {
+      fprintf(fp, "launch of %d steps, cta %d, cycles per segment\n  with the selected robot here (%d steps):", ctl.iters_done, T.prof_cta, nsel);
+      for (int k = 0; k < 8; ++k) fprintf(fp, " %s=%.0f", nm[k], nsel ? acc_sel[k] / nsel : 0.0);
+      fprintf(fp, " step_total=%.0f\n  without (%d steps):", nsel ? acc_sel[8] / nsel : 0.0, nnon);
+      for (int k = 0; k < 8; ++k) fprintf(fp, " %s=%.0f", nm[k], nnon ? acc_non[k] / nnon : 0.0);
+      fprintf(fp, " step_total=%.0f\n", nnon ? acc_non[8] / nnon : 0.0);
+      fclose(fp);
+    }
+  }
   res.device_ms = ms;
   res.kernel_launches = 1;
   res.iterations = ctl.iters_done;
@@ -1366,9 +1602,36 @@ void Team::read_back() {
   }
 }
 
+bool Team::edge_grad_loop(int use_grid) const {
+  if (agents.empty()) return false;
+  const dpgo_b200_params &P = agents[0]->P;
+  if (P.method != 1 || !P.rgd_use_preconditioner || P.acceleration) return false;
+  static const bool disabled = getenv("DPGO_B200_NO_EDGE_GRAD") != nullptr;   // diagnostics: keep the in-kernel gradient
+  if (disabled) return false;
+  if (!team_needs_streaming(T, use_grid)) return false;
+  for (const Agent *a : agents)
+    if (!a->has_edge_arrays()) return false;
+  return true;
+}
+
+// local agents (bit mask) whose gradient of this launch comes from k_edge_grad
+unsigned Team::ext_grad_mask(const RunArgs &args, int use_grid) const {
+  if (args.max_iters != 1 || args.mode != 0 || args.commit_only || !edge_grad_loop(use_grid)) return 0;
+  if (args.parallel) return (agents.size() >= 32) ? ~0u : ((1u << agents.size()) - 1u);
+  int sel = args.force_selected;
+  if (sel == -2) sel = T.local_of_robot[ctl.selected];
+  return sel >= 0 ? (1u << sel) : 0u;
+}
+
 // launch the persistent kernel (control state travels as a kernel argument), queue ONE read-back
 // copy of the result block [ctl | stats | outboxes], synchronise once
 void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, float *ms) {
+  PendingLaunch pl;
+  launch_begin(args_in, use_grid, timed, pl);
+  launch_finish(pl, ms);
+}
+
+void Team::launch_begin(const RunArgs &args_in, int use_grid, bool timed, PendingLaunch &pl) {
   RunArgs args = args_in;
   args.seq = ++seq;
   for (Agent *a : agents) a->resid_valid = false;
@@ -1424,12 +1687,53 @@ void Team::launch_and_read(const RunArgs &args_in, int use_grid, bool timed, flo
   const TeamDev &Tl = T;
   const auto hp0 = std::chrono::steady_clock::now();
   if (timed) cuda_check(cudaEventRecord(ev0, stream), "eventRecord");
+  args.ext_grad_mask = ext_grad_mask(args, use_grid);
+  for (size_t i = 0; i < agents.size(); ++i)
+    if ((args.ext_grad_mask >> i) & 1u) {
+      Agent *a = agents[i];
+      EdgeGradArgs eg{};
+      eg.n = a->n;
+      eg.build_g = 1;
+      eg.rec = a->d_er_rec.p;
+      eg.inc_ptr = a->d_inc_ptr.p;
+      eg.inc_item = a->d_inc_item.p;
+      eg.Xin = a->dX.p;
+      eg.inbox = a->d_inbox_reg();
+      eg.G = a->dG.p;
+      eg.Rg = a->dRg.p;
+      eg.RgT = a->dRgT.p;
+      eg.partials = a->d_eg_partials.p;
+      eg.tmarks = nullptr;
+      if (a->eg_profile) {
+        cuda_check(cudaMemsetAsync(a->d_eg_marks.p, 0xff, sizeof(unsigned long long), stream), "marks");
+        cuda_check(cudaMemsetAsync(a->d_eg_marks.p + 1, 0, sizeof(unsigned long long), stream), "marks");
+        eg.tmarks = a->d_eg_marks.p;
+      }
+      cuda_check(launch_edge_grad(eg, a->r, stream), "launch k_edge_grad");
+      args.ext_partials[i] = a->d_eg_partials.p;
+      args.ext_grid[i] = edge_grad_grid(a->n);
+      ++launches;
+    }
   if ((args.force_selected == -1 || args.mode == 1) && args.max_iters == 1 && args.mode != 2)
     cuda_check(launch_nesterov_only(Tl, args, use_grid, stream), "launch k_nesterov_only");
   else
     cuda_check(launch_team_run(Tl, args, use_grid, stream), "launch k_team_run");
   if (timed) cuda_check(cudaEventRecord(ev1, stream), "eventRecord");
   ++launches;
+  pl.args = args;
+  pl.la = la;
+  pl.la_depth = la_depth;
+  pl.timed = timed;
+  pl.hp0 = hp0;
+}
+
+void Team::launch_finish(PendingLaunch &pl, float *ms) {
+  const RunArgs &args = pl.args;
+  Agent *la = pl.la;
+  const int la_depth = pl.la_depth;
+  const bool timed = pl.timed;
+  const auto hp0 = pl.hp0;
+  const dpgo_b200_params &P = agents[0]->P;
   if (timed) {
     cuda_check(cudaEventSynchronize(ev1), "k_team_run");
     if (ms) cudaEventElapsedTime(ms, ev0, ev1);
@@ -1554,16 +1858,21 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
     if (!a->all_inbox_valid(false) || (a->P.acceleration && !a->all_inbox_valid(true)))
       fail(DPGO_B200_ERR_MISSING, "team_run: neighbour poses missing; call team_exchange_all first");
   int remaining = max_iters;
+  const bool eg_loop = edge_grad_loop(grid);
   while (remaining > 0) {
     RunArgs args{};
-    args.max_iters = std::min(remaining, 1 << 16);
+    // LARGE agents: one iteration per launch, the gradient in k_edge_grad in front of it; the statistics of
+    // mLocalOptResult (a second gradient pass) only with the last iteration of this call
+    args.max_iters = eg_loop ? 1 : std::min(remaining, 1 << 16);
+    args.skip_stats = (eg_loop && remaining > 1) ? 1 : 0;
     args.force_selected = -2;
     args.stop_on_terminate = stop_on_terminate ? 1 : 0;
     args.parallel = parallel_schedule_checked();
     float ms = 0;
+    const int l0 = launches;
     launch_and_read(args, grid, true, &ms);
     res.device_ms += ms;
-    res.kernel_launches++;
+    res.kernel_launches += launches - l0;
     res.iterations += ctl.iters_done;
     remaining -= ctl.iters_done;
     if (ctl.stop_reason == 2) {
@@ -1571,8 +1880,11 @@ dpgo_b200_run_result Team::run(int max_iters, bool stop_on_terminate) {
       res.weight_updates++;
       continue;
     }
-    if (ctl.stop_reason == 1) res.terminated = 1;
-    break;
+    if (ctl.stop_reason == 1) {
+      res.terminated = 1;
+      if (stop_on_terminate) break;
+    }
+    if (ctl.iters_done == 0) break;   // nothing ran (cannot happen with max_iters >= 1; guards the loop)
   }
   res.stop_reason = ctl.stop_reason;
   return res;

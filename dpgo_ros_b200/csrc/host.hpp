@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -179,6 +180,12 @@ class Agent {
   bool lookahead_usable() const;      // stand-alone, accelerated, initialised
   void materialize_lookahead();       // write the consumed speculated state back to X / Y / V (one tiny launch)
   void drop_lookahead() { la_valid = la_used = 0; la_vsrc = -1; }
+  // ---- armed launch (Agent::arm): the solve kernel of the NEXT iterate(true) already sits on the GPU and waits for
+  // the doorbell, so that call costs neither the launch latency nor the Nesterov phase
+  bool armed = false;
+  int arm_backoff = 0;          // iterate(true) calls to sit out after an armed launch expired or was aborted
+  void maybe_arm();             // called when neighbour poses arrive and the next call is expected to be iterate(true)
+  void disarm();                // ring "abort", wait for the kernel to leave, take over the committed state
   bool stats_pending = false;  // fOpt / gradNormOpt of the last iterate(true) not evaluated yet
   void finish_opt_stats();
   DevBuf<double> d_stat_partials;
@@ -195,7 +202,8 @@ class Agent {
   bool outbox_mirror_valid = false;
   void free_pinned();
   DevBuf<double *> d_pub_dst_reg, d_pub_dst_aux;
-  DevBuf<double> dPinv;
+  DevBuf<double> dPinv, dPwork, dPdinv;   // dense preconditioner + the factorisation workspace
+  DevBuf<int> dPinfo;
   DevBuf<double> dG, dRg, dRgT, dZ, dEta, dDlt0, dDlt1, dHd, dHdT, dRv, dRvT, dRw, dRwT, dX2, dX3, dRg2, dRg2T, dZeta, dS, dS2;
   // the measurements on the device, [odom | plc | slc] (assemble.cu: MeasDev), and the slot lists of the
   // weight-dependent blocks (AssembleDev)
@@ -218,6 +226,14 @@ class Agent {
   std::vector<unsigned char> lc_mask;
   void build_lc_list();
   void upload_weights();
+  // LARGE agents: 128-byte edge records + per-pose incidence lists for k_edge_grad (edge_grad.cu)
+  static constexpr int kEdgeGradMinPoses = 1024;
+  DevBuf<double> d_er_rec, d_eg_partials;
+  DevBuf<int> d_inc_ptr;
+  DevBuf<int2> d_inc_item;
+  DevBuf<unsigned long long> d_eg_marks;   // [0] min start, [1] max end of the last profiled k_edge_grad (globaltimer ns)
+  bool has_edge_arrays() const { return d_inc_ptr.n != 0; }
+  bool eg_profile = false;
   // cached residuals of every measurement (TERMINATE handler, src/PGOAgentROS.cpp:1044-1057)
   std::vector<double> h_resid;
   bool resid_valid = false;
@@ -272,6 +288,7 @@ class Team {
   unsigned char *peer_base[kMaxRanks] = {};
   bool peer_is_ipc[kMaxRanks] = {};
   unsigned long long fab_seq = 0;
+  unsigned long long fab_step = 0;   // global steps run over the fabric (base of the point-to-point progress words)
   double fab_timeout_s = 20.0;
   std::map<std::pair<int, int>, Route> routes;  // (local robot, remote neighbour)
   void fabric_init(int world, int rank);
@@ -288,6 +305,26 @@ class Team {
   int small_grid = 1;
   void flush_inboxes();
   void launch_and_read(const RunArgs &args, int use_grid, bool timed, float *ms);
+  // the two halves of launch_and_read (an armed launch is begun by Agent::arm and finished by iterate(true))
+  struct PendingLaunch {
+    RunArgs args;
+    Agent *la = nullptr;
+    int la_depth = 0;
+    bool timed = false;
+    std::chrono::steady_clock::time_point hp0, hp1;
+  };
+  PendingLaunch pending;
+  void launch_begin(const RunArgs &args, int use_grid, bool timed, PendingLaunch &pl);
+  void launch_finish(PendingLaunch &pl, float *ms);
+  volatile unsigned long long *doorbell() const {
+    return reinterpret_cast<volatile unsigned long long *>(h_result + kCtlDoorbellOff);
+  }
+  volatile unsigned long long *arm_state() const {
+    return reinterpret_cast<volatile unsigned long long *>(h_result + kCtlArmStateOff);
+  }
+  // LARGE agents without acceleration run one iteration per launch with the gradient in k_edge_grad (edge_grad.cu)
+  bool edge_grad_loop(int use_grid) const;
+  unsigned ext_grad_mask(const RunArgs &args, int use_grid) const;
   std::vector<Agent *> agents;
   TeamDev T{};
   TeamCtl ctl{};

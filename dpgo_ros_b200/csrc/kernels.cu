@@ -54,6 +54,24 @@ __global__ void __launch_bounds__(kThreads) k_nesterov_only(const __grid_constan
   }
 }
 
+// Ranks enter a fabric launch together: arrive at all-rank barrier `seq`, wait for everybody (or for the time-out;
+// the persistent kernel behind it then times out on its own first wait and reports it).
+__global__ void k_fabric_rendezvous(const __grid_constant__ Fabric F, unsigned long long seq) {
+  const int s = threadIdx.x;
+  if (s >= F.world || s == F.rank) return;
+  __threadfence_system();
+  st_release_sys_u64(F.peer_flags[s] + F.rank, seq);
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys_u64(F.flags + s) < seq)
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > F.timeout_ns) break;
+}
+cudaError_t launch_fabric_rendezvous(const Fabric &F, unsigned long long seq, cudaStream_t stream) {
+  count_launch();
+  k_fabric_rendezvous<<<1, 32, 0, stream>>>(F, seq);
+  return cudaGetLastError();
+}
+
 // barrier / reduction micro-benchmark (diagnostics)
 __global__ void __launch_bounds__(kThreads, 1) k_barrier_bench(GridSync gs, int iters, int mode, unsigned epoch0,
                                                                double *out) {
@@ -260,6 +278,7 @@ static bool needs_streaming(const TeamDev &T, int grid) {
   }
   return false;
 }
+bool team_needs_streaming(const TeamDev &T, int grid) { return needs_streaming(T, grid); }
 template <int R>
 static cudaError_t launch_run_m(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
   if (T.p.method != 1) return launch_run_t<R, 0, false>(T, args, grid, stream);

@@ -22,6 +22,8 @@ struct RunArgs {
   //   0 full iterate, 1 Nesterov phase only (iteration counter advances), 2 local solve only
   int mode;
   int fabric;  // 1: this launch is one rank of a multi-GPU run (TeamDev::fab is live)
+  int fab_variant;  // diagnostics (DPGO_B200_FAB_VARIANT): bit 0 the selected rank keeps its redundant "2k" post,
+                    // bit 1 every thread fences at system scope after a publishing phase (round 1's belt and braces)
   unsigned pull_mask;  // local agents whose staged host inbox (AgentDev::inbox_src) is copied in by the kernel
   // stand-alone lookahead (phases.cuh, phase_lookahead)
   int la_commit;       // speculated steps the host consumed since the last launch (state = LX[la_commit - 1])
@@ -29,6 +31,18 @@ struct RunArgs {
   int la_depth;        // steps to speculate at the end of this launch
   int commit_only;     // k_nesterov_only: write the consumed state back to X / Y / V and do nothing else
   double2 la_tab[kLaMax];  // (alpha, restart != 0) of the speculated steps
+  // LARGE agents (streaming kernels, no acceleration): the gradient of these local agents (bit mask) was computed by
+  // k_edge_grad launched in front of this kernel (edge_grad.cu); only its per-CTA sums of f and |rgrad|^2 are read here
+  unsigned ext_grad_mask;
+  const double *ext_partials[kMaxLocal];
+  int ext_grid[kMaxLocal];
+  // ARMED launch of a stand-alone accelerated agent (host.cu, Agent::arm): the kernel is launched BEFORE the host's
+  // iterate(true) call, does everything that needs no neighbour pose (lookahead commit, Nesterov phase, slab prefetch),
+  // then CTA 0 waits for the doorbell word in the mapped result block; go -> pull the staged inbox and solve,
+  // abort / time-out -> put Y back, report and leave
+  int armed;
+  unsigned long long arm_timeout_ns;
+  int *arm_decision;   // device word: CTA 0's reading of the doorbell, published to the grid by the next grid barrier
   int parallel;        // 1: asynchronous mode as the equal-rate / unit-delay schedule (every robot steps every tick)
   int skip_stats;  // 1: leave fOpt / gradNormOpt of the last step to Agent::finish_opt_stats (AgentStat::optimized = 2)
 };
@@ -64,10 +78,30 @@ struct ResidualJob {
   int cost_type;
 };
 
+// edge_grad.cu: the gradient of a LARGE agent straight from 128-byte edge records (the HBM-bound regime)
+struct EdgeGradArgs {
+  int n, build_g;
+  const double *rec;         // [M][16]: R(9, column-major) | t(3) | w kappa | w tau | pad(2)
+  const int *inc_ptr;        // [n + 1] incidence list of every pose ...
+  const int2 *inc_item;      // ... (edge * 2 + "this pose is the edge's destination", pose at the other end, or
+                             //      -(inbox slot + 1) when that end belongs to a neighbour)
+  const double *Xin, *inbox;
+  double *G, *Rg, *RgT;      // linear term (written when build_g, read otherwise), Riemannian gradient (+ row-major copy)
+  double *partials;          // [grid][2]: f, |rgrad|^2 per CTA
+  unsigned long long *tmarks;  // optional: [0] min start, [1] max end (globaltimer ns) over the CTAs
+};
+int edge_grad_grid(int n);
+cudaError_t launch_pack_edge_records(const MeasDev &M, double *rec, cudaStream_t s);
+cudaError_t launch_edge_grad(const EdgeGradArgs &a, int r, cudaStream_t s);
+// whether a team takes the streaming ("BIG") kernels on a grid of `grid` CTAs
+bool team_needs_streaming(const TeamDev &T, int grid);
+
 long long kernel_launch_count();
 long long dense_inverse_launch_count();
 int max_coop_grid(int device);
 cudaError_t launch_team_run(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream);
+// all-rank meeting point in front of a fabric launch (one warp; barrier number `seq` in the windows)
+cudaError_t launch_fabric_rendezvous(const Fabric &F, unsigned long long seq, cudaStream_t stream);
 cudaError_t launch_nesterov_only(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream);
 cudaError_t launch_eval(const AgentDev &A, const double *X, const double *inbox, double *egrad, double *rgrad,
                         double *partials, int grid, cudaStream_t s);

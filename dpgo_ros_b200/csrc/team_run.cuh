@@ -140,9 +140,12 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
   double Delta = P.rtr_initial_radius;
   double maxDelta = single ? Delta : 5.0 * P.rtr_initial_radius;
   int iter = 0, shrink = 0;
-  bool stop = false;
+  // ROPTLIB evaluates the stopping criterion before the first iteration: a start whose gradient norm already meets
+  // the tolerance is returned untouched (same rule in oracle rtrRun)
+  bool stop = ngf < P.gradnorm_tol;
   const double theta = 1.0, kappa = 0.1;
   while (true) {
+    if (stop && iter == 0) break;
     if (!single && (stop || iter >= P.rtr_iterations)) break;
     // ---------------- tCG
     const double *rsrc = Rg1, *rsrcT = Rg1T;
@@ -314,6 +317,21 @@ __device__ __forceinline__ void defer_total5(const TeamDev &T, int ai, double (&
   for (int q = 0; q < 5; ++q) t[q] = wsum32(t[q]);
 }
 
+// f and |rgrad|^2 of an agent whose gradient came from k_edge_grad (edge_grad.cu): warp 0 of CTA 0 sums that kernel's
+// per-CTA partials (fixed order) into the same parked slots a gradient phase of this kernel would have filled
+__device__ __forceinline__ void ext_grad_stats(const TeamDev &T, const RunArgs &args, int ai) {
+  double pf = 0, pg2 = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const double *p = args.ext_partials[ai];
+    for (int b = threadIdx.x; b < args.ext_grid[ai]; b += 32) {
+      pf += __ldcg(p + 2 * b);
+      pg2 += __ldcg(p + 2 * b + 1);
+    }
+  }
+  defer_store(T, ai, 0, pf);
+  defer_store(T, ai, 1, pg2);
+}
+
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
@@ -357,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const bool use_slab = (M == 0) || P.rgd_use_precond;
   if (M == 2 && !args.parallel) return;  // (never launched that way)
   const bool schedule = args.force_selected < -1;
-  if (args.pull_mask) {
+  if (args.pull_mask && !args.armed) {
     // updateNeighborPoses staged the neighbours' poses in pinned host memory: fetch them with 16-byte loads
     // spread over the whole grid (one PCIe round trip, overlapped with the Nesterov phase that follows)
     for (int ai = 0; ai < T.num_local; ++ai)
@@ -373,7 +391,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   const Fabric &F = T.fab;
   const bool fab = args.fabric && F.world > 1;
   FabState fs{F.seq0};
-  unsigned long long fab_wait_to = F.seq0;  // barrier to pass before my next store into a peer's inbox
   bool dead = false;
   int done = 0;
   int stop_reason = 0;
@@ -394,6 +411,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         // poses of the previous tick.  One agent per GPU makes the ticks of all robots truly concurrent.
         for (int ai = 0; ai < T.num_local; ++ai) {
           const AgentDev &A = T.ag[ai];
+          if ((args.ext_grad_mask >> ai) & 1u) {   // G, Rg, RgT are there already (k_edge_grad in front of this launch)
+            ext_grad_stats(T, args, ai);
+            continue;
+          }
           double pf = 0, pg2 = 0;
           phase_grad<R>(A, A.X, A.inbox_reg, true, nullptr, A.Rg, A.RgT, nullptr, L.stage, pf, pg2);
           defer_store(T, ai, 0, pf);
@@ -437,6 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       sel_local = T.local_of_robot[sel_robot];
     }
     const bool restart = accel && ((iter + 1) % P.restart_interval == 0);
+    // multi-GPU: this is global step `kstep` of the fabric's point-to-point protocol (struct Fabric, device.cuh)
+    const unsigned long long kstep = F.step0 + (unsigned long long)step + 1ull;
     // Nesterov sequences come from the host (same arithmetic on every path): gamma_t, alpha_t
     double gamma = 0, alpha = 0;
     if (accel) {
@@ -445,31 +468,92 @@ __global__ void __launch_bounds__(kThreads, 1)
       alpha = ga.y;
       if (args.mode != 2) {
         __syncthreads();  // X / V / Y of my chunk were last written by other threads of this CTA
-        // the selected robot of the previous iteration has finished reading its inbox
-        if (fab && !fabric_wait(F, gs, bs, fab_wait_to)) { dead = true; break; }
+        // my neighbours have consumed what I stored into their inboxes in the previous step
+        if (fab && kstep > 1 && !fabric_wait_prog(F, gs, bs, F.nbr_ranks, 2ull * (kstep - 1) + 1ull, /*acquire=*/false)) { dead = true; break; }
+        PROF(7)
         LaCommit lc{nullptr, nullptr};
         if (step == 0 && args.la_commit > 0) {
           const size_t vec = (size_t)4 * R * T.ag[0].n;
           lc.X = T.ag[0].LX + (size_t)(args.la_commit - 1) * vec;
           lc.V = args.la_vsrc >= 0 ? T.ag[0].LX + (size_t)args.la_vsrc * vec : nullptr;
         }
+        if (args.armed && step == 0 && use_slab && sel_local >= 0)   // its HBM / L2 latency hides behind the wait below
+          slab_prefetch(T.ag[sel_local], sel_local, ss, mbar, L.slab, L.slab_cap);
         phase_nesterov_chunk<R>(T, chunks, sel_local, restart, alpha, lc);
+        if (args.armed && step == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+          // everything that does not need the neighbours is done: wait for the host's iterate(true)
+          volatile unsigned long long *db = reinterpret_cast<volatile unsigned long long *>(
+              reinterpret_cast<unsigned char *>(T.ctl) + kCtlDoorbellOff);
+          const unsigned long long go = args.seq * 2ull + 1ull, ab = args.seq * 2ull;
+          const unsigned long long t0 = globaltimer_ns();
+          int dec = 3;
+          for (unsigned spins = 1;; ++spins) {
+            const unsigned long long v = *db;
+            if (v == go) { dec = 1; break; }
+            if (v == ab) { dec = 2; break; }
+            if ((spins & 31u) == 0 && globaltimer_ns() - t0 > args.arm_timeout_ns) {
+              dec = (*db == go) ? 1 : 3;   // one last look: the host takes "expired" as final
+              break;
+            }
+          }
+          *reinterpret_cast<volatile int *>(args.arm_decision) = dec;
+        }
         PROF(1)
-        if (fab) __threadfence_system();  // my stores into peer inboxes are performed before I arrive (see fabric_arrive)
+        // peer stores of any CTA -> grid barrier (release / acquire at gpu scope) -> the poster's system fence + release
+        // store: the progress word is ordered after them by cumulativity (the NCCL / NVSHMEM "barrier, then one thread
+        // fences and flags" pattern).  A system fence in EVERY thread here costs ~6 us per phase (2-GPU profile,
+        // profiles/fabric_profile_r2.txt); fab_variant bit 1 brings it back for comparison.
+        if (fab && (args.fab_variant & 2)) __threadfence_system();
         grid_barrier(gs, bs);
-        if (fab) {  // every rank's Y (and X) of this iteration has reached its neighbours' inboxes
-          fabric_arrive(F, fs, 0);
-          if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
+        // "my Y (and X) of this step have landed".  A rank without the selected robot has no inbox to read in this
+        // step and says so in the same word; the rank WITH it says nothing yet: nobody reads its Y before a later
+        // step, and its "inbox consumed" word, a gradient phase later, covers these stores as well (one system
+        // fence less on the critical path of the selected robot)
+        if (fab && (sel_local < 0 || (args.fab_variant & 1)))
+          fabric_post(F, F.nbr_ranks, sel_local >= 0 ? 2ull * kstep : 2ull * kstep + 1ull);
+        if (args.armed && step == 0) {
+          const int dec = *reinterpret_cast<volatile int *>(args.arm_decision);   // written before CTA 0 arrived
+          if (dec != 1) {
+            // not solving after all (another call came first, or nobody rang in time): the agent's state is the
+            // committed one with Y = X again, re-published, as if this launch had only materialised the lookahead
+            const AgentDev &A0 = T.ag[0];
+            for (int k0 = 0; k0 < chunks.np[0]; k0 += kGroupsPerCta) {
+              const int k = k0 + (int)(threadIdx.x >> 3), a = threadIdx.x & 7;
+              if (k < chunks.np[0]) {
+                const int j = chunks.p0[0] + k;
+                const bool act = a < R;
+                double x[4];
+                ld4(A0.X + (size_t)j * 4 * R, R, a, act, x);
+                st4(A0.Y + (size_t)j * 4 * R, R, a, act, x);
+                publish(A0.pub_rowptr, A0.pub_dst_aux, j, R, a, act, x);
+              }
+            }
+            if (ss.pending) slab_wait(mbar, ss.parity);
+            grid_barrier(gs, bs);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+              __threadfence_system();
+              *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<unsigned char *>(T.ctl) + kCtlArmStateOff) =
+                  args.seq * 2ull;
+            }
+            return;
+          }
+          // go: the neighbours' poses are staged in pinned host memory -- fetch them (16-byte loads, whole grid)
+          const double2 *src = reinterpret_cast<const double2 *>(T.ag[0].inbox_src);
+          double2 *dst = reinterpret_cast<double2 *>(T.ag[0].inbox_reg);
+          const int cnt = T.ag[0].inbox_doubles / 2;
+          for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) dst[i] = __ldcv(src + i);
+          grid_barrier(gs, bs);
         }
         PROF(2)
       }
-    } else if (fab) {
-      // plain RBCD: the X+ published by the previous iteration's robot has arrived (its step ended with a
-      // grid barrier / reduction, so the arrival below is ordered after those stores)
-      fabric_arrive(F, fs, 0);
-      if (!fabric_wait(F, gs, bs, fs.seq)) { dead = true; break; }
     }
-    bool inbox_released = !(fab && accel);
+    if (fab && sel_local >= 0) {
+      // the gate of src/PGOAgentROS.cpp:136-149, between GPUs: the selected robot waits for ITS neighbours only --
+      // accelerated: their Y of this step; plain RBCD: the end of their previous step (their latest X+ has landed)
+      const unsigned long long need = accel ? 2ull * kstep : 2ull * (kstep - 1) + 1ull;
+      if (need > 1 && !fabric_wait_prog(F, gs, bs, F.agent_nbr_ranks[sel_local], need)) { dead = true; break; }
+      PROF(8)
+    }
     if (sel_local >= 0) {
       const AgentDev &A = T.ag[sel_local];
       const bool use_aux = accel && !restart;
@@ -483,10 +567,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         // the two gradient passes are independent: warps 0-3 take the step's gradient, warps 4-7 the
         // deferred statistics of the previous step (both fit: <= 4 groups of 16 per CTA are busy)
         const bool split = pend_ai >= 0 && A.n <= 16 * (int)gridDim.x && T.ag[pend_ai].n <= 16 * (int)gridDim.x;
-        double pf = 0, pg2 = 0;
-        phase_grad<R>(A, Xs, inbox, true, nullptr, A.Rg, A.RgT, nullptr, L.stage, pf, pg2, 0, split ? 4 : 8);
-        defer_store(T, sel_local, 0, pf);
-        defer_store(T, sel_local, 1, pg2);
+        if ((args.ext_grad_mask >> sel_local) & 1u) {   // computed by k_edge_grad in front of this launch
+          ext_grad_stats(T, args, sel_local);
+        } else {
+          double pf = 0, pg2 = 0;
+          phase_grad<R>(A, Xs, inbox, true, nullptr, A.Rg, A.RgT, nullptr, L.stage, pf, pg2, 0, split ? 4 : 8);
+          defer_store(T, sel_local, 0, pf);
+          defer_store(T, sel_local, 1, pg2);
+        }
         if (pend_ai >= 0) {
           const AgentDev &B = T.ag[pend_ai];
           double qf = 0, qg2 = 0;
@@ -498,11 +586,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         PROF(3)
         grid_barrier(gs, bs);
-        if (!inbox_released) {  // G is assembled: the other ranks may overwrite my inbox (next Nesterov phase)
-          fabric_arrive(F, fs, 0);
-          fab_wait_to = fs.seq;
-          inbox_released = true;
-        }
+        // G is assembled: my neighbours may overwrite my inbox (their next Nesterov phase)
+        if (fab && accel) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);
         PROF(4)
         double prel = 0;
         phase_rgd_step<R, BIG>(A, sel_local, P, Xs, accel, restart, gamma, ss, mbar, L.slab, L.slab_cap, L.zs,
@@ -517,8 +602,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         pend_ai = sel_local;
         touched |= 1u << sel_local;
         rel_due |= 1u << sel_local;
-        if (fab) __threadfence_system();  // X+ stored into peer inboxes: performed before the next fabric arrival
-        if (!accel) grid_barrier(gs, bs);  // plain RBCD has no Nesterov phase (and its sync) before the next gradient
+        if (fab && (args.fab_variant & 2)) __threadfence_system();  // (see the Nesterov phase: the next poster's fence covers X+)
+        if (!accel) {
+          grid_barrier(gs, bs);  // plain RBCD has no Nesterov phase (and its sync) before the next gradient
+          if (fab) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);   // my step, X+ included, is over
+        }
         PROF(6)
       } else {
         // ---- RTR (a2)
@@ -531,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, mbar, L.slab, L.slab_cap);
         }
         grid_reduce<1>(gs, bs, v, sm_red);
+        if (fab) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);   // inbox consumed, X+ published
         const double relchange = sqrt(v[0] / A.n);
         const bool ready = !(relchange > P.rel_change_tol) && A.conv_ok;
         if (ready)
@@ -547,10 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
-    if (!inbox_released) {  // ranks without the selected robot (and RTR, whose solve ends with a reduction)
-      fabric_arrive(F, fs, 0);
-      fab_wait_to = fs.seq;
-    }
+    if (fab && !accel && sel_local < 0) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);   // nothing to do in this step
     c.iter = iter;
     if (P.robust && args.mode != 2) c.robust_inner_iter++;
     ++done;
@@ -587,7 +673,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (threadIdx.x == 0) sm_mask = fabric_or_payload(F, fs.seq, mine);
           __syncthreads();
           c.ready_mask = sm_mask;
-          fab_wait_to = fs.seq;
         }
         const unsigned long long all = (N >= 64) ? ~0ull : ((1ull << N) - 1ull);
         bool terminate;
@@ -610,7 +695,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   // ---- epilogue: everything that was deferred becomes observable now
   grid_barrier(gs, bs);
-  if (args.skip_stats) pend_ai = -1;  // fOpt / gradNormOpt are evaluated on demand by the host (finish_opt_stats)
+  if (args.skip_stats) {  // fOpt / gradNormOpt are evaluated on demand by the host (finish_opt_stats) or by a later launch
+    pend_ai = -1;
+    pend_all = 0;
+  }
   if (pend_all) {
     for (int ai = 0; ai < T.num_local; ++ai) {
       const AgentDev &B = T.ag[ai];
@@ -676,6 +764,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     c.fab_seq = fs.seq;
+    c.fab_step = F.step0 + (M == 2 ? 0ull : (unsigned long long)done);
     if (dead) stop_reason = -1;
     c.stop_reason = stop_reason;
     c.iters_done = done;

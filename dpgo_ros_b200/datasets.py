@@ -591,3 +591,97 @@ def make_synthetic_problem(num_poses: int, num_edges: int, num_robots: int, seed
         T[:, :, 3] = tg[start[r]:start[r + 1]]
         T_init.append(T)
     return Problem(name=f"synthetic{num_poses}/{num_robots}", num_robots=num_robots, meas=part, n=n, T_init=T_init)
+
+
+def make_random_walk_problem(num_poses: int = 100000, num_edges: int = 1000000, num_robots: int = 8, seed: int = 0,
+                             kappa: float = 200.0, tau: float = 100.0, window: int = 2000, far_fraction: float = 0.1,
+                             g2o_path: str | None = None) -> Problem:
+    """BASELINE config 5 exactly as SURVEY 8(d) specifies it (the lattice graph of make_synthetic_problem is the
+    better-conditioned stand-in round 1 benchmarked; both are kept and the bench line says which one ran):
+
+      * poses on a seeded 3-D random walk, numpy default_rng(seed): step i -> i+1 = translation U([0.5, 1.5]) e_x in the
+        body frame, then a rotation exp(w^), w ~ N(0, 0.2^2 I);
+      * num_poses - 1 odometry edges + (num_edges - num_poses + 1) loop closures (i, j), i < j, no duplicates, none with
+        j = i + 1: 90 % with |i - j| <= `window` (2000), 10 % uniform over all pairs;
+      * measurement noise: rotation exp(N(0, 0.05^2 I)), translation N(0, 0.1^2 I); kappa = 200, tau = 100 on every edge;
+      * initial guess: the odometry chain from pose 0 (global, then cut per robot);
+      * contiguous split over `num_robots` (src/PGODatasetPublisherNode.cpp:84-103).
+
+    g2o_path: also write the graph as EDGE_SE3:QUAT with the matching information matrices (tau I_3 for the
+    translation, 2 kappa I_3 for the rotation: the SE-Sync rule of SURVEY App. B gives kappa = 3 / (2 tr(I_R^-1)),
+    tau = 3 / tr(I_t^-1) back)."""
+    rng = np.random.default_rng(seed)
+
+    def expm_so3(w):
+        th = np.maximum(np.linalg.norm(w, axis=-1, keepdims=True), 1e-12)
+        k = w / th
+        K = np.zeros(w.shape[:-1] + (3, 3))
+        K[..., 0, 1], K[..., 0, 2] = -k[..., 2], k[..., 1]
+        K[..., 1, 0], K[..., 1, 2] = k[..., 2], -k[..., 0]
+        K[..., 2, 0], K[..., 2, 1] = -k[..., 1], k[..., 0]
+        return np.eye(3) + np.sin(th)[..., None] * K + (1 - np.cos(th))[..., None] * (K @ K)
+
+    step_len = rng.uniform(0.5, 1.5, size=num_poses - 1)
+    dR = expm_so3(rng.normal(0, 0.2, size=(num_poses - 1, 3)))
+    Rgt = np.empty((num_poses, 3, 3))
+    tgt = np.zeros((num_poses, 3))
+    Rgt[0] = np.eye(3)
+    for i in range(num_poses - 1):
+        tgt[i + 1] = tgt[i] + Rgt[i][:, 0] * step_len[i]
+        Rgt[i + 1] = Rgt[i] @ dR[i]
+    n_lc = num_edges - (num_poses - 1)
+    if n_lc < 0:
+        raise ValueError("num_edges must be at least num_poses - 1")
+    n_far = int(round(far_fraction * n_lc))
+    n_near = n_lc - n_far
+    have = set()
+    src_l, dst_l = [], []
+
+    def draw(count, near):
+        got = 0
+        while got < count:
+            k = max(1024, 2 * (count - got))
+            a = rng.integers(0, num_poses, size=k)
+            if near:
+                d = rng.integers(2, window + 1, size=k)
+                b = a + d
+            else:
+                b = rng.integers(0, num_poses, size=k)
+            lo, hi = np.minimum(a, b), np.maximum(a, b)
+            ok = (hi < num_poses) & (hi - lo >= 2)
+            for x, y in zip(lo[ok].tolist(), hi[ok].tolist()):
+                key = x * num_poses + y
+                if key in have:
+                    continue
+                have.add(key)
+                src_l.append(x)
+                dst_l.append(y)
+                got += 1
+                if got == count:
+                    break
+
+    draw(n_near, True)
+    draw(n_far, False)
+    order = np.lexsort((np.array(dst_l, dtype=np.int64), np.array(src_l, dtype=np.int64)))
+    src = np.concatenate([np.arange(num_poses - 1, dtype=np.int64), np.array(src_l, dtype=np.int64)[order]])
+    dst = np.concatenate([np.arange(1, num_poses, dtype=np.int64), np.array(dst_l, dtype=np.int64)[order]])
+    m = src.shape[0]
+    Rn = expm_so3(rng.normal(0, 0.05, size=(m, 3)))
+    tn = rng.normal(0, 0.1, size=(m, 3))
+    Rrel = np.einsum("mji,mjk->mik", Rgt[src], Rgt[dst]) @ Rn
+    trel = np.einsum("mji,mj->mi", Rgt[src], tgt[dst] - tgt[src]) + tn
+    meas = Measurements(r1=np.zeros(m, np.int32), p1=src.astype(np.int32), r2=np.zeros(m, np.int32),
+                        p2=dst.astype(np.int32), R=Rrel, t=trel, kappa=np.full(m, kappa), tau=np.full(m, tau),
+                        weight=np.ones(m), fixed=np.zeros(m, np.uint8))
+    if g2o_path:
+        write_g2o(g2o_path, meas, num_poses)
+    Rg, tg = _global_odometry_init(meas, num_poses)
+    part, start = partition_contiguous(meas, num_poses, num_robots)
+    n = [int(start[r + 1] - start[r]) for r in range(num_robots)]
+    T_init = []
+    for r in range(num_robots):
+        T = np.zeros((n[r], 3, 4))
+        T[:, :, :3] = Rg[start[r]:start[r + 1]]
+        T[:, :, 3] = tg[start[r]:start[r + 1]]
+        T_init.append(T)
+    return Problem(name=f"randomwalk{num_poses}/{num_robots}", num_robots=num_robots, meas=part, n=n, T_init=T_init)

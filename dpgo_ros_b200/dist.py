@@ -507,6 +507,7 @@ def bench_multi_gpu(args, config: dict, workload: str) -> int:
     pb = datasets.load_g2o_problem("sphere2500", 8)
     dev = f"cuda:{local_rank}"
     rt = GpuRankTeam(pb, rank, world, local_rank, fabric=True, **config)
+    run_log = [args.warmup] + [2000] * 12 + [args.steps]   # every fabric launch of this rank, in order
     with benchmod.ClockSampler(local_rank) as clk:
         rt.run(args.warmup, False)
         for _ in range(12):  # ~0.5 s of back-to-back steps: clocks up, caches warm
@@ -529,6 +530,23 @@ def bench_multi_gpu(args, config: dict, workload: str) -> int:
     Xs = {rid: ag.getX() for rid, ag in rt.agents.items()}
     gathered = [None] * world
     dist.all_gather_object(gathered, Xs)
+    # in-run proof that the fabric computes what one GPU computes: rank 0 replays the same launches with all robots in
+    # ONE team on its GPU and compares every robot's iterate bit for bit (replaces a multi-GPU pytest the driver's
+    # 1-GPU test run has to skip)
+    bit_identical = None
+    if rank == 0:
+        from . import agent as gpu
+        team1, agents1 = gpu.make_team(pb, device=local_rank, **config)
+        for k in run_log:
+            team1.run(k, stop_on_terminate=False)
+        allX0 = {}
+        for g in gathered:
+            allX0.update(g)
+        bit_identical = all(np.array_equal(a.getX(), allX0[a.id]) for a in agents1)
+        team1.close()
+        for a in agents1:
+            a.close()
+    dist.barrier()
     # library baseline: the same steps host-driven, NCCL point-to-point of the packed outboxes
     nccl_steps = min(args.steps, 400)
     rn = GpuRankTeam(pb, rank, world, local_rank, fabric=False, **config)
@@ -545,7 +563,7 @@ def bench_multi_gpu(args, config: dict, workload: str) -> int:
     dist.all_reduce(nccl_ms, op=dist.ReduceOp.MAX)
     # e2e: per-robot C ABI with host buffers, driven natively (one OS thread per robot); poses between the processes
     # through shared memory
-    e2e_steps = min(args.steps, 2000)
+    e2e_steps = benchmod.e2e_step_count(args)   # the same count at every N
     ht = ShmHostTeam(pb, rank, world, local_rank, tag=str(os.environ.get("MASTER_PORT", "0")), **config)
     ht.run(40)
     dist.barrier()
@@ -596,10 +614,13 @@ def bench_multi_gpu(args, config: dict, workload: str) -> int:
             "data": "sphere2500.g2o (reference data/, odometry initial guess)",
             "config": {"workload": workload, "agents_per_gpu": 8 // world,
                        "transport": "fabric: persistent kernel per GPU, public poses stored into the neighbour's inbox "
-                                    "in peer memory (CUDA IPC over NVLink), flag barriers between the GPUs; one launch "
-                                    "per rank for all K steps",
+                                    "in peer memory (CUDA IPC over NVLink), point-to-point progress words between "
+                                    "neighbour ranks (no all-rank barrier on the critical path); one launch per rank "
+                                    "for all K steps, the ranks meet in a one-warp kernel in front of it so that the "
+                                    "CUDA events do not count launch skew",
                        "l2": "steady state, working set L2/HBM resident, no flush (see the 1-GPU line)"},
             "final_cost_2f": cost, "gpu_launches": int(launches.item()),
+            "bit_identical_to_single_team": bool(bit_identical),
             "wall_ms_per_step": float(ms[1].item()) / args.steps,
             "nccl_p2p_ms_per_step": float(nccl_ms.item()),
             "clocks": clk.summary(),

@@ -258,10 +258,17 @@ int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const int *robot_id
  * assembles it in PoseGraph::quadraticMatrix after addMeasurement :277 / clearDataMatrices :1351): dense 4n x 4n
  * column-major, once from the block-CSR copy and once from the ELL + overflow copy.  Either pointer may be NULL. */
 int dpgo_b200_debug_dense_q(dpgo_b200_agent_t a, double *Q_from_csr, double *Q_from_ell);
-/* wall-clock seconds spent inside each entry point of this library since load (or the last reset), one
- * "name seconds calls" line per entry point; returns the bytes the full report needs.  Lets a caller (the
- * reference's wrapper in oracle/_ref) split its run time into library time and its own host code. */
-int dpgo_b200_debug_api_profile(char *buf, int cap, int reset);
+/* the LARGE-agent Riemannian-gradient kernel on its own (dpgo_ros_b200/csrc/edge_grad.cu; QuadraticProblem::f /
+ * EucGrad + tangent projection straight from 128-byte edge records): f and rgrad at X (NULL: the agent's X) against
+ * the current neighbour poses, the kernel's device time (first CTA start -> last CTA end, globaltimer ns) and the
+ * CUDA-event time around the launch.  flush_l2: rewrite 512 MB first so that the graph comes from HBM. */
+int dpgo_b200_debug_edge_grad(dpgo_b200_agent_t a, const double *X, int flush_l2, double *f, double *rgrad,
+                              double *kernel_ns, double *event_ns);
+/* wall-clock seconds spent inside each entry point of this library between two instants of
+ * std::chrono::steady_clock (seconds since its epoch), one "name seconds calls" line per entry point; returns the
+ * bytes the full report needs.  Lets a caller (the reference's wrapper in oracle/_ref) split the run time of a round
+ * into library time and its own host code.  reset != 0 forgets the recorded calls afterwards. */
+int dpgo_b200_debug_api_profile(double t_begin, double t_end, char *buf, int cap, int reset);
 
 #ifdef __cplusplus
 }

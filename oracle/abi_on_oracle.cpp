@@ -38,31 +38,44 @@ static thread_local std::string g_err;
 namespace {
 struct ApiClock {
   std::mutex mu;
-  std::map<std::string, std::pair<double, long long>> acc;
+  struct Ev {
+    const char *name;
+    double t0, t1;   // steady_clock seconds
+  };
+  std::vector<Ev> ev;
 };
 ApiClock &api_clock() {
   static ApiClock c;
   return c;
 }
+inline double api_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 struct ApiTimer {
   const char *name;
-  std::chrono::steady_clock::time_point t0;
-  explicit ApiTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  double t0;
+  explicit ApiTimer(const char *n) : name(n), t0(api_now()) {}
   ~ApiTimer() {
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double t1 = api_now();
     ApiClock &c = api_clock();
     std::lock_guard<std::mutex> lock(c.mu);
-    auto &e = c.acc[name];
-    e.first += dt;
-    e.second += 1;
+    if (c.ev.size() < (size_t)4 << 20) c.ev.push_back({name, t0, t1});
   }
 };
 }  // namespace
-extern "C" int dpgo_b200_debug_api_profile(char *buf, int cap, int reset) {
+extern "C" int dpgo_b200_debug_api_profile(double t_begin, double t_end, char *buf, int cap, int reset) {
   ApiClock &c = api_clock();
   std::lock_guard<std::mutex> lock(c.mu);
+  std::map<std::string, std::pair<double, long long>> acc;
+  for (const auto &e : c.ev) {
+    const double a = std::max(e.t0, t_begin), b = std::min(e.t1, t_end);
+    if (b <= a) continue;
+    auto &x = acc[e.name];
+    x.first += b - a;
+    x.second += 1;
+  }
   std::string out;
-  for (const auto &kv : c.acc) {
+  for (const auto &kv : acc) {
     char line[160];
     snprintf(line, sizeof line, "%s %.9f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
     out += line;
@@ -72,7 +85,7 @@ extern "C" int dpgo_b200_debug_api_profile(char *buf, int cap, int reset) {
     std::memcpy(buf, out.data(), k);
     buf[k] = 0;
   }
-  if (reset) c.acc.clear();
+  if (reset) c.ev.clear();
   return (int)out.size() + 1;
 }
 

@@ -13,6 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_NATIVE = False
 
 
 class OrcParams(C.Structure):
@@ -74,11 +75,38 @@ def build(force: bool = False) -> str:
     return so
 
 
+def build_native() -> str | None:
+    """liboracle_native.so: the same sources with the reference's own flags (CMakeLists.txt:9: -O3 -march=native), built
+    ON THE MACHINE THAT RUNS IT -- what bench.py's CPU arms time (liboracle.so is pinned to x86-64-v3 so that one
+    binary runs both in the build container and on the GPU box).  None when it cannot be built here."""
+    so = os.path.join(_HERE, "liboracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                              timeout=300)
+        C.CDLL(so)
+        return so
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def use_native() -> bool:
+    """Switch this process to liboracle_native.so (before the first oracle call).  Returns whether it worked."""
+    global _LIB, _NATIVE
+    if _LIB is not None:
+        return _NATIVE
+    so = build_native()
+    if so is None:
+        return False
+    os.environ["DPGO_ORACLE_LIB"] = so
+    _NATIVE = True
+    return True
+
+
 def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    so = build()
+    so = os.environ.get("DPGO_ORACLE_LIB") or build()
     try:
         L = C.CDLL(so)
     except OSError:

@@ -668,7 +668,10 @@ Mat QuadraticOptimizer::rtrRun(const Mat &x0, int maxOuter, double initialDelta,
   tangentProject(x1, eg1, gf1);
   double ngf = std::sqrt(squaredNorm(gf1));
   double Delta = initialDelta;
-  bool isstop = false;
+  // ROPTLIB's Run() evaluates the stopping criterion BEFORE the first iteration (isstop = IsStopped(); while (!isstop
+  // && iter < Max_Iteration)): a start whose gradient norm is already below the tolerance is returned untouched
+  // ("early-return if initial ||grad|| already below tol"; round 1 always took one step)
+  bool isstop = ngf < tol;
   *lastAccepted = false;
   int iter = 0;
   enum { TR_NEGCURV, TR_EXCREGION, TR_LCON, TR_SCON, TR_MAXITER } status;
@@ -753,7 +756,9 @@ Mat QuadraticOptimizer::rtrRun(const Mat &x0, int maxOuter, double initialDelta,
 Mat QuadraticOptimizer::trustRegion(const Mat &Yinit) {
   const double initial = params_.RTR_initial_radius;
   if (params_.RTR_iterations == 1) {
-    // single-step mode: shrink the radius until the step is accepted
+    // single-step mode: shrink the radius until the step is accepted (a start that already meets the gradient
+    // tolerance takes no step at all and comes back as it is)
+    if (prob_->rieGradNorm(Yinit) < params_.gradnorm_tol) return Yinit;
     double radius = initial;
     int total = 0;
     while (true) {

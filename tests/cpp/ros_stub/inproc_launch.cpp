@@ -165,12 +165,14 @@ class Monitor {
         if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration > last_update_iteration_) last_update_iteration_ = m->executing_iteration;
         if (m->command == dpgo_ros::Command::UPDATE && m->executing_iteration == 1) {
           round_start_ = ros::sim::world().delivering_published_at;
-          dpgo_b200_debug_api_profile(nullptr, 0, 1);   // library clock: this round only
         }
         if (m->command == dpgo_ros::Command::TERMINATE) {
           round_wall_seconds_.push_back(std::chrono::duration<double>(ros::sim::world().delivering_published_at - round_start_).count());
-          std::string prof((size_t)dpgo_b200_debug_api_profile(nullptr, 0, 0), '\0');
-          dpgo_b200_debug_api_profile(&prof[0], (int)prof.size(), 0);
+          // library clock over the same window (publish-time stamps: this node may hear both commands late)
+          const double tb = std::chrono::duration<double>(round_start_.time_since_epoch()).count();
+          const double te = std::chrono::duration<double>(ros::sim::world().delivering_published_at.time_since_epoch()).count();
+          std::string prof((size_t)dpgo_b200_debug_api_profile(tb, te, nullptr, 0, 0), '\0');
+          dpgo_b200_debug_api_profile(tb, te, &prof[0], (int)prof.size(), 0);
           round_library_profile_.push_back(prof.c_str());
         }
         if (m->command == dpgo_ros::Command::TERMINATE) {

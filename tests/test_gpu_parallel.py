@@ -97,3 +97,27 @@ def test_streaming_preconditioner_matches_oracle():
     oteam.run_parallel(6, threads=2)
     for rid in range(2):
         assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-8, rid
+
+
+def test_edge_record_gradient_matches_oracle():
+    """k_edge_grad (LARGE agents: the gradient straight from 128-byte edge records, edge_grad.cu) against the oracle's
+    f and Riemannian gradient, and against the block-ELL gradient phase of the small-agent kernels, at a random point of
+    the manifold with fresh neighbour poses: private and shared edges, both orientations."""
+    pb = datasets.make_synthetic_problem(4000, 30000, 2, seed=1)
+    kw = dict(ASYNC)
+    oteam = orc.OracleTeam(pb, **kw)
+    team, agents = gpu.make_team(pb, **kw)
+    rng = np.random.default_rng(3)
+    for rid in range(2):
+        a = agents[rid]
+        X = a.getX()
+        Xr = orc.manifold_project(X + 0.05 * rng.standard_normal(X.shape))
+        f, rg, kns, ens = a.edgeGrad(Xr)
+        fo, ego, rgo = oteam.eval(rid, Xr)
+        f2, eg2, rg2 = a.eval(Xr)
+        assert abs(f - fo) <= 1e-12 * abs(fo), (rid, f, fo)
+        assert rel(rg, rgo) < 1e-12 and rel(rg, rg2) < 1e-12, (rid, rel(rg, rgo), rel(rg, rg2))
+        assert kns > 0 and ens > 0
+    team.close()
+    for a in agents:
+        a.close()

@@ -1,30 +1,28 @@
-import sys, os, time
+"""e2e through the per-robot C ABI with host buffers (dpgo_b200_sync_driver_run), armed launches on / off."""
+import sys, os, time, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["DPGO_B200_DRIVER_PROFILE"] = "1"
-from dpgo_ros_b200 import agent as gpu, datasets
-import bench
-pb = datasets.load_g2o_problem("sphere2500", 8)
-_, agents = gpu.make_team(pb, colocate=False, **bench.CONFIG2)
-gpu.exchange_host(agents, accel=True)
-gpu.sync_driver_run(agents, 50, True)
-sec, _ = gpu.sync_driver_run(agents, 2000, True)
-print("e2e it/s", 2000 / sec)
-# single-agent call latencies
-a = agents[3]
-for name, fn in (("iterate(false)", lambda: a.iterate(False)), ("iterate(true)", lambda: a.iterate(True))):
-    t = time.perf_counter()
-    for _ in range(200): fn()
-    print(name, (time.perf_counter() - t) / 200 * 1e6, "us")
-import ctypes as C
-L = a.L
-L.dpgo_b200_debug_host_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-out = (C.c_double * 4)()
-for name, flag in (("iterate(false)", False), ("iterate(true)", True)):
-    L.dpgo_b200_debug_host_profile(a.h, out, 1)
-    t = time.perf_counter()
-    for _ in range(300): a.iterate(flag)
-    dt = (time.perf_counter() - t) / 300 * 1e6
-    L.dpgo_b200_debug_host_profile(a.h, out, 1)
-    print(f"{name}: total {dt:.1f} us | launch call {out[0]/out[2]*1e6:.1f} | until result {out[1]/out[2]*1e6:.1f} | other host {dt - (out[0]+out[1])/out[2]*1e6:.1f} | kernel (events) {out[3]/out[2]*1e6:.1f}")
-# kernel-only time of a 1-agent team iteration
-from dpgo_ros_b200 import capi
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    os.environ["DPGO_B200_DRIVER_PROFILE"] = "1"
+    import numpy as np
+    from dpgo_ros_b200 import agent as gpu, datasets
+    from oracle import binding as orc
+    import bench
+    pb = datasets.load_g2o_problem("sphere2500", 8)
+    _, agents = gpu.make_team(pb, colocate=False, **bench.CONFIG2)
+    gpu.exchange_host(agents, accel=True)
+    gpu.sync_driver_run(agents, 50, True)
+    sec, _ = gpu.sync_driver_run(agents, 4000, True)
+    print("e2e it/s", 4000 / sec, "us/iter", sec / 4000 * 1e6, flush=True)
+    # parity of the whole driven run against the oracle
+    oteam = orc.OracleTeam(pb, **bench.CONFIG2)
+    oteam.run(4050, threads=8, stop_on_terminate=False)
+    err = max(np.linalg.norm(a.getX() - oteam.get_x(a.id)) / np.linalg.norm(oteam.get_x(a.id)) for a in agents)
+    print("max rel. difference to the oracle after 4050 iterations:", err, flush=True)
+    for a in agents:
+        a.close()
+else:
+    for env in ({"DPGO_B200_NO_ARM": "1"}, {}, {"DPGO_B200_NO_ARM": "1"}, {}):
+        e = dict(os.environ); e.update(env)
+        print("==", env or "armed launches", flush=True)
+        r = subprocess.run([sys.executable, __file__, "child"], env=e, capture_output=True, text=True, timeout=300)
+        print(r.stdout[-600:], r.stderr[-700:], flush=True)
