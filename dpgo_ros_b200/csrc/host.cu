@@ -28,6 +28,10 @@ static inline cudaError_t use_device(int device) {
   return cudaSetDevice(device);
 }
 
+// agents alive per device: an armed launch (Agent::maybe_arm) keeps every SM of its device busy while it waits for
+// the doorbell, which is only acceptable when nobody else can want that device
+static std::atomic<int> g_agents_on_device[64];
+
 // ============================================================================
 // Agent
 // ============================================================================
@@ -47,9 +51,11 @@ Agent::Agent(int id_, const dpgo_b200_params &p, int device_) : id(id_), P(p), d
   status.agent_id = id;
   own.reset(new Team(device_));
   own->add(this);
+  ++g_agents_on_device[device_ & 63];
 }
 
 Agent::~Agent() {
+  --g_agents_on_device[device & 63];
   if (armed) {
     try {
       disarm();
@@ -778,6 +784,7 @@ bool Agent::iterate(bool do_opt) {
     status.iteration_number = iter;
     team_status[id] = get_status();
     publish_requested = true;
+    if (la_used == la_valid) maybe_arm();   // the next call is iterate(true): have its kernel wait on the GPU
     return false;
   }
   const bool restart = accel && ((iter + 2) % P.restart_interval == 0);
@@ -787,7 +794,6 @@ bool Agent::iterate(bool do_opt) {
     if (can_opt) {
       // the solve kernel of this very call has been on the GPU since the last neighbour poses arrived (Agent::arm):
       // ring the doorbell -- the kernel pulls the staged inbox itself -- and wait for its result
-      inbox_dirty = false;
       std::atomic_thread_fence(std::memory_order_release);
       *tm->doorbell() = tm->pending.args.seq * 2ull + 1ull;
       const unsigned long long seq = tm->pending.args.seq;
@@ -805,6 +811,7 @@ bool Agent::iterate(bool do_opt) {
       }
       armed = false;
       if (!expired) {
+        inbox_dirty = false;
         float ms = 0;
         tm->launch_finish(tm->pending, &ms);
         stats_pending = true;
@@ -904,6 +911,11 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
 void Agent::maybe_arm() {
   static const bool disabled = getenv("DPGO_B200_NO_ARM") != nullptr;
   if (disabled || armed || !lookahead_usable() || P.method != 1 || P.cost_type != 0) return;
+  // the waiting kernel occupies the whole device: only when this robot has it to itself (one robot per GPU, the
+  // deployment of BASELINE config 2 at 8 GPUs).  With several robots on one device the kernel of whoever holds the
+  // UPDATE token would queue behind it (measured: the 300 us time-out every iteration).
+  static const bool shared_ok = getenv("DPGO_B200_ARM_SHARED") != nullptr;   // tests: exercise go / expiry / abort on one GPU
+  if (!shared_ok && g_agents_on_device[device & 63].load() != 1) return;
   if (la_valid <= 0 || la_used != la_valid) return;
   if (structure_dirty || values_dirty || precon_dirty || wiring_dirty || lc_dirty || team->team_dirty) return;
   if (arm_backoff > 0) return;

@@ -2,6 +2,8 @@
 the same seeded inputs.  Tolerances are written next to each assertion; the
 north-star bar is 1e-6 relative Frobenius error on the final iterate and an
 identical iteration count."""
+import os
+
 import numpy as np
 import pytest
 
@@ -386,3 +388,83 @@ def test_native_sync_driver_rtr_accelerated(small_problem):
         assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6, rid
         assert rel(agents[rid].getX(2), oteam.get_x(rid, 2)) < 1e-6, rid
         assert agents[rid].iteration_number() == 12
+
+
+def test_config3_torus3d_to_termination():
+    """BASELINE config 3 to the leader's shouldTerminate (Chordal guess like launch/dpgo_demo.launch:9, g2o precisions):
+    the north-star bar -- identical iteration-to-convergence count and <= 1e-6 relative Frobenius error on the final
+    iterate (the run is short enough for RTR's sensitivity to rounding, DESIGN.md 5, not to matter)."""
+    pb = datasets.load_g2o_problem("torus3D", 4)
+    kw = dict(r=6, method=0, rtr_iterations=3, rtr_tcg_iterations=50, gradnorm_tol=0.5, rel_change_tol=0.2)
+    o0 = orc.OracleTeam(pb, r=6, initialize=False)
+    pbc = datasets.with_local_initialization(pb, lambda rid: o0.initialize_chordal(rid))
+    oteam = orc.OracleTeam(pbc, **kw)
+    team, agents = gpu.make_team(pbc, **kw)
+    ores = oteam.run(1000)
+    res = team.run(1000)
+    assert ores.terminated and res.terminated
+    assert res.iterations == ores.iterations, (res.iterations, ores.iterations)
+    for rid in range(4):
+        assert rel(agents[rid].getX(), oteam.get_x(rid)) < 1e-6, (rid, rel(agents[rid].getX(), oteam.get_x(rid)))
+    assert abs(team.global_cost() - oteam.global_cost()) < 1e-8 * oteam.global_cost()
+
+
+@pytest.mark.slow
+def test_config4_tunnels_gnc_tls_full_schedule():
+    """BASELINE config 4 with the demo's own schedule (launch/dpgo_gnc_demo.launch:30-43: 50 inner iterations per robot
+    = 400 per stage, 3 weight updates, 3 resets, max 1598 iterations).  Every stage restarts from the initial guess
+    (robust_opt_num_resets = 3), so rounding differences are amplified over at most 400 RTR iterations; what is asserted
+    is what stays well defined through that: the same number of weight updates and of iterations to termination, the
+    same accept / reject verdict on every loop closure (weights within 1e-2 of 0 / 1 where the oracle's are), and the
+    final cost within 1e-3."""
+    pb = datasets.load_tunnels_problem()
+    kw = dict(r=5, method=0, rtr_iterations=3, rtr_tcg_iterations=50, gradnorm_tol=0.5, rel_change_tol=0.2,
+              cost_type=5, gnc_barc=3.0, gnc_mu_step=2.0, gnc_init_mu=1e-5, robust_opt_num_weight_updates=3,
+              robust_opt_num_resets=3, robust_opt_inner_iters=400, max_num_iters=1598)
+    oteam = orc.OracleTeam(pb, **kw)
+    team, agents = gpu.make_team(pb, **kw)
+    ores = oteam.run(2000, threads=4)
+    res = team.run(2000)
+    assert ores.terminated and res.terminated
+    assert res.weight_updates == ores.weight_updates == 3
+    assert res.iterations == ores.iterations, (res.iterations, ores.iterations)
+    for rid in range(8):
+        wg, wo = agents[rid].lcWeights(), oteam.lc_weights(rid)
+        settled = (wo < 1e-6) | (wo > 1 - 1e-6)
+        assert np.max(np.abs(wg[settled] - wo[settled])) < 1e-2, rid
+    assert abs(team.global_cost() - oteam.global_cost()) < 1e-3 * oteam.global_cost()
+
+
+def test_armed_launches_keep_parity(tmp_path):
+    """Armed launches (Agent::maybe_arm: the solve kernel of the next iterate(true) waits on the GPU for a doorbell) are
+    meant for one robot per GPU; DPGO_B200_ARM_SHARED=1 forces them with all 8 robots on one device, where kernels queue
+    behind a waiting one until it times out -- slow, but it drives the go, expiry and abort paths.  The driven run must
+    still match the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os
+sys.path.insert(0, os.getcwd())
+import os
+
+import numpy as np
+from dpgo_ros_b200 import agent as gpu, datasets
+from oracle import binding as orc
+kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=1, acceleration=1, restart_interval=7, rel_change_tol=0.0, max_num_iters=10 ** 9)
+pb = datasets.load_g2o_problem("sphere2500", 8)
+_, agents = gpu.make_team(pb, colocate=False, **kw)
+gpu.exchange_host(agents, accel=True)
+gpu.sync_driver_run(agents, 120, True)
+X3 = agents[3].getX()                      # a read-out in the middle of a cycle: disarms whoever is armed
+gpu.sync_driver_run(agents, 60, True)
+oteam = orc.OracleTeam(pb, **kw)
+oteam.run(180, threads=4, stop_on_terminate=False)
+err = max(np.linalg.norm(a.getX() - oteam.get_x(a.id)) / np.linalg.norm(oteam.get_x(a.id)) for a in agents)
+print("ERR", err)
+'''
+    env = dict(os.environ, DPGO_B200_ARM_SHARED="1", DPGO_B200_ARM_TIMEOUT_US="60")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0, res.stderr[-2000:]
+    err = float([l for l in res.stdout.splitlines() if l.startswith("ERR")][0].split()[1])
+    assert err < 1e-8, err
