@@ -704,6 +704,9 @@ void Agent::ensure_device() {
   if (values_dirty) build_values();
   if (lc_dirty) build_lc_list();
   if (precon_dirty) build_preconditioner();
+  // (allocated here, not at the first launch: no cudaMalloc once kernels of several ranks wait for each other)
+  if (has_edge_arrays() && need_preconditioner() && !P.acceleration && P.method == 1 && getenv("DPGO_B200_SYM_PRECOND"))
+    ensure_sym_buffers();
 }
 
 AgentDev Agent::dev_view() const {
@@ -1319,8 +1322,9 @@ void Team::fabric_init(int world, int rank) {
     a->inbox_ext = dst;
     a->wiring_dirty = true;
   }
-  // no allocation (cudaFree synchronises the device) may happen once the ranks' kernels wait for each other
+  // no allocation (cudaMalloc / cudaFree synchronise the device) may happen once the ranks' kernels wait for each other
   dGammaTab.alloc((size_t)1 << 16, false);
+  if (dProf.n < 4096 + 64) dProf.alloc((size_t)4096 + 64);
   fab_world = world;
   fab_rank = rank;
   fab_seq = 0;
@@ -1454,6 +1458,7 @@ dpgo_b200_run_result Team::fabric_run(int max_iters, bool stop_on_terminate) {
   // start together: a one-warp kernel in front of the timed launch meets the other ranks (all-rank barrier in the
   // windows), so the CUDA events around the persistent kernel do not count the skew between the processes' launch
   // calls -- with K = 20 steps of 20 us that skew used to be most of the measurement
+  const int use_grid = grid;
   cuda_check(launch_fabric_rendezvous(T.fab, fab_seq + 1, stream), "k_fabric_rendezvous");
   fab_seq += 1;
   T.fab.seq0 = fab_seq;
@@ -1461,14 +1466,13 @@ dpgo_b200_run_result Team::fabric_run(int max_iters, bool stop_on_terminate) {
   // diagnostics: DPGO_B200_FAB_PROF=<cta> records clock64() marks of that CTA for the first 64 steps of every launch
   static const char *fab_prof = getenv("DPGO_B200_FAB_PROF");
   if (fab_prof) {
-    if (dProf.n < 4096 + 64) dProf.alloc((size_t)4096 + 64);
     cuda_check(cudaMemsetAsync(dProf.p, 0, dProf.n * sizeof(long long), stream), "clear prof");
     T.prof = dProf.p;
     T.prof_iters = std::min(64, args.max_iters);
     T.prof_cta = atoi(fab_prof);
   }
   float ms = 0;
-  launch_and_read(args, grid, true, &ms);
+  launch_and_read(args, use_grid, true, &ms);
   fab_seq = ctl.fab_seq;
   fab_step = ctl.fab_step;
   if (fab_prof && ctl.iters_done >= 64) {
@@ -1614,11 +1618,22 @@ void Team::read_back() {
   }
 }
 
+void Agent::ensure_sym_buffers() {
+  if (sym_ntiles > 0 && dZt.n == (size_t)r * 4 * n) return;
+  std::vector<int> first;
+  sym_ntiles = sym_precond_tiles(4 * n, r, first);
+  sym_npanels = (int)first.size() - 1;
+  d_sym_first_tile.upload(first);
+  d_sym_partials.alloc(sym_precond_partial_doubles(sym_ntiles, r), false);
+  d_sym_counter.alloc(1);
+  dZt.alloc((size_t)r * 4 * n);
+}
+
 bool Team::edge_grad_loop(int use_grid) const {
   if (agents.empty()) return false;
   const dpgo_b200_params &P = agents[0]->P;
   if (P.method != 1 || !P.rgd_use_preconditioner || P.acceleration) return false;
-  static const bool disabled = getenv("DPGO_B200_NO_EDGE_GRAD") != nullptr;   // diagnostics: keep the in-kernel gradient
+  const bool disabled = getenv("DPGO_B200_NO_EDGE_GRAD") != nullptr;   // diagnostics: keep the in-kernel gradient
   if (disabled) return false;
   if (!team_needs_streaming(T, use_grid)) return false;
   for (const Agent *a : agents)
@@ -1725,6 +1740,28 @@ void Team::launch_begin(const RunArgs &args_in, int use_grid, bool timed, Pendin
       args.ext_partials[i] = a->d_eg_partials.p;
       args.ext_grid[i] = edge_grad_grid(a->n);
       ++launches;
+      // Z^T = (Rg Pinv)^T with one triangle of the dense inverse streamed (sym_precond.cu).  OPT-IN
+      // (DPGO_B200_SYM_PRECOND=1): correct to 1e-12 and half the HBM bytes, but on a B200 it runs at 1.8 TB/s against
+      // 3.8 TB/s for the full pass inside the persistent kernel (5.57 vs 5.27 ms per step on config 5)
+      const bool use_sym = getenv("DPGO_B200_SYM_PRECOND") != nullptr;
+      args.ext_zt[i] = nullptr;
+      if (use_sym) {
+        a->ensure_sym_buffers();
+        SymPrecondArgs sp{};
+        sp.P = a->dPinv.p;
+        sp.ld = roundup32((size_t)4 * a->n);
+        sp.n4 = 4 * a->n;
+        sp.VT = a->dRgT.p;
+        sp.Zt = a->dZt.p;
+        sp.partials = a->d_sym_partials.p;
+        sp.first_tile = a->d_sym_first_tile.p;
+        sp.npanels = a->sym_npanels;
+        sp.ntiles = a->sym_ntiles;
+        sp.tile_counter = a->d_sym_counter.p;
+        cuda_check(launch_sym_precond(sp, a->r, max_coop_grid(device), stream), "launch k_sym_precond");
+        args.ext_zt[i] = a->dZt.p;
+        launches += 2;
+      }
     }
   if ((args.force_selected == -1 || args.mode == 1) && args.max_iters == 1 && args.mode != 2)
     cuda_check(launch_nesterov_only(Tl, args, use_grid, stream), "launch k_nesterov_only");

@@ -233,6 +233,12 @@ class Agent {
   DevBuf<int2> d_inc_item;
   DevBuf<unsigned long long> d_eg_marks;   // [0] min start, [1] max end of the last profiled k_edge_grad (globaltimer ns)
   bool has_edge_arrays() const { return d_inc_ptr.n != 0; }
+  // ... and the symmetric streaming pass of the dense preconditioner (sym_precond.cu): tile table, per-tile partials,
+  // the result Z^T
+  DevBuf<double> d_sym_partials, dZt;
+  DevBuf<int> d_sym_first_tile, d_sym_counter;
+  int sym_ntiles = 0, sym_npanels = 0;
+  void ensure_sym_buffers();
   bool eg_profile = false;
   // cached residuals of every measurement (TERMINATE handler, src/PGOAgentROS.cpp:1044-1057)
   std::vector<double> h_resid;

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "device.cuh"
 
 namespace dpgo {
@@ -36,6 +38,9 @@ struct RunArgs {
   unsigned ext_grad_mask;
   const double *ext_partials[kMaxLocal];
   int ext_grid[kMaxLocal];
+  // ... and whose preconditioned gradient Z^T = (Rg Pinv)^T ([r][4n] row-major) was computed by k_sym_precond
+  // (sym_precond.cu: one triangle of Pinv streamed) -- the step phase then starts at the tangent projection
+  const double *ext_zt[kMaxLocal];
   // ARMED launch of a stand-alone accelerated agent (host.cu, Agent::arm): the kernel is launched BEFORE the host's
   // iterate(true) call, does everything that needs no neighbour pose (lookahead commit, Nesterov phase, slab prefetch),
   // then CTA 0 waits for the doorbell word in the mapped result block; go -> pull the staged inbox and solve,
@@ -93,6 +98,22 @@ struct EdgeGradArgs {
 int edge_grad_grid(int n);
 cudaError_t launch_pack_edge_records(const MeasDev &M, double *rec, cudaStream_t s);
 cudaError_t launch_edge_grad(const EdgeGradArgs &a, int r, cudaStream_t s);
+// sym_precond.cu: Zt = (V P)^T for a symmetric dense P, reading only its lower triangle (LARGE agents)
+struct SymPrecondArgs {
+  const double *P;        // n4 x n4 (leading dimension ld), column-major, symmetric
+  size_t ld;
+  int n4;
+  const double *VT;       // [r][n4] row-major operand
+  double *Zt;             // [r][n4] row-major result
+  double *partials;       // per-tile partial sums (sym_precond_partial_doubles)
+  const int *first_tile;  // [npanels + 1]
+  int npanels, ntiles;
+  int *tile_counter;
+};
+cudaError_t launch_sym_precond(const SymPrecondArgs &a, int r, int grid, cudaStream_t s);
+// tile bookkeeping of the symmetric pass: fills first_tile_of_panel[npanels + 1], returns the number of tiles
+int sym_precond_tiles(int n4, int r, std::vector<int> &first_tile_of_panel);
+size_t sym_precond_partial_doubles(int ntiles, int r);
 // whether a team takes the streaming ("BIG") kernels on a grid of `grid` CTAs
 bool team_needs_streaming(const TeamDev &T, int grid);
 

@@ -743,11 +743,13 @@ __device__ __forceinline__ void finish_pose(const AgentDev &A, int j, bool valid
 //   X+ = Retr_Xs( -eta * Proj_Xs( P^-1 rgrad ) ), fused with finish_pose.
 // With the preconditioner the CTA first computes its dense slab.
 // ---------------------------------------------------------------------------
+// ext_zt != nullptr: Z^T = (Rg Pinv)^T was computed in front of this launch (sym_precond.cu), [r][4n] row-major
 template <int R, bool BIG = false>
 __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const SolverParams &P, const double *Xs,
                                                bool accel, bool restart, double gamma, SlabState &ss,
                                                uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
-                                               double *red, double *xcopy, double &prel) {
+                                               double *red, double *xcopy, double &prel,
+                                               const double *ext_zt = nullptr) {
   const int n = A.n, r = rdim<R>(A);
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   if (P.rgd_use_precond) {
@@ -763,7 +765,7 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
     }
     DBG(20);
     // poses of this CTA's chunk are processed by group k (same ownership as phase_nesterov_chunk)
-    dense_slab<R, BIG>(A, ai, A.RgT, p0, np, ss, mbar, slab, slab_cap, zs, red);
+    if (!ext_zt) dense_slab<R, BIG>(A, ai, A.RgT, p0, np, ss, mbar, slab, slab_cap, zs, red);
     DBG(19);
     for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
       const int k = k0 + lg;
@@ -772,8 +774,13 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
       const bool act = valid && a < r;
       double y[4], z[4];
       ld4(Xs + (size_t)j * 4 * r, r, a, act, y);
+      if (ext_zt) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) z[c] = act ? zs[((valid ? k : 0) * 4 + c) * 8 + a] : 0.0;
+        for (int c = 0; c < 4; ++c) z[c] = act ? ext_zt[(size_t)a * 4 * n + 4 * j + c] : 0.0;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) z[c] = act ? zs[((valid ? k : 0) * 4 + c) * 8 + a] : 0.0;
+      }
       tangent_project_row(y, z);
       if (z[0] == 123.456) DBG(31);
       DBG(21);

@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const Fabric &F = T.fab;
   const bool fab = args.fabric && F.world > 1;
   FabState fs{F.seq0};
+#define FAB_POST(value) fabric_post(F, F.nbr_ranks, (value))
   bool dead = false;
   int done = 0;
   int stop_reason = 0;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (use_slab) slab_prefetch(A, ai, ss, mbar, L.slab, L.slab_cap);
           double prel = 0;
           phase_rgd_step<R, BIG>(A, ai, P, A.X, false, false, 0.0, ss, mbar, L.slab, L.slab_cap, L.zs, sm_slab, A.X2,
-                                 prel);
+                                 prel, ((args.ext_grad_mask >> ai) & 1u) ? args.ext_zt[ai] : nullptr);
           defer_store(T, ai, 4, prel);
           __syncthreads();  // the slab buffer and zs are reused by the next agent
         }
@@ -509,8 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         // step and says so in the same word; the rank WITH it says nothing yet: nobody reads its Y before a later
         // step, and its "inbox consumed" word, a gradient phase later, covers these stores as well (one system
         // fence less on the critical path of the selected robot)
-        if (fab && (sel_local < 0 || (args.fab_variant & 1)))
-          fabric_post(F, F.nbr_ranks, sel_local >= 0 ? 2ull * kstep : 2ull * kstep + 1ull);
+        if (fab && (sel_local < 0 || (args.fab_variant & 1))) FAB_POST(sel_local >= 0 ? 2ull * kstep : 2ull * kstep + 1ull);
         if (args.armed && step == 0) {
           const int dec = *reinterpret_cast<volatile int *>(args.arm_decision);   // written before CTA 0 arrived
           if (dec != 1) {
@@ -587,11 +587,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         PROF(3)
         grid_barrier(gs, bs);
         // G is assembled: my neighbours may overwrite my inbox (their next Nesterov phase)
-        if (fab && accel) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);
+        if (fab && accel) FAB_POST(2ull * kstep + 1ull);
         PROF(4)
         double prel = 0;
         phase_rgd_step<R, BIG>(A, sel_local, P, Xs, accel, restart, gamma, ss, mbar, L.slab, L.slab_cap, L.zs,
-                               sm_slab, A.X2, prel);
+                               sm_slab, A.X2, prel, ((args.ext_grad_mask >> sel_local) & 1u) ? args.ext_zt[sel_local] : nullptr);
         defer_store(T, sel_local, 4, prel);
         // the next agent's slab is fetched while the following phases run
         if (use_slab && schedule) {
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (fab && (args.fab_variant & 2)) __threadfence_system();  // (see the Nesterov phase: the next poster's fence covers X+)
         if (!accel) {
           grid_barrier(gs, bs);  // plain RBCD has no Nesterov phase (and its sync) before the next gradient
-          if (fab) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);   // my step, X+ included, is over
+          if (fab) FAB_POST(2ull * kstep + 1ull);   // my step, X+ included, is over
         }
         PROF(6)
       } else {
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (nxt >= 0) slab_prefetch(T.ag[nxt], nxt, ss, mbar, L.slab, L.slab_cap);
         }
         grid_reduce<1>(gs, bs, v, sm_red);
-        if (fab) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);   // inbox consumed, X+ published
+        if (fab) FAB_POST(2ull * kstep + 1ull);   // inbox consumed, X+ published
         const double relchange = sqrt(v[0] / A.n);
         const bool ready = !(relchange > P.rel_change_tol) && A.conv_ok;
         if (ready)
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
-    if (fab && !accel && sel_local < 0) fabric_post(F, F.nbr_ranks, 2ull * kstep + 1ull);   // nothing to do in this step
+    if (fab && !accel && sel_local < 0) FAB_POST(2ull * kstep + 1ull);   // nothing to do in this step
     c.iter = iter;
     if (P.robust && args.mode != 2) c.robust_inner_iter++;
     ++done;

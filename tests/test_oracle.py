@@ -1,5 +1,7 @@
 """CPU tests of the oracle: two independent restatements must agree, plus
 known-answer checks.  No GPU, no /root/reference at run time."""
+import os
+
 import numpy as np
 import pytest
 
@@ -355,3 +357,36 @@ def test_deactivated_neighbour_equals_removed_edges():
     for _ in range(3):
         d.iterate(1, True)
     assert np.linalg.norm(d.get_x(1) - c.get_x(1)) <= 1e-12 * np.linalg.norm(Xb)
+
+
+def test_random_walk_generator_follows_survey_8d(tmp_path):
+    """datasets.make_random_walk_problem: the config-5 generator exactly as SURVEY 8(d) specifies it -- seeded random
+    walk, num_poses - 1 odometry edges, loop closures without duplicates (90 % within the window, 10 % anywhere), constant
+    kappa / tau, odometry initial guess, a g2o file that reads back to the same measurements."""
+    path = os.path.join(str(tmp_path), "rw.g2o")
+    pb = datasets.make_random_walk_problem(3000, 30000, 4, seed=0, window=200, g2o_path=path)
+    m = pb.meas
+    assert sum(pb.n) == 3000 and len(m) == 30000
+    start = np.concatenate([[0], np.cumsum(pb.n)])
+    gi = start[m.r1] + m.p1
+    gj = start[m.r2] + m.p2
+    assert np.all(gi < gj)
+    assert np.sum(gj - gi == 1) == 2999                          # exactly the odometry chain
+    assert len(set(zip(gi.tolist(), gj.tolist()))) == len(m)      # no duplicates
+    lc = gj - gi > 1
+    near = np.sum((gj - gi)[lc] <= 200)
+    assert 0.88 * lc.sum() <= near <= 0.93 * lc.sum()             # 90 % near + the few uniform ones that fall inside
+    assert np.all(m.kappa == 200.0) and np.all(m.tau == 100.0)
+    again = datasets.make_random_walk_problem(3000, 30000, 4, seed=0, window=200)
+    assert np.array_equal(again.meas.R, m.R) and np.array_equal(again.meas.t, m.t)
+    meas2, n2 = datasets.read_g2o(path)
+    assert n2 == 3000 and len(meas2) == 30000
+    assert np.allclose(meas2.kappa, 200.0) and np.allclose(meas2.tau, 100.0)
+    order = np.lexsort((gj, gi))
+    assert np.allclose(meas2.t[np.lexsort((meas2.p2, meas2.p1))], m.t[order], atol=1e-12)
+    # the odometry guess is exact on the odometry edges
+    T = np.concatenate(pb.T_init)
+    e = np.nonzero(gj - gi == 1)[0][:50]
+    for k in e:
+        Ri, ti, Rj, tj = T[gi[k]][:, :3], T[gi[k]][:, 3], T[gj[k]][:, :3], T[gj[k]][:, 3]
+        assert np.allclose(Ri @ m.R[k], Rj, atol=1e-9) and np.allclose(ti + Ri @ m.t[k], tj, atol=1e-9)

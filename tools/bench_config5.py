@@ -7,6 +7,7 @@ so it is the HBM-bound regime SURVEY 8d names for the roofline statement.
     python tools/bench_config5.py [--poses 100000 --edges 1000000 --robots 8 --robot 0 --iters 10]
 """
 import argparse, json, os, sys, time
+os.environ["DPGO_B200_SYM_PRECOND"] = "1"   # allocate the symmetric pass's buffers with the agent (variant 1 below)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dpgo_ros_b200 import agent as gpu, datasets, capi
@@ -51,6 +52,22 @@ t0 = time.time()
 ag.iterate(True)          # first call builds Q, the dense inverse and everything else
 t_setup = time.time() - t0
 L = capi.lib()
+variants = {}
+for name, env in (("edge-record gradient + one triangle of Pinv (opt-in)", {"DPGO_B200_SYM_PRECOND": "1"}),
+                  ("edge-record gradient + full Pinv pass inside the persistent kernel (default)", {}),
+                  ("everything inside the persistent kernel (round 1)", {"DPGO_B200_NO_EDGE_GRAD": "1"})):
+    for k in ("DPGO_B200_SYM_PRECOND", "DPGO_B200_NO_EDGE_GRAD"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    ag.iterate(True)
+    tv = []
+    for _ in range(args.iters):
+        t0 = time.perf_counter()
+        ag.iterate(True)
+        tv.append(time.perf_counter() - t0)
+    variants[name] = float(np.median(tv)) * 1e3
+for k in ("DPGO_B200_SYM_PRECOND", "DPGO_B200_NO_EDGE_GRAD"):
+    os.environ.pop(k, None)
 ts = []
 for _ in range(args.iters):
     t0 = time.perf_counter()
@@ -58,6 +75,13 @@ for _ in range(args.iters):
     ts.append(time.perf_counter() - t0)
 opt = ag.localOptResult()
 ms = float(np.median(ts)) * 1e3
+grad_us = None
+try:
+    g = [ag.edgeGrad(None, flush_l2=True)[2] for _ in range(7)]
+    gw = [ag.edgeGrad(None, flush_l2=False)[2] for _ in range(7)]
+    grad_us = {"cold_l2": float(np.median(g)) * 1e-3, "warm_l2": float(np.median(gw)) * 1e-3}
+except Exception as e:  # noqa: BLE001
+    grad_us = {"error": str(e)[:200]}
 n4 = 4 * n
 npad = (n4 + 31) // 32 * 32
 b_precond = npad * npad * 8 + 2 * n * args.r * 4 * 8
@@ -67,7 +91,7 @@ peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
 achieved = (b_precond + b_grad) / (ms * 1e-3) / 1e9
 print(json.dumps({"workload": f"synthetic {args.poses} poses / {args.edges} edges / {args.robots} agents, robot {rid} "
                               f"(n={n}, {edges} edges, {len(need)} neighbours), r={args.r}, RGD 0.2 + dense preconditioner",
-                  "ms_per_iterate": ms, "setup_s": t_setup, "generate_s": t_gen, "f_init": opt.f_init,
+                  "ms_per_iterate": ms, "ms_per_iterate_by_variant": variants, "k_edge_grad_us": grad_us, "setup_s": t_setup, "generate_s": t_gen, "f_init": opt.f_init,
                   "gradnorm_init": opt.gradnorm_init, "relative_change": opt.relative_change,
                   "algorithmic_bytes": b_precond + b_grad, "achieved_GBps": achieved, "peak_GBps": peak,
                   "frac": achieved / peak}))
