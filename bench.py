@@ -390,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3000, help="bounded CPU-baseline sample (steps)")
     ap.add_argument("--e2e-steps", type=int, default=2000, help="lower bound of the steps the e2e arm is timed over")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary objects (async_mode, hbm_bound_regime, reference_wrapper): profiler runs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -463,12 +465,16 @@ def main():
             break
     model_achieved = step_bytes * args.steps / (res.device_ms * 1e-3) / 1e9
     cpu = cpu_reference(args.cpu_steps, 50)
-    async_mode = async_mode_single_gpu(pb, local_rank)
-    async_mode["cpu_ticks_per_s"] = async_cpu_reference()
-    try:
-        hbm_regime = hbm_regime_single_rank(local_rank)
-    except Exception as e:  # noqa: BLE001  (secondary figure: never fail the bench line over it)
-        hbm_regime = {"error": str(e)[:200]}
+    if args.no_secondary:
+        async_mode = hbm_regime = wrapper = {"skipped": "--no-secondary"}
+    else:
+        async_mode = async_mode_single_gpu(pb, local_rank)
+        async_mode["cpu_ticks_per_s"] = async_cpu_reference()
+        try:
+            hbm_regime = hbm_regime_single_rank(local_rank)
+        except Exception as e:  # noqa: BLE001  (secondary figure: never fail the bench line over it)
+            hbm_regime = {"error": str(e)[:200]}
+        wrapper = reference_wrapper_e2e()
     line = {
         "metric": "rbcd_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -508,7 +514,7 @@ def main():
                          "iterate_true_median_us": cpu.get("iterate_true_median_us")},
         "async_mode": async_mode,
         "hbm_bound_regime": hbm_regime,
-        "reference_wrapper": reference_wrapper_e2e(),
+        "reference_wrapper": wrapper,
     }
     print(json.dumps(line))
     return 0

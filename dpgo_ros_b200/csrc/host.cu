@@ -912,7 +912,7 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
 // of the preconditioner slab), and waits for the doorbell.  Nothing else may want this GPU in between: any other
 // device-touching call disarms first, and a kernel nobody rings within the time-out leaves by itself.
 void Agent::maybe_arm() {
-  static const bool disabled = getenv("DPGO_B200_NO_ARM") != nullptr;
+  const bool disabled = getenv("DPGO_B200_NO_ARM") != nullptr;
   if (disabled || armed || !lookahead_usable() || P.method != 1 || P.cost_type != 0) return;
   // the waiting kernel occupies the whole device: only when this robot has it to itself (one robot per GPU, the
   // deployment of BASELINE config 2 at 8 GPUs).  With several robots on one device the kernel of whoever holds the
