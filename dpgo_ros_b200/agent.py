@@ -447,3 +447,20 @@ def exchange_payload_bytes(agents: List[PGOAgent], accelerated: bool) -> int:
         for nb in a.getNeighbors():
             total += a.L.dpgo_b200_num_shared_poses(a.h, nb) * a.r * 4 * 8 * (2 if accelerated else 1)
     return total
+
+
+def spd_inverse(A: np.ndarray, device: int = 0) -> Tuple[np.ndarray, float]:
+    """A^-1 of a symmetric positive definite matrix through the library's own dense inverse
+    (`dpgo_b200_debug_spd_inverse`, dpgo_ros_b200/csrc/dense_inverse.cu -- the kernel set behind the preconditioner,
+    where the reference factors Q + lambda I with CHOLMOD).  N is padded to a multiple of 32 with identity, as the
+    library pads its own matrices.  Returns (inverse, device milliseconds of the factorisation)."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    N = (n + 31) // 32 * 32
+    Ap = np.eye(N)
+    Ap[:n, :n] = A
+    Af = np.asfortranarray(Ap)
+    P = np.empty((N, N), dtype=np.float64, order="F")
+    ms = C.c_double(0.0)
+    check(capi.lib().dpgo_b200_debug_spd_inverse(int(device), N, _dp(Af), _dp(P), C.byref(ms)), "debug_spd_inverse")
+    return np.ascontiguousarray(P[:n, :n]), ms.value

@@ -85,6 +85,7 @@ SYMBOLS = [
     "dpgo_b200_get_pose", "dpgo_b200_sync_driver_shm_bytes", "dpgo_b200_sync_driver_run_shm",
     "dpgo_b200_initialize_chordal", "dpgo_b200_get_local_trajectory", "dpgo_b200_set_iteration_number", "dpgo_b200_set_robot_active",
     "dpgo_b200_debug_dense_q", "dpgo_b200_debug_api_profile", "dpgo_b200_debug_edge_grad",
+    "dpgo_b200_debug_spd_inverse",
 ]
 
 
@@ -157,6 +158,7 @@ def lib():
     L.dpgo_b200_get_shared_loop_closures.argtypes = [vp, ip, ip, ip, ip, dp, C.POINTER(C.c_ubyte), C.c_int]
     L.dpgo_b200_debug_dense_q.argtypes = [vp, dp, dp]
     L.dpgo_b200_debug_edge_grad.argtypes = [vp, dp, C.c_int, dp, dp, dp, dp]
+    L.dpgo_b200_debug_spd_inverse.argtypes = [C.c_int, C.c_int, dp, dp, dp]
     L.dpgo_b200_debug_api_profile.argtypes = [C.c_double, C.c_double, C.c_char_p, C.c_int, C.c_int]
     L.dpgo_b200_eval.argtypes = [vp, dp, dp, dp, dp]
     L.dpgo_b200_hess.argtypes = [vp, dp, dp, dp]

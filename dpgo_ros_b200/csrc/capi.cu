@@ -52,6 +52,16 @@ struct ApiTimer {
 };
 }  // namespace
 
+namespace dpgo {
+ProfSection::ProfSection(const char *n) : name(n), t0(api_now()) {}
+ProfSection::~ProfSection() {
+  const double t1 = api_now();
+  ApiClock &c = api_clock();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (c.ev.size() < (size_t)4 << 20) c.ev.push_back({name, t0, t1});
+}
+}  // namespace dpgo
+
 #define API_BEGIN   \
   ApiTimer api_timer_(__func__); \
   try {
@@ -720,6 +730,35 @@ int dpgo_b200_debug_dense_q(dpgo_b200_agent_t h, double *Q_csr, double *Q_ell) {
       for (int e = orp[j]; e < orp[j + 1]; ++e) put(Q_ell, j, oc[e], &ov[(size_t)e * 16]);
     }
   }
+  API_END
+}
+int dpgo_b200_debug_spd_inverse(int device, int N, const double *Ah, double *Ph, double *device_ms) {
+  API_BEGIN
+  if (N <= 0 || N % 32 != 0 || !Ah || !Ph) fail(DPGO_B200_ERR_INVALID, "spd_inverse: N must be a positive multiple of 32");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  const size_t NN = (size_t)N * N;
+  DevBuf<double> dA, dW;
+  DevBuf<int> dinfo;
+  dA.alloc(NN, false);
+  dW.alloc(NN, false);
+  dinfo.alloc(1);
+  cuda_check(cudaMemcpy(dA.p, Ah, NN * sizeof(double), cudaMemcpyHostToDevice), "H2D A");
+  cudaEvent_t e0, e1;
+  cuda_check(cudaEventCreate(&e0), "event");
+  cuda_check(cudaEventCreate(&e1), "event");
+  cuda_check(cudaEventRecord(e0, 0), "event record");
+  cuda_check(spd_inverse(dA.p, dW.p, N, dinfo.p, 0), "spd_inverse");
+  cuda_check(cudaEventRecord(e1, 0), "event record");
+  cuda_check(cudaDeviceSynchronize(), "spd_inverse kernels");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (device_ms) *device_ms = ms;
+  int info = 0;
+  cuda_check(cudaMemcpy(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
+  if (info != 0) fail(DPGO_B200_ERR_NUMERIC, "spd_inverse: the matrix is not positive definite (pivot " + std::to_string(info) + ")");
+  cuda_check(cudaMemcpy(Ph, dA.p, NN * sizeof(double), cudaMemcpyDeviceToHost), "D2H P");
   API_END
 }
 // "name seconds calls\n" per entry point, restricted to the part of every call that fell inside [t_begin, t_end]

@@ -177,6 +177,7 @@ void Agent::initialize(const double *T) {
 // comes from the preconditioner machinery (dense_inverse.cu); the host only assembles the sparse blocks and the two
 // right-hand sides.  Same arithmetic as oracle Agent::initializeChordal.
 void Agent::initialize_chordal() {
+  ProfSection prof_(".chordal");
   if (n == 0) fail(DPGO_B200_ERR_STATE, "initialize: empty pose graph");
   cuda_check(use_device(device), "cudaSetDevice");
   Tlocal.assign((size_t)12 * n, 0.0);
@@ -232,16 +233,15 @@ void Agent::initialize_chordal() {
     }
     const size_t npad = roundup32((size_t)4 * N);
     DevBuf<int> d_rp, d_ci, info;
-    DevBuf<double> d_v, P, work, dinv, dB, dZ;
+    DevBuf<double> d_v, P, work, dB, dZ;
     d_rp.upload(rowptr);
     d_ci.upload(colidx);
     d_v.upload(vals);
     P.alloc(npad * npad);
     work.alloc(npad * npad, false);
-    dinv.alloc((npad / 32) * 1024, false);
     info.alloc(1);
     cuda_check(launch_scatter_blocks(P.p, npad, d_rp.p, d_ci.p, d_v.p, N, 0.0, (int)npad, 0), "scatter_blocks");
-    cuda_check(spd_inverse(P.p, work.p, dinv.p, (int)npad, info.p, 0), "spd_inverse");
+    cuda_check(spd_inverse(P.p, work.p, (int)npad, info.p, 0), "spd_inverse");
     int h_info = 0;
     cuda_check(cudaMemcpy(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
     if (h_info != 0) fail(DPGO_B200_ERR_NUMERIC, "Chordal initialisation: the pose graph is not connected to pose 0");
@@ -348,6 +348,7 @@ void Agent::reset() {
 
 // ---- device structures --------------------------------------------------------
 void Agent::build_structure() {
+  ProfSection prof_(".build_structure");
   // neighbour slots, ordered by (robot, frame)
   slot_of.clear();
   slot_key.clear();
@@ -602,6 +603,7 @@ void Agent::build_structure() {
 // loop closures subject to re-weighting: every non-fixed private / shared loop closure; the lower-ID robot owns a
 // shared edge's weight (src/PGOAgentROS.cpp:732, 1340)
 void Agent::build_lc_list() {
+  ProfSection prof_(".build_lc_list");
   lc_meas.clear();
   lc_mask.clear();
   const int no = (int)odom.size(), np = (int)plc.size();
@@ -655,6 +657,7 @@ AssembleDev Agent::assemble_view() const {
 // most the weight vector (when the host changed a weight: setMeasurementWeight, a neighbour's weights) and the
 // per-measurement "neighbour deactivated" flags -- never a matrix.
 void Agent::build_values() {
+  ProfSection prof_(".build_values");
   if (lc_dirty) build_lc_list();
   if (weights_host_dirty) upload_weights();
   {
@@ -675,6 +678,7 @@ void Agent::build_values() {
 }
 
 void Agent::build_preconditioner() {
+  ProfSection prof_(".build_preconditioner");
   if (!need_preconditioner()) {
     precon_dirty = false;
     return;
@@ -685,12 +689,11 @@ void Agent::build_preconditioner() {
   // robot: cudaMalloc / cudaFree of a few MB each time cost more than the kernels on the tunnels robots, and
   // cudaFree synchronises the device) -- except for agents whose workspace is measured in GB
   dPwork.alloc(npad * npad, false);
-  dPdinv.alloc((npad / 32) * 1024, false);
   dPinfo.alloc(1);
   cuda_check(launch_scatter_blocks(dPinv.p, npad, d_q_rowptr.p, d_q_col.p, d_q_val.p, n, P.precond_lambda,
                                    (int)npad, 0),
              "scatter_blocks");
-  cuda_check(spd_inverse(dPinv.p, dPwork.p, dPdinv.p, (int)npad, dPinfo.p, 0), "spd_inverse");
+  cuda_check(spd_inverse(dPinv.p, dPwork.p, (int)npad, dPinfo.p, 0), "spd_inverse");
   int h_info = 0;
   cuda_check(cudaMemcpy(&h_info, dPinfo.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
   if (npad * npad * sizeof(double) > ((size_t)1 << 30)) dPwork.release();
@@ -767,7 +770,10 @@ bool Agent::iterate(bool do_opt) {
     if (P.cost_type != 0) tm->ctl.robust_inner_iter = ++robust_inner_iter;
     return false;
   }
-  tm->prepare(false, true);
+  {
+    ProfSection prof_(".prepare");
+    tm->prepare(false, true);
+  }
   const bool accel = P.acceleration != 0;
   if (!do_opt && la_used < la_valid && lookahead_usable()) {
     // this iterate(false) was computed ahead of time by the last launch (phase_lookahead): no GPU round trip
@@ -838,7 +844,10 @@ bool Agent::iterate(bool do_opt) {
     return false;
   }
   if (do_opt && arm_backoff > 0) --arm_backoff;
-  tm->run_forced(can_opt ? local_index : -1);
+  {
+    ProfSection prof_(can_opt ? ".solve" : ".step_without_solve");
+    tm->run_forced(can_opt ? local_index : -1);
+  }
   publish_requested = accel || can_opt;  // mPublishPublicPosesRequested, src/PGOAgentROS.cpp:109
   return can_opt;
 }

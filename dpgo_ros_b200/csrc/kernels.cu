@@ -262,10 +262,13 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 11 * 1024;  // leave room for the st
 
 template <int R, int M, bool BIG>
 cudaError_t launch_run_t(const TeamDev &T, RunArgs args, int grid, cudaStream_t stream);
-// a team with an agent whose per-pose slab (4 columns of Pinv) exceeds the shared-memory budget takes the
-// streaming kernels
+// a team with an agent whose slab (the columns of Pinv of one CTA's poses) exceeds the shared-memory budget takes the
+// streaming kernels.  RGD under the synchronous schedule prefetches the selected agent's first sub-chunk during the
+// phases in front of the dense pass, so it only streams when not even one pose's columns fit; RTR applies the
+// preconditioner back to back (tCG) and streams as soon as the chunk would have to be re-filled in pieces.
 static bool needs_streaming(const TeamDev &T, int grid) {
-  if (T.p.method != 1 || !T.p.rgd_use_precond) return false;
+  const bool rtr = T.p.method != 1;
+  if (!rtr && !T.p.rgd_use_precond) return false;
   int max_n = 1;
   for (int i = 0; i < T.num_local; ++i) max_n = std::max(max_n, T.ag[i].n);
   // same budget as smem_plan (team_run.cuh): what is left for the slab after the staging tiles and zs
@@ -274,14 +277,17 @@ static bool needs_streaming(const TeamDev &T, int grid) {
   const size_t slab_cap = fixed + 16 * 1024 < kMaxDynSmem ? ((kMaxDynSmem - fixed) / 128) * 128 : 0;
   for (int i = 0; i < T.num_local; ++i) {
     const size_t ldp = ((size_t)4 * T.ag[i].n + 31) / 32 * 32;
-    if (4 * ldp * sizeof(double) > slab_cap) return true;  // not even one pose's columns fit
+    const size_t poses = rtr ? (size_t)(T.ag[i].n + grid - 1) / grid : 1;
+    if (poses * 4 * ldp * sizeof(double) > slab_cap) return true;
   }
   return false;
 }
 bool team_needs_streaming(const TeamDev &T, int grid) { return needs_streaming(T, grid); }
 template <int R>
 static cudaError_t launch_run_m(const TeamDev &T, const RunArgs &args, int grid, cudaStream_t stream) {
-  if (T.p.method != 1) return launch_run_t<R, 0, false>(T, args, grid, stream);
+  if (T.p.method != 1)
+    return needs_streaming(T, grid) ? launch_run_t<R, 0, true>(T, args, grid, stream)
+                                    : launch_run_t<R, 0, false>(T, args, grid, stream);
   if (needs_streaming(T, grid))
     return args.parallel ? launch_run_t<R, 2, true>(T, args, grid, stream) : launch_run_t<R, 1, true>(T, args, grid, stream);
   return args.parallel ? launch_run_t<R, 2, false>(T, args, grid, stream) : launch_run_t<R, 1, false>(T, args, grid, stream);

@@ -147,6 +147,6 @@ cudaError_t launch_measurement_residuals(const MeasDev &M, const ResidualJob &J,
 // dense_inverse.cu: P <- (blocks scattered) ; P <- P^-1 (SPD), N multiple of 32
 cudaError_t launch_scatter_blocks(double *P, size_t ld, const int *rowptr, const int *col, const double *val,
                                   int n, double lambda, int npad, cudaStream_t s);
-cudaError_t spd_inverse(double *A, double *work, double *dinv, int N, int *d_info, cudaStream_t s);
+cudaError_t spd_inverse(double *A, double *work, int N, int *d_info, cudaStream_t s);
 
 }  // namespace dpgo

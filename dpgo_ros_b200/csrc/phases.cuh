@@ -637,7 +637,9 @@ __device__ __forceinline__ void dense_slab(const AgentDev &A, int ai, const doub
   const int r = rdim<R>(A), n4 = 4 * A.n;
   const size_t ldp = agent_ldp(A);
   const int pps = slab_poses(A, np, slab_cap_bytes);
-  if (pps <= 0) {
+  // BIG kernels stream whenever the CTA's whole chunk does not fit shared memory: re-filling the buffer pose by pose
+  // is load-then-compute (1.3 TB/s at n = 1250), the streaming pass keeps QC x NC loads per thread in flight
+  if (BIG ? pps < np : pps <= 0) {
     // slab larger than shared memory (BASELINE config 5: n = 12 500 poses, 136 MB of columns per CTA): stream the
     // columns from global memory.  This is the HBM-bound regime -- Pinv is read exactly once per application.
     // With all 36 loads of a chunk requested before the first multiply (dense_pass<R, true>) the pass runs at
@@ -819,7 +821,7 @@ __device__ __forceinline__ void phase_rgd_step(const AgentDev &A, int ai, const 
 
 // Z = Proj_Xbase( V Pinv ) for the whole agent (tCG preconditioner, a6).  Writes
 // Z and optionally dlt = -Z; pzr accumulates <Z, Rin>.
-template <int R>
+template <int R, bool BIG = false>
 __device__ __forceinline__ void phase_precond(const AgentDev &A, int ai, const double *Xbase, const double *Rin,
                                               const double *RinT, double *Zout, double *neg_out, SlabState &ss,
                                               uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
@@ -828,7 +830,7 @@ __device__ __forceinline__ void phase_precond(const AgentDev &A, int ai, const d
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   int p0, np;
   cta_pose_chunk(n, p0, np);
-  dense_slab<R>(A, ai, RinT, p0, np, ss, mbar, slab, slab_cap, zs, red);
+  dense_slab<R, BIG>(A, ai, RinT, p0, np, ss, mbar, slab, slab_cap, zs, red);
   for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
     const int k = k0 + lg;
     const bool valid = k < np;
@@ -973,7 +975,7 @@ __device__ __forceinline__ void phase_hess_dir(const AgentDev &A, const double *
 // z+ = Proj_Xbase( (r + alpha Hd) Pinv ) for the whole agent, and for the poses of this CTA's chunk:
 //   r+ = r + alpha Hd  (stored column- and row-major),  eta (+)= alpha delta,
 //   prr += |r+|^2,  pzr += <z+, r+>.
-template <int R>
+template <int R, bool BIG = false>
 __device__ __forceinline__ void phase_precond_cg(const AgentDev &A, int ai, const double *Xbase, const double *Rin,
                                                  const double *RinT, const double *Hd, const double *HdT,
                                                  double alpha, const double *Dcur, bool eta_zero, double *eta,
@@ -985,7 +987,7 @@ __device__ __forceinline__ void phase_precond_cg(const AgentDev &A, int ai, cons
   const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
   int p0, np;
   cta_pose_chunk(n, p0, np);
-  dense_slab<R, false, true>(A, ai, RinT, p0, np, ss, mbar, slab, slab_cap, zs, red, HdT, alpha);
+  dense_slab<R, BIG, true>(A, ai, RinT, p0, np, ss, mbar, slab, slab_cap, zs, red, HdT, alpha);
   for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
     const int k = k0 + lg;
     const bool valid = k < np;

@@ -118,7 +118,7 @@ struct RtrOut {
   int outer, tcg, rej;
 };
 
-template <int R>
+template <int R, bool BIG = false>
 __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const SolverParams &P, const GridSync &gs,
                                             BarState &bs, const double *Xs, const double *inbox, SlabState &ss,
                                             uint64_t *mbar, const SmemLayout &L, double *red, double *sm) {
@@ -151,7 +151,7 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
     const double *rsrc = Rg1, *rsrcT = Rg1T;
     const double norm_r0 = ngf;
     v[0] = 0;
-    phase_precond<R>(A, ai, x1, rsrc, rsrcT, A.Z, A.dlt0, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
+    phase_precond<R, BIG>(A, ai, x1, rsrc, rsrcT, A.Z, A.dlt0, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
     grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
     double z_r = v[0], d_Pd = z_r, e_Pe = 0.0, e_Pd = 0.0;
     bool eta_zero = true;
@@ -177,7 +177,7 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
       }
       e_Pe = e_Pe_new;
       v[0] = v[1] = 0;
-      phase_precond_cg<R>(A, ai, x1, rsrc, rsrcT, A.Hd, A.HdT, alpha, dcur, eta_zero, A.eta, rnext, rnextT, A.Z, ss,
+      phase_precond_cg<R, BIG>(A, ai, x1, rsrc, rsrcT, A.Hd, A.HdT, alpha, dcur, eta_zero, A.eta, rnext, rnextT, A.Z, ss,
                           mbar, L.slab, L.slab_cap, L.zs, red, v[0], v[1]);
       eta_zero = false;
       grid_reduce<2>(gs, bs, reinterpret_cast<double(&)[2]>(v), sm);
@@ -338,7 +338,7 @@ __device__ __forceinline__ void ext_grad_stats(const TeamDev &T, const RunArgs &
 // M: local solver / schedule, fixed at compile time (0 RTR, 1 RGD, 2 RGD under the parallel schedule) so that the RGD kernel -- the bench workload and the
 // stand-alone iterate() path -- does not carry the RTR-tCG code (instruction-cache footprint on a cold launch,
 // register pressure)
-// BIG: some agent's preconditioner slab does not fit shared memory (streaming dense pass; RGD kernels only)
+// BIG: some agent's preconditioner slab does not fit shared memory (streaming dense pass)
 template <int R, int M, bool BIG = false>
 __global__ void __launch_bounds__(kThreads, 1)
     k_team_run(const __grid_constant__ TeamDev T, const __grid_constant__ RunArgs args) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         PROF(6)
       } else {
         // ---- RTR (a2)
-        const RtrOut ro = rtr_solve<R>(A, sel_local, P, gs, bs, Xs, inbox, ss, mbar, L, sm_slab, sm_red);
+        const RtrOut ro = rtr_solve<R, BIG>(A, sel_local, P, gs, bs, Xs, inbox, ss, mbar, L, sm_slab, sm_red);
         double v[1] = {0};
         phase_commit<R>(A, ro.x, accel, restart, gamma, v[0]);
         if (fab) __threadfence_system();

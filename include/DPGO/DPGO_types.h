@@ -13,6 +13,7 @@
 #ifndef DPGO_SHIM_TYPES_H
 #define DPGO_SHIM_TYPES_H
 
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstddef>
@@ -35,6 +36,59 @@ namespace DPGO {
 
 // the wrapper says `using namespace DPGO;` and then writes `vector<...>` unqualified (src/PGOAgentROS.cpp:288)
 using std::vector;
+
+// Storage of a Matrix: up to 32 coefficients (a lifted pose is r x (d+1) <= 8 x 4) live inside the object, anything
+// larger on the heap.  The wrapper builds and copies one Matrix per public pose per message (src/utils.cpp:100-110,
+// src/PGOAgentROS.cpp:1255-1284: millions per run); with heap storage those allocations were most of its host time.
+class MatrixStorage {
+ public:
+  static constexpr size_t kInline = 32;
+  MatrixStorage() = default;
+  MatrixStorage(size_t n, double v) : n_(n) {
+    if (n_ > kInline) heap_ = new double[n_];
+    std::fill(data(), data() + n_, v);
+  }
+  MatrixStorage(const MatrixStorage &o) : n_(o.n_) {
+    if (n_ > kInline) heap_ = new double[n_];
+    std::copy(o.data(), o.data() + n_, data());
+  }
+  MatrixStorage(MatrixStorage &&o) noexcept : n_(o.n_), heap_(o.heap_) {
+    if (!heap_) std::copy(o.buf_, o.buf_ + n_, buf_);
+    o.heap_ = nullptr;
+    o.n_ = 0;
+  }
+  MatrixStorage &operator=(const MatrixStorage &o) {
+    if (this != &o) {
+      MatrixStorage t(o);
+      swap(t);
+    }
+    return *this;
+  }
+  MatrixStorage &operator=(MatrixStorage &&o) noexcept {
+    if (this != &o) swap(o);
+    return *this;
+  }
+  ~MatrixStorage() { delete[] heap_; }
+  void swap(MatrixStorage &o) noexcept {
+    std::swap_ranges(buf_, buf_ + kInline, o.buf_);
+    std::swap(n_, o.n_);
+    std::swap(heap_, o.heap_);
+  }
+  size_t size() const { return n_; }
+  double *data() { return heap_ ? heap_ : buf_; }
+  const double *data() const { return heap_ ? heap_ : buf_; }
+  double &operator[](size_t i) { return data()[i]; }
+  double operator[](size_t i) const { return data()[i]; }
+  double *begin() { return data(); }
+  double *end() { return data() + n_; }
+  const double *begin() const { return data(); }
+  const double *end() const { return data() + n_; }
+
+ private:
+  size_t n_ = 0;
+  double *heap_ = nullptr;
+  double buf_[kInline];
+};
 
 class Matrix {
  public:
@@ -132,7 +186,7 @@ class Matrix {
 
  private:
   size_t r_ = 0, c_ = 0;
-  std::vector<double> a_;
+  MatrixStorage a_;
 };
 
 inline Matrix operator*(const Matrix &A, const Matrix &B) {  // src/PGOAgentROS.cpp:1419

@@ -264,6 +264,12 @@ int dpgo_b200_debug_dense_q(dpgo_b200_agent_t a, double *Q_from_csr, double *Q_f
  * CUDA-event time around the launch.  flush_l2: rewrite 512 MB first so that the graph comes from HBM. */
 int dpgo_b200_debug_edge_grad(dpgo_b200_agent_t a, const double *X, int flush_l2, double *f, double *rgrad,
                               double *kernel_ns, double *event_ns);
+/* the dense SPD inverse behind the preconditioner and the Chordal initialisation on its own
+ * (dpgo_ros_b200/csrc/dense_inverse.cu; stands where the reference factors Q + lambda I with CHOLMOD,
+ * QuadraticProblem's preconditioner / src/PGOAgentROS.cpp:1351 after every weight update): A is N x N column-major on the
+ * host, N a multiple of 32, only its lower triangle is read; P receives A^-1 (both triangles).  device_ms: CUDA-event
+ * time of the factorisation alone.  DPGO_B200_ERR_NUMERIC when A is not positive definite. */
+int dpgo_b200_debug_spd_inverse(int device, int N, const double *A, double *P, double *device_ms);
 /* wall-clock seconds spent inside each entry point of this library between two instants of
  * std::chrono::steady_clock (seconds since its epoch), one "name seconds calls" line per entry point; returns the
  * bytes the full report needs.  Lets a caller (the reference's wrapper in oracle/_ref) split the run time of a round

@@ -212,7 +212,8 @@ class Monitor {
       std::string name;
       double sec;
       long long calls;
-      while (is >> name >> sec >> calls) total += sec;
+      while (is >> name >> sec >> calls)
+        if (name[0] != '.') total += sec;  // '.name': a nested section of an entry point already counted
       f << (k ? ", " : "") << total;
     }
     f << "],\n  \"round_library_profile\": [";

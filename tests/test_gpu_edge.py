@@ -257,3 +257,43 @@ def test_neighbour_inactive_from_the_start():
     assert fresh[1].iterate(True) is False and fresh[1].iteration_number() == 1
     for a in agents + fresh:
         a.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the dense SPD inverse behind the preconditioner (dpgo_ros_b200/csrc/dense_inverse.cu: recursive blocked
+# Cholesky / triangular inverse / W^T W on the FP64 tensor path, 64 x 64 register-resident leaves)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [32, 64, 96, 100, 160, 448, 1248, 2016])
+def test_spd_inverse_matches_lapack(n):
+    """Random SPD matrices with condition number ~1e6 (the preconditioner's Q + 0.1 I is ill-conditioned too):
+    ||A P - I|| at the level numpy's own inverse reaches, symmetric output, every recursion shape: a single leaf, a
+    32-row leaf behind a 64-row one, sizes that are not multiples of the tile, both tile sizes of the product kernel."""
+    rng = np.random.default_rng(n)
+    U, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (U * np.logspace(0, 6, n)) @ U.T
+    A = 0.5 * (A + A.T)
+    P, ms = gpu.spd_inverse(A)
+    assert ms > 0.0
+    assert np.array_equal(P, P.T)
+    ref = np.linalg.inv(A)
+    res_gpu = np.linalg.norm(A @ P - np.eye(n)) / np.sqrt(n)
+    res_ref = np.linalg.norm(A @ ref - np.eye(n)) / np.sqrt(n)
+    assert res_gpu < 10 * res_ref + 1e-12, (res_gpu, res_ref)
+    assert rel(P, ref) < 1e-9, rel(P, ref)
+
+
+def test_spd_inverse_of_the_preconditioner_matrix():
+    """Q + 0.1 I of a sphere2500 robot (n = 312 poses, the bench workload): the inverse the preconditioner streams."""
+    pb = datasets.load_g2o_problem("sphere2500", 8)
+    oteam = orc.OracleTeam(pb, r=5, method=1)
+    Q, _ = oteam.dense_q(0)
+    A = Q + 0.1 * np.eye(Q.shape[0])
+    P, _ = gpu.spd_inverse(A)
+    assert rel(P, np.linalg.inv(A)) < 1e-10
+    assert np.linalg.norm(A @ P - np.eye(A.shape[0])) / np.sqrt(A.shape[0]) < 1e-10
+
+
+def test_spd_inverse_reports_an_indefinite_matrix():
+    A = np.diag(np.r_[np.full(70, 2.0), -1.0, np.full(25, 2.0)])
+    with pytest.raises(DpgoError):
+        gpu.spd_inverse(A)
