@@ -861,12 +861,20 @@ int dpgo_b200_debug_host_profile(dpgo_b200_agent_t h, double *out3, int reset) {
   if (reset) t->host_prof[0] = t->host_prof[1] = t->host_prof[2] = t->host_prof[3] = 0;
   API_END
 }
+// clock64 marks of CTA 0 along the RTR solve(s) of the last profiled launch (rtr_solve, team_run.cuh): 160 slots
+int dpgo_b200_debug_team_marks(dpgo_b200_team_t h, long long *out160) {
+  API_BEGIN
+  Team *t = TT(h);
+  if (t->dProf.n < 4096 + 256) fail(DPGO_B200_ERR_STATE, "debug_team_marks: run dpgo_b200_debug_team_profile first");
+  cuda_check(cudaMemcpy(out160, t->dProf.p + 4096 + 64, sizeof(long long) * 160, cudaMemcpyDeviceToHost), "D2H marks");
+  API_END
+}
 int dpgo_b200_debug_team_profile(dpgo_b200_team_t h, int iters, int cta, long long *out /* iters*16 */) {
   API_BEGIN
   Team *t = TT(h);
   t->prof_iters = iters;
   t->prof_cta = cta;
-  t->dProf.alloc((size_t)4096 + 64);
+  t->dProf.alloc((size_t)4096 + 256);
   t->team_dirty = true;
   t->run(iters, false);
   cuda_check(cudaMemcpy(out, t->dProf.p, sizeof(long long) * iters * 16, cudaMemcpyDeviceToHost), "D2H prof");

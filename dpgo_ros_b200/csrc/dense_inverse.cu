@@ -21,6 +21,8 @@
 // Round 1's version (32-wide right-looking tiles, one serial single-warp kernel
 // per diagonal block and per row of the triangular inverse) spent 86 % of its
 // time in those serial kernels (profiles/launches_r2_summary.csv).
+#include <atomic>
+
 #include "kernels.h"
 
 namespace dpgo {
@@ -332,20 +334,20 @@ __global__ void __launch_bounds__(256, (HM * HN >= 4) ? 1 : 2) k_gemm(GemmArgs g
     }
 }
 
-static long long g_inv_launches = 0;
-long long dense_inverse_launch_count() { return g_inv_launches; }
+static std::atomic<long long> g_inv_launches{0};  // (robots on several host threads build at the same time)
+long long dense_inverse_launch_count() { return g_inv_launches.load(); }
 
 template <int HM, int HN, bool AK, bool BK>
 static cudaError_t gemm_launch_t(const GemmArgs &g, cudaStream_t s) {
   constexpr size_t smem = sizeof(double) * 2 * GemmChunk<HM, HN>::value * ((64 * HM + kPad) + (64 * HN + kPad));
-  static bool attr_done[64] = {};  // (the attribute is per device)
+  static std::atomic<bool> attr_done[64];  // (the attribute is per device)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_done[dev].load()) {
     e = cudaFuncSetAttribute(k_gemm<HM, HN, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    if (dev >= 0 && dev < 64) attr_done[dev].store(true);
   }
   dim3 grid((g.M + 64 * HM - 1) / (64 * HM), (g.N + 64 * HN - 1) / (64 * HN));
   ++g_inv_launches;

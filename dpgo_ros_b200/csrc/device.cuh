@@ -421,8 +421,10 @@ __device__ __forceinline__ void grid_barrier(const GridSync &gs, BarState &bs) {
 // barrier, so it also orders global memory between phases.  Slots are double
 // buffered by parity: a fast CTA may start writing the next reduction's slots
 // while a slow one is still reading this one's.
+// sm: 64 doubles of shared memory (per-warp partials in [0, 8 K), totals in [48, 48 + K))
 template <int K>
 __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, double (&vals)[K], double *sm) {
+  static_assert(K <= kRed && 8 * K <= 48, "grid_reduce: scratch layout");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) vals[k] = wsum32(vals[k]);
@@ -448,13 +450,27 @@ __device__ __forceinline__ void grid_reduce(const GridSync &gs, BarState &bs, do
     if (v >= kBarPoison) bs.dead = 1;
   }
   __syncthreads();
-  // every warp sums the per-CTA partials itself, in the same order
+  // warp 0 sums the per-CTA partials (fixed order: lane-strided, then the butterfly) and hands the totals to the other
+  // warps through shared memory.  Until round 2 every warp read the slots itself: 1184 warps x 5 x K loads on the same
+  // 37 cache lines cost 1.0 us (K = 1) to 3.2 us (K = 4) on top of the barrier (tools/probe_rtr_phases.py).
+  if (warp == 0) {
+    double s[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double s = 0;
-    for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&slots[(size_t)b * kRed + k]);
-    vals[k] = wsum32(s);
+    for (int k = 0; k < K; ++k) s[k] = 0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) s[k] += __ldcg(&slots[(size_t)b * kRed + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) s[k] = wsum32(s[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) sm[48 + k] = s[k];
+    }
   }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) vals[k] = sm[48 + k];
   bs.parity ^= 1;
 }
 

@@ -65,6 +65,12 @@ Agent::~Agent() {
   if (team && team != own.get()) team->remove(this);
   if (own) own->agents.clear();
   team = nullptr;
+  if (pstream) {
+    cudaStreamSynchronize(pstream);
+    cudaStreamDestroy(pstream);
+    cudaEventDestroy(pevent);
+    cudaEventDestroy(pevent_in);
+  }
   free_pinned();
 }
 
@@ -349,6 +355,7 @@ void Agent::reset() {
 // ---- device structures --------------------------------------------------------
 void Agent::build_structure() {
   ProfSection prof_(".build_structure");
+  quiesce_preconditioner();
   // neighbour slots, ordered by (robot, frame)
   slot_of.clear();
   slot_key.clear();
@@ -658,6 +665,7 @@ AssembleDev Agent::assemble_view() const {
 // per-measurement "neighbour deactivated" flags -- never a matrix.
 void Agent::build_values() {
   ProfSection prof_(".build_values");
+  quiesce_preconditioner();
   if (lc_dirty) build_lc_list();
   if (weights_host_dirty) upload_weights();
   {
@@ -678,11 +686,17 @@ void Agent::build_values() {
 }
 
 void Agent::build_preconditioner() {
-  ProfSection prof_(".build_preconditioner");
+  start_preconditioner();
+  finish_preconditioner();
+}
+
+void Agent::start_preconditioner() {
+  if (precon_inflight) return;
   if (!need_preconditioner()) {
     precon_dirty = false;
     return;
   }
+  ProfSection prof_(".start_preconditioner");
   const size_t npad = roundup32((size_t)4 * n);
   dPinv.alloc(npad * npad, false);
   // the factorisation workspace stays allocated between rebuilds (a GNC weight update rebuilds the inverse of every
@@ -690,23 +704,51 @@ void Agent::build_preconditioner() {
   // cudaFree synchronises the device) -- except for agents whose workspace is measured in GB
   dPwork.alloc(npad * npad, false);
   dPinfo.alloc(1);
+  if (!pstream) {
+    cuda_check(cudaStreamCreateWithFlags(&pstream, cudaStreamNonBlocking), "streamCreate (preconditioner)");
+    cuda_check(cudaEventCreateWithFlags(&pevent, cudaEventDisableTiming), "eventCreate");
+    cuda_check(cudaEventCreateWithFlags(&pevent_in, cudaEventDisableTiming), "eventCreate");
+  }
+  // the block values were assembled on the legacy stream, which a non-blocking stream does not wait for by itself
+  cuda_check(cudaEventRecord(pevent_in, 0), "eventRecord");
+  cuda_check(cudaStreamWaitEvent(pstream, pevent_in, 0), "streamWaitEvent");
   cuda_check(launch_scatter_blocks(dPinv.p, npad, d_q_rowptr.p, d_q_col.p, d_q_val.p, n, P.precond_lambda,
-                                   (int)npad, 0),
+                                   (int)npad, pstream),
              "scatter_blocks");
-  cuda_check(spd_inverse(dPinv.p, dPwork.p, (int)npad, dPinfo.p, 0), "spd_inverse");
+  cuda_check(spd_inverse(dPinv.p, dPwork.p, (int)npad, dPinfo.p, pstream), "spd_inverse");
+  cuda_check(cudaEventRecord(pevent, pstream), "eventRecord");
+  precon_inflight = true;
+}
+
+void Agent::finish_preconditioner() {
+  if (!precon_inflight) return;
+  ProfSection prof_(".build_preconditioner");
+  cuda_check(cudaEventSynchronize(pevent), "dense inverse");
+  precon_inflight = false;
   int h_info = 0;
-  cuda_check(cudaMemcpy(&h_info, dPinfo.p, sizeof(int), cudaMemcpyDeviceToHost), "D2H info");
+  cuda_check(cudaMemcpyAsync(&h_info, dPinfo.p, sizeof(int), cudaMemcpyDeviceToHost, pstream), "D2H info");
+  cuda_check(cudaStreamSynchronize(pstream), "D2H info");
+  const size_t npad = roundup32((size_t)4 * n);
   if (npad * npad * sizeof(double) > ((size_t)1 << 30)) dPwork.release();
   if (h_info != 0) fail(DPGO_B200_ERR_NUMERIC, "preconditioner: Q + lambda I is not positive definite");
   precon_dirty = false;
 }
 
-void Agent::ensure_device() {
+void Agent::quiesce_preconditioner() {
+  if (!precon_inflight) return;
+  cudaEventSynchronize(pevent);
+  precon_inflight = false;  // precon_dirty stays set: whoever changes the values rebuilds
+}
+
+void Agent::ensure_device(bool wait_precond) {
   cuda_check(use_device(device), "cudaSetDevice");
   if (structure_dirty) build_structure();
   if (values_dirty) build_values();
   if (lc_dirty) build_lc_list();
-  if (precon_dirty) build_preconditioner();
+  if (precon_dirty) {
+    start_preconditioner();
+    if (wait_precond) finish_preconditioner();
+  }
   // (allocated here, not at the first launch: no cudaMalloc once kernels of several ranks wait for each other)
   if (has_edge_arrays() && need_preconditioner() && !P.acceleration && P.method == 1 && getenv("DPGO_B200_SYM_PRECOND"))
     ensure_sym_buffers();
@@ -772,7 +814,9 @@ bool Agent::iterate(bool do_opt) {
   }
   {
     ProfSection prof_(".prepare");
+    tm->defer_precond = !do_opt;   // iterate(false) never applies the preconditioner: its build keeps running behind it
     tm->prepare(false, true);
+    tm->defer_precond = false;
   }
   const bool accel = P.acceleration != 0;
   if (!do_opt && la_used < la_valid && lookahead_usable()) {
@@ -1176,10 +1220,12 @@ void Team::prepare(bool need_inbox, bool keep_lookahead) {
     }
   bool rewire = team_dirty;
   for (Agent *a : agents) {
-    if (a->structure_dirty || a->values_dirty || a->precon_dirty) rewire = true;
-    a->ensure_device();
+    if (a->structure_dirty || a->values_dirty || (a->precon_dirty && !a->precon_inflight)) rewire = true;
+    a->ensure_device(false);   // every agent's dense inverse is in flight before the first one is waited for
     if (a->wiring_dirty) rewire = true;
   }
+  if (!defer_precond)
+    for (Agent *a : agents) a->ensure_device(true);
   if (need_inbox) flush_inboxes();
   if (!rewire) return;
   layout_result();
@@ -1333,7 +1379,7 @@ void Team::fabric_init(int world, int rank) {
   }
   // no allocation (cudaMalloc / cudaFree synchronise the device) may happen once the ranks' kernels wait for each other
   dGammaTab.alloc((size_t)1 << 16, false);
-  if (dProf.n < 4096 + 64) dProf.alloc((size_t)4096 + 64);
+  if (dProf.n < 4096 + 256) dProf.alloc((size_t)4096 + 256);
   fab_world = world;
   fab_rank = rank;
   fab_seq = 0;

@@ -105,7 +105,16 @@ class Agent {
   double robust_weight(double residual) const;
 
   // ---- device structures
-  void ensure_device();   // allocate + build everything that is stale
+  // allocate + build everything that is stale.  wait_precond = false: the dense inverse is only STARTED (on the agent's
+  // own non-blocking stream) -- what iterate(false) needs, and what lets the inverses of several robots on one GPU
+  // run side by side instead of one after the other (each alone fills a fraction of the SMs)
+  void ensure_device(bool wait_precond = true);
+  void start_preconditioner();    // enqueue scatter + inverse on pstream, no host synchronisation
+  void finish_preconditioner();   // wait for it, read the pivot flag
+  void quiesce_preconditioner();  // a build in flight reads d_q_*: wait before those arrays change (result discarded)
+  cudaStream_t pstream = nullptr;
+  cudaEvent_t pevent = nullptr, pevent_in = nullptr;
+  bool precon_inflight = false;
   void build_structure(); // graph topology -> CSR / slots / publication lists
   void build_values();    // Q blocks, G blocks, LC arrays (weights) -> device
   void build_preconditioner();
@@ -352,6 +361,7 @@ class Team {
   static double next_gamma(double g, int N) { return (1.0 + std::sqrt(1.0 + 4.0 * N * N * g * g)) / (2.0 * N); }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool team_dirty = true;
+  bool defer_precond = false;  // prepare(): start the agents' dense inverses without waiting (Agent::iterate(false))
   int launches = 0;
   double host_prof[4] = {0, 0, 0, 0};  // diagnostics: seconds in the launch call, seconds until the result, launches
   DevBuf<long long> dProf;

@@ -974,12 +974,15 @@ __device__ __forceinline__ void phase_hess_dir(const AgentDev &A, const double *
 
 // z+ = Proj_Xbase( (r + alpha Hd) Pinv ) for the whole agent, and for the poses of this CTA's chunk:
 //   r+ = r + alpha Hd  (stored column- and row-major),  eta (+)= alpha delta,
-//   prr += |r+|^2,  pzr += <z+, r+>.
+//   prr += |r+|^2,  pzr += <z+, r+>,
+//   cand = Retr_Xbase(eta)  -- the candidate of the outer iteration, should tCG stop after this iteration (it does so
+//   on the residual test the reduction behind this phase feeds): a retraction per pose and inner iteration buys the
+//   barrier + retraction phase + barrier the outer iteration would otherwise spend after tCG.
 template <int R, bool BIG = false>
 __device__ __forceinline__ void phase_precond_cg(const AgentDev &A, int ai, const double *Xbase, const double *Rin,
                                                  const double *RinT, const double *Hd, const double *HdT,
                                                  double alpha, const double *Dcur, bool eta_zero, double *eta,
-                                                 double *Rout, double *RoutT, double *Zout, SlabState &ss,
+                                                 double *cand, double *Rout, double *RoutT, double *Zout, SlabState &ss,
                                                  uint64_t *mbar, double *slab, size_t slab_cap, double *zs,
                                                  double *red, double &prr, double &pzr) {
   const int n = A.n, r = rdim<R>(A);
@@ -1022,6 +1025,16 @@ __device__ __forceinline__ void phase_precond_cg(const AgentDev &A, int ai, cons
 #pragma unroll
         for (int c = 0; c < 4; ++c) RoutT[(size_t)a * n4 + 4 * j + c] = rr[c];
       }
+    }
+    {  // the same operations, in the same order, as phase_retract (team_run.cuh)
+      double xc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xc[c] = y[c] + e[c];
+      if (!valid) {
+        xc[0] = (a == 0); xc[1] = (a == 1); xc[2] = (a == 2);
+      }
+      qf_row(xc);
+      if (valid) st4(cand + off, r, a, act, xc);
     }
   }
 }

@@ -47,6 +47,44 @@ __device__ __forceinline__ void phase_axpy_eta(const AgentDev &A, double tau, bo
   }
 }
 
+// eta (+)= tau * dlt and cand = Retr_x1(eta) for the poses of this CTA's chunk -- the owner of eta in phase_precond_cg, so
+// no barrier separates the two (dlt comes from the Hessian-vector phase, behind a grid reduction)
+template <int RC>
+__device__ __forceinline__ void phase_axpy_eta_retract(const AgentDev &A, double tau, bool eta_zero, const double *dlt,
+                                                       double *eta, const double *X1, double *cand) {
+  const int a = threadIdx.x & 7, lg = threadIdx.x >> 3;
+  const int r = rdim<RC>(A);
+  int p0, np;
+  cta_pose_chunk(A.n, p0, np);
+  for (int k0 = 0; k0 < np; k0 += kGroupsPerCta) {
+    const int k = k0 + lg;
+    const bool valid = k < np;
+    const int j = p0 + (valid ? k : 0);
+    const bool act = valid && a < r;
+    const size_t off = (size_t)j * 4 * r;
+    double d[4], e[4], x[4];
+    ld4(dlt + off, r, a, act, d);
+    ld4(X1 + off, r, a, act, x);
+    if (eta_zero) {
+      e[0] = e[1] = e[2] = e[3] = 0.0;
+    } else {
+      ld4(eta + off, r, a, act, e);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) e[c] += tau * d[c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] += e[c];
+    if (!valid) {
+      x[0] = (a == 0); x[1] = (a == 1); x[2] = (a == 2);
+    }
+    qf_row(x);
+    if (valid) {
+      st4(eta + off, r, a, act, e);
+      st4(cand + off, r, a, act, x);
+    }
+  }
+}
+
 // out = Retr_x(eta)  (group-collective)
 template <int RC>
 __device__ __forceinline__ void phase_retract(const AgentDev &A, const double *X1, const double *eta, double *out) {
@@ -124,6 +162,9 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
                                             uint64_t *mbar, const SmemLayout &L, double *red, double *sm) {
   RtrOut out;
   out.outer = out.tcg = out.rej = 0;
+  int dseq = 0;  // diagnostics: clock64 of CTA 0 after every phase / reduction of the first solve of a profiled launch
+#define RMARK() do { if (g_dbg && threadIdx.x == 0 && blockIdx.x == 0 && dseq < 160) g_dbg[64 + dseq] = clock64(); ++dseq; } while (0)
+  RMARK();
   const double *x1 = Xs;
   double *cand = A.X2;
   double *Rg1 = A.Rg, *Rg1T = A.RgT, *S1 = A.S;
@@ -132,7 +173,9 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
   // gradient at the starting point (also assembles G)
   v[0] = v[1] = v[2] = v[3] = 0;
   phase_grad<R>(A, x1, inbox, true, S1, Rg1, Rg1T, nullptr, L.stage, v[0], v[1]);
+  RMARK();
   grid_reduce<2>(gs, bs, reinterpret_cast<double(&)[2]>(v), sm);
+  RMARK();
   double f1 = v[0], ngf = sqrt(v[1]);
   out.f_init = f1;
   out.gn_init = ngf;
@@ -152,7 +195,9 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
     const double norm_r0 = ngf;
     v[0] = 0;
     phase_precond<R, BIG>(A, ai, x1, rsrc, rsrcT, A.Z, A.dlt0, ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0]);
+    RMARK();
     grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
+    RMARK();
     double z_r = v[0], d_Pd = z_r, e_Pe = 0.0, e_Pd = 0.0;
     bool eta_zero = true;
     int status = 4;  // 0 negcurv, 1 exceeded, 2 lcon, 3 scon, 4 maxiter
@@ -161,26 +206,32 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
     double beta = 0.0;
     double *dcur = A.dlt0, *dprev = A.dlt1;   // delta_j (materialised by the Hessian-vector phase) / delta_{j-1}
     double *rnext = A.rv, *rnextT = A.rvT;    // ping-pong target of r+ (never the buffer other CTAs still read)
+    bool cand_pending = false;
     for (j = 0; j < P.rtr_tcg_iterations; ++j) {
       v[0] = 0;
       phase_hess_dir<R>(A, x1, S1, j == 0, A.Z, dprev, beta, dcur, A.Hd, A.HdT, L.stage, v[0]);
+      RMARK();
       grid_reduce<1>(gs, bs, reinterpret_cast<double(&)[1]>(v), sm);
+      RMARK();
       const double d_Hd = v[0];
       const double alpha = z_r / d_Hd;
       const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
       if (d_Hd <= 0 || e_Pe_new >= Delta * Delta) {
         const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
-        phase_axpy_eta<R>(A, tau, eta_zero, dcur, A.eta);
+        phase_axpy_eta_retract<R>(A, tau, eta_zero, dcur, A.eta, x1, cand);
         eta_zero = false;
         status = (d_Hd <= 0) ? 0 : 1;
+        cand_pending = true;   // written after the last grid-wide synchronisation
         break;
       }
       e_Pe = e_Pe_new;
       v[0] = v[1] = 0;
-      phase_precond_cg<R, BIG>(A, ai, x1, rsrc, rsrcT, A.Hd, A.HdT, alpha, dcur, eta_zero, A.eta, rnext, rnextT, A.Z, ss,
-                          mbar, L.slab, L.slab_cap, L.zs, red, v[0], v[1]);
+      phase_precond_cg<R, BIG>(A, ai, x1, rsrc, rsrcT, A.Hd, A.HdT, alpha, dcur, eta_zero, A.eta, cand, rnext, rnextT, A.Z,
+                               ss, mbar, L.slab, L.slab_cap, L.zs, red, v[0], v[1]);
       eta_zero = false;
+      RMARK();
       grid_reduce<2>(gs, bs, reinterpret_cast<double(&)[2]>(v), sm);
+      RMARK();
       rsrc = rnext;
       rsrcT = rnextT;
       rnext = (rnext == A.rv) ? A.rw : A.rv;
@@ -203,18 +254,27 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
       d_Pd = z_r + beta * beta * d_Pd;
     }
     out.tcg += min(j + 1, P.rtr_tcg_iterations);
+    // ---------------- candidate, model decrease, ratio
+    // eta and cand = Retr_x1(eta) are already there: phase_precond_cg keeps the candidate of "tCG stops here" up to date
+    // (complete behind its grid reduction), the boundary / negative-curvature exit writes both in one chunk-owned pass.
     if (eta_zero) {  // maxInner == 0: eta = 0
       phase_axpy_eta<R>(A, 0.0, true, A.dlt0, A.eta);
+      grid_barrier(gs, bs);
+      phase_retract<R>(A, x1, A.eta, cand);
+      cand_pending = true;
     }
-    grid_barrier(gs, bs);
-    // ---------------- candidate, model decrease, ratio
-    phase_retract<R>(A, x1, A.eta, cand);
-    grid_barrier(gs, bs);
+    RMARK();
+    if (cand_pending) grid_barrier(gs, bs);
+    RMARK();
     v[0] = v[1] = v[2] = v[3] = 0;
     phase_grad<R>(A, cand, inbox, false, S2, Rg2, Rg2T, nullptr, L.stage, v[0], v[1]);
+    RMARK();
     phase_hess<R>(A, x1, S1, A.eta, A.zeta, L.stage, v[2]);
+    RMARK();
     phase_dot<R>(A, A.eta, Rg1, v[3]);
+    RMARK();
     grid_reduce<4>(gs, bs, v, sm);
+    RMARK();
     const double f2 = v[0];
     const double rho = (f1 - f2) / (-(v[3] + 0.5 * v[2]));
     if (rho > 0.75) {
@@ -247,6 +307,7 @@ __device__ __forceinline__ RtrOut rtr_solve(const AgentDev &A, int ai, const Sol
       ++shrink;
     }
   }
+#undef RMARK
   out.x = x1;
   out.f_opt = f1;
   out.gn_opt = ngf;
