@@ -108,7 +108,11 @@ class Agent {
   // allocate + build everything that is stale.  wait_precond = false: the dense inverse is only STARTED (on the agent's
   // own non-blocking stream) -- what iterate(false) needs, and what lets the inverses of several robots on one GPU
   // run side by side instead of one after the other (each alone fills a fraction of the SMs)
-  void ensure_device(bool wait_precond = true);
+  // precond_mode 2: start + wait (default); 1: start only; 0: only reserve its buffers (Agent::warm)
+  void ensure_device(int precond_mode = 2);
+  void reserve_preconditioner();  // every allocation the build needs (device / pinned allocations serialise streams)
+  bool precond_reserved() const;
+  void warm();                    // allocate, assemble and wire everything except the dense inverse (at initialisation)
   void start_preconditioner();    // enqueue scatter + inverse on pstream, no host synchronisation
   void finish_preconditioner();   // wait for it, read the pivot flag
   void quiesce_preconditioner();  // a build in flight reads d_q_*: wait before those arrays change (result discarded)
@@ -361,7 +365,7 @@ class Team {
   static double next_gamma(double g, int N) { return (1.0 + std::sqrt(1.0 + 4.0 * N * N * g * g)) / (2.0 * N); }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool team_dirty = true;
-  bool defer_precond = false;  // prepare(): start the agents' dense inverses without waiting (Agent::iterate(false))
+  int precond_mode = 2;  // prepare(): 2 = dense inverses built and waited for, 1 = started, 0 = buffers only (warm, iterate(false))
   int launches = 0;
   double host_prof[4] = {0, 0, 0, 0};  // diagnostics: seconds in the launch call, seconds until the result, launches
   DevBuf<long long> dProf;
