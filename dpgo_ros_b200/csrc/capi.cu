@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/dpgo_b200.h.  Every entry point
 // converts exceptions into negative error codes; nothing here computes on the
 // CPU -- a missing / unusable CUDA device surfaces as DPGO_B200_ERR_CUDA.
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -39,11 +40,19 @@ ApiClock &api_clock() {
 inline double api_now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// OFF until a caller asks for it (dpgo_b200_debug_api_profile with reset = 2): every entry point would otherwise pay two
+// clock reads and a process-wide mutex -- with one thread per robot (the per-robot e2e path: ~190 calls per global
+// iteration from 8 threads) that lock is contended on the critical path.
+std::atomic<bool> g_api_clock_on{false};
 struct ApiTimer {
   const char *name;
   double t0;
-  explicit ApiTimer(const char *n) : name(n), t0(api_now()) {}
+  bool on;
+  explicit ApiTimer(const char *n) : name(n), t0(0), on(g_api_clock_on.load(std::memory_order_relaxed)) {
+    if (on) t0 = api_now();
+  }
   ~ApiTimer() {
+    if (!on) return;
     const double t1 = api_now();
     ApiClock &c = api_clock();
     std::lock_guard<std::mutex> lock(c.mu);
@@ -53,8 +62,9 @@ struct ApiTimer {
 }  // namespace
 
 namespace dpgo {
-ProfSection::ProfSection(const char *n) : name(n), t0(api_now()) {}
+ProfSection::ProfSection(const char *n) : name(n), t0(g_api_clock_on.load(std::memory_order_relaxed) ? api_now() : -1.0) {}
 ProfSection::~ProfSection() {
+  if (t0 < 0) return;
   const double t1 = api_now();
   ApiClock &c = api_clock();
   std::lock_guard<std::mutex> lock(c.mu);
@@ -764,6 +774,7 @@ int dpgo_b200_debug_spd_inverse(int device, int N, const double *Ah, double *Ph,
 // "name seconds calls\n" per entry point, restricted to the part of every call that fell inside [t_begin, t_end]
 // (std::chrono::steady_clock seconds); returns the number of bytes the full report needs
 int dpgo_b200_debug_api_profile(double t_begin, double t_end, char *buf, int cap, int reset) {
+  if (reset == 2) g_api_clock_on.store(true);
   ApiClock &c = api_clock();
   std::lock_guard<std::mutex> lock(c.mu);
   std::map<std::string, std::pair<double, long long>> acc;

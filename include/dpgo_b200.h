@@ -273,7 +273,8 @@ int dpgo_b200_debug_spd_inverse(int device, int N, const double *A, double *P, d
 /* wall-clock seconds spent inside each entry point of this library between two instants of
  * std::chrono::steady_clock (seconds since its epoch), one "name seconds calls" line per entry point; returns the
  * bytes the full report needs.  Lets a caller (the reference's wrapper in oracle/_ref) split the run time of a round
- * into library time and its own host code.  reset != 0 forgets the recorded calls afterwards. */
+ * into library time and its own host code.  reset != 0 forgets the recorded calls afterwards.  The clock is OFF until
+ * one call passes reset = 2 (which also clears it): entry points pay nothing for it otherwise. */
 int dpgo_b200_debug_api_profile(double t_begin, double t_end, char *buf, int cap, int reset);
 
 #ifdef __cplusplus

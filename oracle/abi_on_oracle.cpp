@@ -12,6 +12,7 @@
 // package never see it; the product has no CPU path.
 // =============================================================================
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -51,11 +52,16 @@ ApiClock &api_clock() {
 inline double api_now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+std::atomic<bool> g_api_clock_on{false};  // switched on by dpgo_b200_debug_api_profile(..., reset = 2), as in the CUDA library
 struct ApiTimer {
   const char *name;
   double t0;
-  explicit ApiTimer(const char *n) : name(n), t0(api_now()) {}
+  bool on;
+  explicit ApiTimer(const char *n) : name(n), t0(0), on(g_api_clock_on.load(std::memory_order_relaxed)) {
+    if (on) t0 = api_now();
+  }
   ~ApiTimer() {
+    if (!on) return;
     const double t1 = api_now();
     ApiClock &c = api_clock();
     std::lock_guard<std::mutex> lock(c.mu);
@@ -64,6 +70,7 @@ struct ApiTimer {
 };
 }  // namespace
 extern "C" int dpgo_b200_debug_api_profile(double t_begin, double t_end, char *buf, int cap, int reset) {
+  if (reset == 2) g_api_clock_on.store(true);
   ApiClock &c = api_clock();
   std::lock_guard<std::mutex> lock(c.mu);
   std::map<std::string, std::pair<double, long long>> acc;

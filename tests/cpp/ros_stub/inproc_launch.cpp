@@ -273,6 +273,7 @@ class Monitor {
 }  // namespace
 
 int main(int argc, char **argv) {
+  dpgo_b200_debug_api_profile(0, 0, nullptr, 0, 2);  // switch the library's per-entry-point clock on (off by default)
   int robots = 0, rounds = 1;
   std::string g2o, measurements_dir, out = "inproc_result.json", preset;
   double max_sim_seconds = 3600, run_sim_seconds = -1, disconnect_at = -1;
