@@ -123,6 +123,46 @@ def test_edge_record_gradient_matches_oracle():
         a.close()
 
 
+def test_config5_full_size_gradient_matches_oracle():
+    """BASELINE config 5 at its full size, on the generator SURVEY 8(d) specifies (seeded random walk, 100 000 poses,
+    1 000 000 edges, 90 % of the loop closures within 2000 poses + 10 % uniform, odometry guess; robot 0 of 8: 12 500
+    poses, ~136 000 edges): f and the Riemannian gradient of the edge-record kernel against the oracle's at the initial
+    guess and at a random point of the manifold.  (No solve on this instance: the oracle's sparse Cholesky of this robot's
+    Q + 0.1 I does not finish in 6 minutes -- the far loop closures fill it in -- so the iterate comparison at this size
+    runs on the lattice generator, bench.py hbm_bound_regime.)"""
+    pb = datasets.make_random_walk_problem(100000, 1000000, 8, seed=0)
+    kw = dict(r=5, method=1, rgd_stepsize=0.2, rgd_use_preconditioner=0, acceleration=0, rel_change_tol=0.0,
+              max_num_iters=10 ** 9, num_robots=8)
+    oteam = orc.OracleTeam(pb, **{k: v for k, v in kw.items() if k != "num_robots"})
+    oteam.exchange_all()
+    P = gpu.make_params(**kw)
+    yl = datasets.fixed_lifting_matrix(P.r)
+    eye = np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1)
+    a = gpu.PGOAgent(0, P, 0)
+    m = pb.robot_measurements(0)
+    a.addMeasurements(m)
+    a.setLiftingMatrix(yl)
+    a.initialize(pb.T_init[0])
+    a.initializeInGlobalFrame(eye)
+    need = {}
+    for e in np.nonzero(m.r1 != m.r2)[0]:
+        o, f = (int(m.r2[e]), int(m.p2[e])) if int(m.r1[e]) == 0 else (int(m.r1[e]), int(m.p1[e]))
+        need.setdefault(o, set()).add(f)
+    for o, frames in need.items():
+        fr = np.array(sorted(frames), dtype=np.int32)
+        a.updateNeighborPoses(o, fr, np.ascontiguousarray(np.einsum("ak,nkc->nca", yl, pb.T_init[o][fr])), False)
+    X0 = oteam.get_x(0)
+    assert rel(a.getX(), X0) < 1e-14
+    rng = np.random.default_rng(5)
+    for X in (X0, orc.manifold_project(X0 + 0.05 * rng.standard_normal(X0.shape))):
+        f, rg, kns, _ = a.edgeGrad(X)
+        fo, _, rgo = oteam.eval(0, X)
+        assert abs(f - fo) <= 1e-11 * abs(fo), (f, fo)
+        assert rel(rg, rgo) < 1e-11, rel(rg, rgo)
+        assert kns > 0
+    a.close()
+
+
 def test_symmetric_pass_keeps_parity():
     """sym_precond.cu (opt-in, DPGO_B200_SYM_PRECOND=1): one triangle of the dense inverse per step, per-tile partial
     sums added in tile order.  Same iterates as the oracle's sparse solve, and bit-identical from run to run although the

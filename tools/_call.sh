@@ -1,5 +1,10 @@
-mkdir -p gpurun_out/c37
-timeout 120 python tools/probe_rtr_phases.py > gpurun_out/c37/rtr_phases.txt 2>&1; tail -6 gpurun_out/c37/rtr_phases.txt
-timeout 120 python tools/probe_rtr.py > gpurun_out/c37/probe_rtr.txt 2>&1; grep "per iterate" gpurun_out/c37/probe_rtr.txt
-timeout 300 python tools/bench_config5.py > gpurun_out/c37/config5.json 2> gpurun_out/c37/config5.err; tail -c 900 gpurun_out/c37/config5.json
-timeout 800 python -m pytest tests -m gpu -q -x > gpurun_out/c37/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/c37/pytest.log
+mkdir -p gpurun_out/c39
+timeout 300 python -m pytest tests/test_gpu_parallel.py -m gpu -q -k "config5_full_size or edge_record" 2>&1 | tail -5
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/c39/bench_n1_s20.json 2> gpurun_out/c39/bench_n1_s20.err; echo "bench rc=$?"; tail -3 gpurun_out/c39/bench_n1_s20.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/c39/bench_n1_s20.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, "e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"]["value"])
+print(json.dumps(d["hbm_bound_regime_8d_generator"])[:2500])
+h = d["hbm_bound_regime"]; print(h["ms_per_iterate"], h["preconditioner_build_s"], h["frac"], h.get("cpu_beside"))
+PY
