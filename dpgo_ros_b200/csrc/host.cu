@@ -706,19 +706,21 @@ void Agent::build_preconditioner() {
   finish_preconditioner();
 }
 
+// (what the kernels are wired to is dPinv: the workspace never appears in a device view)
 bool Agent::precond_reserved() const {
   const size_t npad = roundup32((size_t)4 * n);
-  return !need_preconditioner() || (dPinv.n == npad * npad && dPwork.n == npad * npad && pstream != nullptr);
+  return !need_preconditioner() || dPinv.n == npad * npad;
 }
 
-void Agent::reserve_preconditioner() {
+void Agent::reserve_preconditioner(bool with_workspace) {
   if (!need_preconditioner()) return;
   const size_t npad = roundup32((size_t)4 * n);
   dPinv.alloc(npad * npad, false);
   // the factorisation workspace stays allocated between rebuilds (a GNC weight update rebuilds the inverse of every
   // robot: cudaMalloc / cudaFree of a few MB each time cost more than the kernels on the tunnels robots, and
-  // cudaFree synchronises the device) -- except for agents whose workspace is measured in GB
-  dPwork.alloc(npad * npad, false);
+  // cudaFree synchronises the device) -- except for agents whose workspace is measured in GB: those allocate it when
+  // the build starts and give it back when it ends
+  if (with_workspace || npad * npad * sizeof(double) <= ((size_t)1 << 30)) dPwork.alloc(npad * npad, false);
   dPinfo.alloc(1);
   if (!pstream) {
     cuda_check(cudaStreamCreateWithFlags(&pstream, cudaStreamNonBlocking), "streamCreate (preconditioner)");
@@ -735,7 +737,7 @@ void Agent::start_preconditioner() {
   }
   ProfSection prof_(".start_preconditioner");
   const size_t npad = roundup32((size_t)4 * n);
-  reserve_preconditioner();
+  reserve_preconditioner(true);
   // the block values were assembled on the legacy stream, which a non-blocking stream does not wait for by itself
   cuda_check(cudaEventRecord(pevent_in, 0), "eventRecord");
   cuda_check(cudaStreamWaitEvent(pstream, pevent_in, 0), "streamWaitEvent");
@@ -774,7 +776,7 @@ void Agent::ensure_device(int precond_mode) {
   if (lc_dirty) build_lc_list();
   if (precon_dirty) {
     if (precond_mode == 0) {
-      reserve_preconditioner();
+      reserve_preconditioner(false);
     } else {
       start_preconditioner();
       if (precond_mode == 2) finish_preconditioner();

@@ -110,7 +110,7 @@ class Agent {
   // run side by side instead of one after the other (each alone fills a fraction of the SMs)
   // precond_mode 2: start + wait (default); 1: start only; 0: only reserve its buffers (Agent::warm)
   void ensure_device(int precond_mode = 2);
-  void reserve_preconditioner();  // every allocation the build needs (device / pinned allocations serialise streams)
+  void reserve_preconditioner(bool with_workspace);  // the allocations of the build (they serialise streams)
   bool precond_reserved() const;
   void warm();                    // allocate, assemble and wire everything except the dense inverse (at initialisation)
   void start_preconditioner();    // enqueue scatter + inverse on pstream, no host synchronisation
