@@ -1,10 +1,5 @@
-mkdir -p gpurun_out/c39
-timeout 300 python -m pytest tests/test_gpu_parallel.py -m gpu -q -k "config5_full_size or edge_record" 2>&1 | tail -5
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/c39/bench_n1_s20.json 2> gpurun_out/c39/bench_n1_s20.err; echo "bench rc=$?"; tail -3 gpurun_out/c39/bench_n1_s20.err
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/c39/bench_n1_s20.json").read().strip().splitlines()[-1])
-print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, "e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"]["value"])
-print(json.dumps(d["hbm_bound_regime_8d_generator"])[:2500])
-h = d["hbm_bound_regime"]; print(h["ms_per_iterate"], h["preconditioner_build_s"], h["frac"], h.get("cpu_beside"))
-PY
+mkdir -p gpurun_out/c40
+REPS=1 timeout 300 compute-sanitizer --tool memcheck ./tools/check_dense_inverse 32 96 448 1248 > gpurun_out/c40/memcheck_inverse.txt 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/c40/memcheck_inverse.txt
+REPS=1 timeout 400 compute-sanitizer --tool racecheck ./tools/check_dense_inverse 96 448 > gpurun_out/c40/racecheck_inverse.txt 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/c40/racecheck_inverse.txt
+timeout 500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -q -k "rtr_team or rtr_single or rtr_accelerated_matches" > gpurun_out/c40/memcheck_rtr.txt 2>&1; echo "memcheck rtr rc=$?"; tail -5 gpurun_out/c40/memcheck_rtr.txt
+REPS=1 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_leaf -s 12 -c 1 -o gpurun_out/c40/leaf2 ./tools/check_dense_inverse 1248 > /dev/null 2>&1; echo "ncu leaf rc=$?"
