@@ -982,7 +982,7 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
     std::memcpy(inbox + (size_t)ns->second.first * 4 * r, poses, pb * count);
     std::memset(valid.data() + ns->second.first, 1, count);
     inbox_dirty = true;
-    maybe_arm();
+    maybe_arm(nbr, aux);
     return;
   }
   for (int k = 0; k < count; ++k) {
@@ -1000,14 +1000,23 @@ void Agent::update_neighbor_poses(int nbr, bool aux, const int *frames, const do
 // everything it can do without the neighbours' latest poses in front (lookahead commit, Nesterov phase, TMA prefetch
 // of the preconditioner slab), and waits for the doorbell.  Nothing else may want this GPU in between: any other
 // device-touching call disarms first, and a kernel nobody rings within the time-out leaves by itself.
-void Agent::maybe_arm() {
+void Agent::maybe_arm(int from_nbr, bool from_aux) {
   const bool disabled = getenv("DPGO_B200_NO_ARM") != nullptr;
   if (disabled || armed || !lookahead_usable() || P.method != 1 || P.cost_type != 0) return;
   // the waiting kernel occupies the whole device: only when this robot has it to itself (one robot per GPU, the
   // deployment of BASELINE config 2 at 8 GPUs).  With several robots on one device the kernel of whoever holds the
   // UPDATE token would queue behind it (measured: the 300 us time-out every iteration).
   static const bool shared_ok = getenv("DPGO_B200_ARM_SHARED") != nullptr;   // tests: exercise go / expiry / abort on one GPU
-  if (!shared_ok && g_agents_on_device[device & 63].load() != 1) return;
+  if (!shared_ok && g_agents_on_device[device & 63].load() != 1) {
+    // Several robots share this GPU.  The one moment at which nobody else wants it before this robot's own
+    // iterate(true): the robot that holds the UPDATE token of the current iteration -- RoundRobin: my predecessor --
+    // has just delivered the poses its solve produced (its auxiliary poses come last, src/PGOAgentROS.cpp:662-690), and
+    // every other robot answers its iterate(false) of the next iteration from its lookahead without a launch.  Arming
+    // on any earlier delivery put this kernel in front of the predecessor's solve (the 300 us time-out every iteration).
+    static const bool multi_ok = getenv("DPGO_B200_NO_ARM_MULTI") == nullptr;
+    const int N = P.num_robots;
+    if (!multi_ok || N < 2 || !from_aux || from_nbr != (id + N - 1) % N || iter % N != id) return;
+  }
   if (la_valid <= 0 || la_used != la_valid) return;
   if (structure_dirty || values_dirty || precon_dirty || wiring_dirty || lc_dirty || team->team_dirty) return;
   if (arm_backoff > 0) return;

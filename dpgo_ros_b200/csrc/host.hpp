@@ -205,7 +205,9 @@ class Agent {
   // the doorbell, so that call costs neither the launch latency nor the Nesterov phase
   bool armed = false;
   int arm_backoff = 0;          // iterate(true) calls to sit out after an armed launch expired or was aborted
-  void maybe_arm();             // called when neighbour poses arrive and the next call is expected to be iterate(true)
+  // called when neighbour poses arrive and the next call is expected to be iterate(true); from_nbr / from_aux: the
+  // delivery that triggered it (several robots per device arm on their RoundRobin predecessor's auxiliary poses only)
+  void maybe_arm(int from_nbr = -1, bool from_aux = false);
   void disarm();                // ring "abort", wait for the kernel to leave, take over the committed state
   bool stats_pending = false;  // fOpt / gradNormOpt of the last iterate(true) not evaluated yet
   void finish_opt_stats();

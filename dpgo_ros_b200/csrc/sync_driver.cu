@@ -205,41 +205,45 @@ extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const in
 extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int steps, int accelerated,
                                          double *seconds, long long *payload_bytes, int *terminated_at) {
   if (!agents || N < 1 || steps < 0) return DPGO_B200_ERR_INVALID;
-  std::vector<int> r(N);
-  // outgoing messages per robot
-  std::vector<std::vector<Msg>> out(N);
-  std::vector<std::vector<Msg *>> in(N);
-  for (int a = 0; a < N; ++a) {
-    const int k = dpgo_b200_num_neighbors(agents[a]);
-    std::vector<int> nb(k > 0 ? k : 1);
-    if (k > 0 && dpgo_b200_get_neighbors(agents[a], nb.data(), k) != 0) return DPGO_B200_ERR_INVALID;
-    out[a].resize(k);
-    for (int i = 0; i < k; ++i) {
-      Msg &m = out[a][i];
-      m.from = a;
-      m.to = nb[i];
-      const int cnt = dpgo_b200_num_shared_poses(agents[a], nb[i]);
-      m.frames.resize(cnt > 0 ? cnt : 1);
-      m.reg.resize((size_t)(cnt > 0 ? cnt : 1) * 4 * 8);
-      m.aux.resize((size_t)(cnt > 0 ? cnt : 1) * 4 * 8);
+  // outgoing messages per robot, double-buffered by the parity of the step: a robot may already pack the next
+  // iteration's poses while a slower one still reads this iteration's (messages in flight, as over TCPROS) -- which
+  // is what lets the step run on three barriers instead of four
+  std::vector<std::vector<Msg>> out[2];
+  std::vector<std::vector<Msg *>> in[2];
+  for (int p = 0; p < 2; ++p) {
+    out[p].resize(N);
+    in[p].resize(N);
+    for (int a = 0; a < N; ++a) {
+      const int k = dpgo_b200_num_neighbors(agents[a]);
+      std::vector<int> nb(k > 0 ? k : 1);
+      if (k > 0 && dpgo_b200_get_neighbors(agents[a], nb.data(), k) != 0) return DPGO_B200_ERR_INVALID;
+      out[p][a].resize(k);
+      for (int i = 0; i < k; ++i) {
+        Msg &m = out[p][a][i];
+        m.from = a;
+        m.to = nb[i];
+        const int cnt = dpgo_b200_num_shared_poses(agents[a], nb[i]);
+        m.frames.resize(cnt > 0 ? cnt : 1);
+        m.reg.resize((size_t)(cnt > 0 ? cnt : 1) * 4 * 8);
+        m.aux.resize((size_t)(cnt > 0 ? cnt : 1) * 4 * 8);
+      }
     }
+    for (int a = 0; a < N; ++a)
+      for (auto &m : out[p][a])
+        if (m.to >= 0 && m.to < N) in[p][m.to].push_back(&m);
   }
-  for (int a = 0; a < N; ++a)
-    for (auto &m : out[a])
-      if (m.to >= 0 && m.to < N) in[m.to].push_back(&m);
 
   std::atomic<int> err{0};
   std::atomic<long long> bytes{0};
   std::atomic<int> term{-1};
   SpinBarrier bar(N);
   const int start_iter = dpgo_b200_iteration_number(agents[0]);
-  dpgo_b200_status st0;
-  dpgo_b200_get_status(agents[0], &st0);
-  const int pose_doubles_hint = 0;
-  (void)pose_doubles_hint;
+  // publishStatus: every robot posts its own, the leader reads them (by step parity, like the messages: without
+  // acceleration a step has a single barrier, and a fast robot posts its next status while the leader still reads)
+  std::vector<dpgo_b200_status> status_board[2] = {std::vector<dpgo_b200_status>(N), std::vector<dpgo_b200_status>(N)};
 
-  auto pack = [&](int a) {
-    for (auto &m : out[a]) {
+  auto pack = [&](int a, int p) {
+    for (auto &m : out[p][a]) {
       int cnt = 0;
       int rc = dpgo_b200_get_shared_pose_dict(agents[a], m.to, 0, m.frames.data(), m.reg.data(),
                                               (int)m.frames.size(), &cnt);
@@ -252,8 +256,8 @@ extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int s
       }
     }
   };
-  auto deliver = [&](int b, int only_from, bool except) {
-    for (Msg *m : in[b]) {
+  auto deliver = [&](int b, int only_from, bool except, int p) {
+    for (Msg *m : in[p][b]) {
       if (except ? (m->from == only_from) : (m->from != only_from)) continue;
       int rc = dpgo_b200_update_neighbor_poses(agents[b], m->from, 0, m->frames.data(), m->reg.data(), m->count);
       if (rc) err.store(rc);
@@ -273,16 +277,17 @@ extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int s
   auto worker = [&](int a) {
     for (int s = 0; s < steps; ++s) {
       const int sel = (start_iter + s) % N;
+      const int p = s & 1;
       auto t = now();
       if (accelerated) {
         if (a != sel) {
           if (dpgo_b200_iterate(agents[a], 0)) err.store(-1);
           if (prof && a == (sel + 1) % N) tp[0] += since(t);
-          pack(a);
+          pack(a, p);
         }
         bar.wait();
         if (prof && a == 0) { tp[1] += since(t); t = now(); }
-        deliver(a, sel, /*except=*/true);  // everything except the selected robot's (not sent yet)
+        deliver(a, sel, /*except=*/true, p);  // everything except the selected robot's (not sent yet)
         bar.wait();
         if (prof && a == 0) { tp[2] += since(t); t = now(); }
       } else if (a != sel) {
@@ -292,30 +297,23 @@ extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int s
         auto t2 = now();
         if (dpgo_b200_iterate(agents[a], 1)) err.store(-1);
         if (prof) tp[3] += since(t2);
-        pack(a);
+        pack(a, p);
       }
+      dpgo_b200_get_status(agents[a], &status_board[p][a]);   // publishStatus
       bar.wait();
       if (prof && a == 0) { tp[4] += since(t); t = now(); }
-      deliver(a, sel, /*except=*/false);  // only the selected robot's poses
+      deliver(a, sel, /*except=*/false, p);  // only the selected robot's poses
       if (a == 0) {
-        // publishStatus: the leader hears everyone; shouldTerminate on the leader's own turn
-        for (int b = 1; b < N; ++b) {
-          dpgo_b200_status st;
-          dpgo_b200_get_status(agents[b], &st);
-          dpgo_b200_set_neighbor_status(agents[0], &st);
-        }
+        // the leader hears everyone; shouldTerminate on the leader's own turn
+        for (int b = 1; b < N; ++b) dpgo_b200_set_neighbor_status(agents[0], &status_board[p][b]);
         if (sel == 0 && term.load() < 0 && dpgo_b200_should_terminate(agents[0]) == 1) term.store(s + 1);
       }
-      bar.wait();
+      // no barrier here: the next step's first one orders this step's deliveries in front of everything that depends
+      // on them (a robot iterates and delivers to itself on its own thread; messages are double-buffered; a status
+      // is posted again only behind two barriers of the next step)
       if (err.load()) return;
     }
   };
-
-  // payload accounting: poses that crossed the host per step
-  long long per_cycle = 0;
-  for (int a = 0; a < N; ++a)
-    for (auto &m : out[a]) per_cycle += (long long)m.frames.size();
-  (void)per_cycle;
 
   const auto t0 = std::chrono::high_resolution_clock::now();
   std::vector<std::thread> th;

@@ -1,7 +1,3 @@
-mkdir -p gpurun_out/c41
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/c41/bench_n8_s20.json 2> gpurun_out/c41/bench_n8_s20.err; echo "bench n8 rc=$?"
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/c41/bench_n8_s20.json").read().strip().splitlines()[-1])
-print({k: d.get(k) for k in ("value", "ms_per_step", "n_gpus", "bit_identical_to_single_team", "gpu_launches")}, "e2e", d["e2e"]["value"], "async", d.get("async_mode", {}).get("ticks_per_s"))
-PY
+mkdir -p gpurun_out/c43
+timeout 400 python tools/probe_e2e.py > gpurun_out/c43/probe_e2e.txt 2>&1; cat gpurun_out/c43/probe_e2e.txt | tail -24
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "sync_driver or armed or standalone" 2>&1 | tail -3
