@@ -59,19 +59,26 @@ struct ShmHeader {
   std::atomic<unsigned> gen;
   std::atomic<int> err, term;
   int cap;  // poses per mailbox
-  dpgo_b200_status status[kShmMaxRobots];
+  dpgo_b200_status status[2][kShmMaxRobots];   // by step parity, like the mailboxes
 };
 struct ShmView {
   ShmHeader *h;
   unsigned char *boxes;
   size_t box_bytes;
   int N;
-  // mailbox a -> b: [int count | int frames[cap] | double reg[cap * 32] | double aux[cap * 32]]
-  unsigned char *box(int a, int b) const { return boxes + ((size_t)a * N + b) * box_bytes; }
+  // mailbox a -> b of step parity p: [int count | int frames[cap] | double reg[cap * 32] | double aux[cap * 32]]
+  // (two sets: a robot may already post the next iteration's poses while a slower one still reads this iteration's)
+  int p = 0;
+  unsigned char *box(int a, int b) const { return boxes + (((size_t)p * N + a) * N + b) * box_bytes; }
   int *count(int a, int b) const { return reinterpret_cast<int *>(box(a, b)); }
   int *frames(int a, int b) const { return reinterpret_cast<int *>(box(a, b)) + 2; }
   double *reg(int a, int b) const { return reinterpret_cast<double *>(box(a, b) + 8 + ((size_t)h->cap * 4 + 7) / 8 * 8); }
   double *aux(int a, int b) const { return reg(a, b) + (size_t)h->cap * kShmPoseDoubles; }
+  ShmView at(int parity) const {
+    ShmView v = *this;
+    v.p = parity;
+    return v;
+  }
 };
 size_t shm_box_bytes(int cap) { return 8 + ((size_t)cap * 4 + 7) / 8 * 8 + (size_t)2 * cap * kShmPoseDoubles * sizeof(double); }
 
@@ -90,7 +97,7 @@ void shm_barrier(ShmHeader *h, int n) {
 
 #pragma GCC visibility push(default)
 extern "C" size_t dpgo_b200_sync_driver_shm_bytes(int num_robots, int max_shared_poses) {
-  return sizeof(ShmHeader) + (size_t)num_robots * num_robots * shm_box_bytes(max_shared_poses);
+  return sizeof(ShmHeader) + (size_t)2 * num_robots * num_robots * shm_box_bytes(max_shared_poses);
 }
 
 extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const int *robot_ids, int num_local,
@@ -115,7 +122,7 @@ extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const in
   }
   ShmHeader *H = V.h;
   auto fail = [&](int rc) { H->err.store(rc); };
-  auto pack = [&](int i) {  // publishPublicPoses of local robot i
+  auto pack = [&](int i, const ShmView &V) {  // publishPublicPoses of local robot i
     const int a = robot_ids[i];
     for (int b : nbrs[i]) {
       int cnt = 0;
@@ -128,7 +135,7 @@ extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const in
       }
     }
   };
-  auto deliver = [&](int i, int sel, bool except) {  // publicPosesCallback of local robot i
+  auto deliver = [&](int i, int sel, bool except, const ShmView &V) {  // publicPosesCallback of local robot i
     const int b = robot_ids[i];
     for (int a : nbrs[i]) {
       if (except ? (a == sel) : (a != sel)) continue;
@@ -146,9 +153,9 @@ extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const in
     // INITIALIZE (:1099-1101): everybody publishes once, everybody hears everybody
     std::vector<std::thread> th0;
     auto once = [&](int i) {
-      pack(i);
+      pack(i, V);
       shm_barrier(H, N);
-      deliver(i, -1, /*except=*/true);
+      deliver(i, -1, /*except=*/true, V);
       shm_barrier(H, N);
     };
     for (int i = 1; i < num_local; ++i) th0.emplace_back(once, i);
@@ -162,31 +169,35 @@ extern "C" int dpgo_b200_sync_driver_run_shm(dpgo_b200_agent_t *agents, const in
     const int a = robot_ids[i];
     for (int s = 0; s < steps; ++s) {
       const int sel = (start_iter + s) % N;
+      const int p = s & 1;
+      const ShmView Vp = V.at(p);
       if (accelerated) {
         if (a != sel) {
           if (dpgo_b200_iterate(agents[i], 0)) fail(-1);
-          pack(i);
+          pack(i, Vp);
         }
         shm_barrier(H, N);
-        deliver(i, sel, /*except=*/true);
+        deliver(i, sel, /*except=*/true, Vp);
         shm_barrier(H, N);
       } else if (a != sel) {
         if (dpgo_b200_iterate(agents[i], 0)) fail(-1);
       }
       if (a == sel) {
         if (dpgo_b200_iterate(agents[i], 1)) fail(-1);
-        pack(i);
+        pack(i, Vp);
       }
-      dpgo_b200_get_status(agents[i], &H->status[a]);  // publishStatus
+      dpgo_b200_get_status(agents[i], &H->status[p][a]);  // publishStatus
       shm_barrier(H, N);
-      deliver(i, sel, /*except=*/false);
+      deliver(i, sel, /*except=*/false, Vp);
       if (a == 0) {
-        for (int b = 1; b < N; ++b) dpgo_b200_set_neighbor_status(agents[i], &H->status[b]);
+        for (int b = 1; b < N; ++b) dpgo_b200_set_neighbor_status(agents[i], &H->status[p][b]);
         if (sel == 0 && H->term.load() < 0 && dpgo_b200_should_terminate(agents[i]) == 1) H->term.store(s + 1);
       }
-      shm_barrier(H, N);
-      if (H->err.load()) return;
+      // no barrier at the end of a step (mailboxes and statuses are double-buffered by the step's parity; see the
+      // in-process driver below).  An error does not end the loop early: without that barrier the threads would not
+      // agree on the step at which to leave; the calls of a failed agent return at once, and the code is reported
     }
+    shm_barrier(H, N);   // the call ends together: the next call restarts the parity at 0
   };
   const auto t0 = std::chrono::high_resolution_clock::now();
   std::vector<std::thread> th;
@@ -310,8 +321,8 @@ extern "C" int dpgo_b200_sync_driver_run(dpgo_b200_agent_t *agents, int N, int s
       }
       // no barrier here: the next step's first one orders this step's deliveries in front of everything that depends
       // on them (a robot iterates and delivers to itself on its own thread; messages are double-buffered; a status
-      // is posted again only behind two barriers of the next step)
-      if (err.load()) return;
+      // is posted again only behind two barriers of the next step).  An error does not end the loop early -- the
+      // threads would not agree on the step at which to leave -- it is reported when the call returns.
     }
   };
 
