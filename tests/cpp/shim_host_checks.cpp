@@ -29,6 +29,30 @@ int main(int argc, char **argv) {
   CHECK(std::fabs((M - M).norm()) == 0.0);
   const Matrix P = M * M.transpose();
   CHECK(P.rows() == 2 && P(0, 0) == 14 && P(0, 1) == 32 && P(1, 1) == 77);
+  {
+    // storage: <= 32 coefficients live inside the object, larger matrices on the heap; copies, moves, swaps and
+    // assignments across the two regimes keep values and shapes (round 2's small-buffer Matrix)
+    Matrix small(5, 4), big(9, 9);
+    for (size_t i = 0; i < small.size(); ++i) small.data()[i] = 1.0 + i;
+    for (size_t i = 0; i < big.size(); ++i) big.data()[i] = 100.0 + i;
+    Matrix c1 = small, c2 = big;
+    CHECK(c1.data() != small.data() && c2.data() != big.data() && c1(4, 3) == 20 && c2(8, 8) == 180);
+    Matrix m1 = std::move(c1), m2 = std::move(c2);
+    CHECK(m1.rows() == 5 && m1(0, 1) == 6 && m2.cols() == 9 && m2(1, 0) == 101);
+    m1 = big;      // inline -> heap
+    m2 = small;    // heap -> inline
+    CHECK(m1.rows() == 9 && m1(8, 8) == 180 && m2.rows() == 5 && m2(4, 3) == 20);
+    m1 = m1;       // self-assignment
+    CHECK(m1(8, 8) == 180 && (m1 - big).norm() == 0.0 && (m2 - small).norm() == 0.0);
+    std::vector<Matrix> v(3, small);
+    v.push_back(big);
+    v.insert(v.begin(), big);
+    CHECK(v.front()(8, 8) == 180 && v[1](4, 3) == 20 && v.back()(0, 0) == 100);
+    Matrix edge(8, 4);   // exactly 32 coefficients: the largest inline shape (r = 8)
+    edge(7, 3) = 3.5;
+    const Matrix ecopy = edge;
+    CHECK(ecopy(7, 3) == 3.5 && ecopy(0, 0) == 0.0);
+  }
   Matrix B = Matrix::Zero(3, 4);
   B.block(0, 0, 3, 3) = Matrix::Identity(3, 3);
   Matrix tcol(3, 1);
