@@ -22,6 +22,7 @@
 // per diagonal block and per row of the triangular inverse) spent 86 % of its
 // time in those serial kernels (profiles/launches_r2_summary.csv).
 #include <atomic>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -361,7 +362,8 @@ static cudaError_t gemm_launch(const GemmArgs &g, cudaStream_t s) {
   // triangular operands the heaviest tile carries twice the average work: they are used once a GPU-full of them is a
   // small part of the product (the longest tile then stays below the per-SM share)
   const long tiles128 = (long)((g.M + 127) / 128) * ((g.N + 127) / 128) / (g.lower_only ? 2 : 1);
-  if (tiles128 >= 4 * 148) return gemm_launch_t<2, 2, AK, BK>(g, s);
+  static const long big_from = getenv("DPGO_B200_GEMM_BIG_TILES") ? atol(getenv("DPGO_B200_GEMM_BIG_TILES")) : 4 * 148;  // (diagnostics)
+  if (tiles128 >= big_from) return gemm_launch_t<2, 2, AK, BK>(g, s);
   return gemm_launch_t<1, 1, AK, BK>(g, s);
 }
 

@@ -1,7 +1,2 @@
-mkdir -p gpurun_out/c48
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/c48/bench_n4_s20.json 2> gpurun_out/c48/bench_n4_s20.err; echo "bench n4 rc=$?"
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/c48/bench_n4_s20.json").read().strip().splitlines()[-1])
-print({k: d.get(k) for k in ("value", "ms_per_step", "n_gpus", "bit_identical_to_single_team")}, "e2e", d["e2e"]["value"], d["e2e"].get("final_cost_2f"), "async", d.get("async_mode", {}).get("ticks_per_s"))
-PY
+mkdir -p gpurun_out/c49
+for t in 74 148 296 592 100000; do echo "== big tiles from $t"; DPGO_B200_GEMM_BIG_TILES=$t ./tools/check_dense_inverse 2016 2528 5024 10016 | grep "N="; done 2>&1 | tee gpurun_out/c49/tile_policy.txt
